@@ -1,0 +1,209 @@
+/*
+ * oak_b200.h -- C ABI of the B200-native OAK Gram / SGPR-statistics / Sobol hot path.
+ *
+ * Drop-in boundary for the reference's gpflow-Kernel-shaped Python API
+ * (amzn/orthogonal-additive-gaussian-processes).  Each entry point names the reference
+ * interface it replaces (file:line relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 on success, non-zero on
+ *     failure; oak_last_error() returns a thread-local message for the last failure.
+ *   - all array arguments named d_* are DEVICE pointers owned by the caller; h_* are HOST
+ *     pointers.  `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - matrices are row-major FP64; `ld*` is the row stride in elements.
+ *   - nothing is allocated behind the caller's back except inside oak_spec_create()
+ *     (a few KB of parameters) and the per-process cuBLAS / cuSOLVER handles.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef OAK_B200_H
+#define OAK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OAK_MAX_DEPTH 16 /* max_interaction_depth supported by the register-tiled kernels */
+
+/* per-dimension sub-kernel kinds (oak/oak_kernel.py:128-189 picks one per input dim) */
+enum {
+  OAK_DIM_RBF = 0,         /* OrthogonalRBFKernel        oak/ortho_rbf_kernel.py:20-177      */
+  OAK_DIM_BINARY = 1,      /* OrthogonalBinary           oak/ortho_binary_kernel.py:13-59    */
+  OAK_DIM_CATEGORICAL = 2  /* OrthogonalCategorical      oak/ortho_categorical_kernel.py:14-74 */
+};
+
+/* input measures (oak/input_measures.py:16-78); NONE = unconstrained RBF
+ * (constrain_orthogonal=False, oak/oak_kernel.py:191-210) */
+enum {
+  OAK_MEASURE_NONE = 0,
+  OAK_MEASURE_GAUSSIAN = 1,
+  OAK_MEASURE_UNIFORM = 2,
+  OAK_MEASURE_EMPIRICAL = 3,
+  OAK_MEASURE_MOG = 4
+};
+
+/* how e_n is formed from the per-dimension kernels */
+enum {
+  OAK_ESP_NEWTON_GIRARD = 0, /* power sums + Newton-Girard, oak/oak_kernel.py:236-249 (default) */
+  OAK_ESP_DIRECT = 1         /* e_n += k_d * e_{n-1}; same polynomial, better conditioned       */
+};
+
+/* One input dimension.  All pointers are HOST pointers, read during oak_spec_create(). */
+typedef struct oak_dim_desc {
+  int32_t type;     /* OAK_DIM_*                                                        */
+  int32_t column;   /* column of X this sub-kernel acts on (active_dims, oak_kernel.py:75-76) */
+  int32_t measure;  /* OAK_MEASURE_* (RBF only)                                         */
+  int32_t count;    /* #locations (EMPIRICAL) / #components (MOG) / #categories (CATEGORICAL) */
+  int32_t rank;     /* CATEGORICAL: columns of W (ortho_categorical_kernel.py:22)       */
+  int32_t reserved;
+  double lengthscale; /* RBF base_kernel.lengthscales                                   */
+  double variance;    /* RBF base_kernel.variance, or the discrete kernel's .variance   */
+  double m0;          /* GAUSSIAN: mu       UNIFORM: a       BINARY: p0                 */
+  double m1;          /* GAUSSIAN: var      UNIFORM: b                                  */
+  const double* v0;   /* EMPIRICAL: location[count]  MOG: means[count]      CATEGORICAL: W[count*rank] row-major */
+  const double* v1;   /* EMPIRICAL: weights[count]   MOG: variances[count]  CATEGORICAL: kappa[count]            */
+  const double* v2;   /*                             MOG: weights[count]    CATEGORICAL: p[count]                */
+} oak_dim_desc;
+
+/* The composite kernel: replaces the state held by OAKKernel (oak/oak_kernel.py:59-221). */
+typedef struct oak_kernel_desc {
+  int32_t num_dims;                /* number of sub-kernels                                   */
+  int32_t depth;                   /* max_interaction_depth                                   */
+  int32_t share_var_across_orders; /* oak_kernel.py:212-221                                   */
+  int32_t esp_algorithm;           /* OAK_ESP_*                                               */
+  const double* variances;         /* HOST: sigma^2_0..depth (share_var) or sigma^2_0 only    */
+  const oak_dim_desc* dims;        /* HOST: num_dims entries                                  */
+} oak_kernel_desc;
+
+typedef struct oak_spec oak_spec; /* opaque, device-resident parameter block */
+
+/* ---- housekeeping ------------------------------------------------------------------ */
+const char* oak_last_error(void);
+int oak_version(void);
+/* number of CUDA devices visible (0 => every compute call fails loudly) */
+int oak_device_count(void);
+
+/* Packs the hyper-parameters once per evaluation (they are gpflow Parameters read at call
+ * time in the reference, oak_kernel.py:251-265).  Computes var_s() for every constrained
+ * RBF dim (ortho_rbf_kernel.py:65-78, 94-97, 109-120, 138-152) and the B tables of the
+ * discrete dims (ortho_binary_kernel.py:29-38, ortho_categorical_kernel.py:34-53). */
+int oak_spec_create(const oak_kernel_desc* desc, void* stream, oak_spec** out);
+int oak_spec_destroy(oak_spec* spec);
+/* var_s() of constrained RBF sub-kernel `dim` (the closure at ortho_rbf_kernel.py:154-155);
+ * synchronises the stream. */
+int oak_spec_var_s_f64(const oak_spec* spec, int32_t dim, double* h_var_s, void* stream);
+
+/* ---- per-point prologue ------------------------------------------------------------ */
+/* Bytes of the prepared-point block for n points (feature-major, padded). */
+size_t oak_points_bytes(const oak_spec* spec, int64_t n);
+/* X: (n x ldx) row-major device matrix.  Writes, per dim and point, the scaled coordinate
+ * x/(sqrt(2) l) and the normalised correction cov_X_s(x)/sqrt(var_s())
+ * (ortho_rbf_kernel.py:47-152, 163-167), or the int32 category index
+ * (ortho_binary_kernel.py:47-51). */
+int oak_prepare_points_f64(const oak_spec* spec, const double* d_X, int64_t n, int64_t ldx,
+                           void* d_points, void* stream);
+
+/* ---- Gram / cross-covariance ------------------------------------------------------- */
+/* Replaces OAKKernel.K(X, X2) (oak_kernel.py:251-265) incl. compute_additive_terms
+ * (:223-249) and every sub-kernel K (ortho_rbf_kernel.py:157-172,
+ * ortho_binary_kernel.py:40-53, ortho_categorical_kernel.py:55-68).
+ * Computes rows [row_begin,row_end) of K(X, X2) into d_K[(i-row_begin)*ldk + j].
+ * d_points2 == NULL means X2 = X (symmetric; with row range == [0,n) only the lower
+ * triangle of tiles is evaluated and mirrored). */
+int oak_gram_f64(const oak_spec* spec, const void* d_points, int64_t n, const void* d_points2,
+                 int64_t n2, int64_t row_begin, int64_t row_end, double* d_K, int64_t ldk,
+                 void* stream);
+
+/* Replaces OAKKernel.K_diag(X) (oak_kernel.py:267-278). d_out[n]. */
+int oak_gram_diag_f64(const oak_spec* spec, const void* d_points, int64_t n, double* d_out,
+                      void* stream);
+
+/* Replaces KernelComponenent.K (oak_kernel.py:300-322): sigma^2_|S| * prod_{d in S} k_d.
+ * h_subset: `order` indices into the spec's dims (order may be 0: constant term). */
+int oak_component_gram_f64(const oak_spec* spec, const int32_t* h_subset, int32_t order,
+                           const void* d_points, int64_t n, const void* d_points2, int64_t n2,
+                           double* d_K, int64_t ldk, void* stream);
+
+/* Replaces KernelComponenent.K_diag (oak_kernel.py:324-335). d_out[n]. */
+int oak_component_diag_f64(const oak_spec* spec, const int32_t* h_subset, int32_t order,
+                           const void* d_points, int64_t n, double* d_out, void* stream);
+
+/* Replaces OAKKernel.compute_additive_terms on explicit arrays (oak_kernel.py:223-249):
+ * d_mats is (num_mats x len), d_out is ((depth+1) x len) = e_0..e_depth, element-wise. */
+int oak_additive_terms_f64(const double* d_mats, int32_t num_mats, int32_t depth, int64_t len,
+                           double* d_out, void* stream);
+
+/* Fused per-component prediction (oak/utils.py:491-530 get_prediction_component):
+ * out[c*n + i] = sigma^2_|S_c| * sum_j prod_{d in S_c} k_d(x_i, z_j) * alpha[j], for a batch
+ * of components; d_subsets is (num_components x max_order) int32, padded with -1. */
+int oak_component_predict_f64(const oak_spec* spec, const int32_t* d_subsets,
+                              int32_t num_components, int32_t max_order, const void* d_points,
+                              int64_t n, const void* d_points_cond, int64_t m,
+                              const double* d_alpha, double* d_out, void* stream);
+
+/* Host-buffer convenience (the reference-facing call: NumPy in, NumPy out).  Copies X (and
+ * X2) to the device, runs prepare + gram in row blocks and streams K back, overlapping the
+ * D2H copies with compute.  h_X2 == NULL => X2 = X. d_work must hold oak_gram_host_work_bytes. */
+size_t oak_gram_host_work_bytes(const oak_spec* spec, int64_t n, int64_t n2, int64_t ldx,
+                                int64_t block_rows);
+int oak_gram_host_f64(const oak_spec* spec, const double* h_X, int64_t n, const double* h_X2,
+                      int64_t n2, int64_t ldx, double* h_K, int64_t ldk, int64_t block_rows,
+                      void* d_work, void* stream);
+
+/* ---- SGPR statistics --------------------------------------------------------------- */
+/* Layout of the packed statistics vector (doubles): Phi[M*M] | Kuf_y[M] | sum_kdiag | yty.
+ * This is the single buffer all-reduced (sum) across ranks. */
+size_t oak_sgpr_stats_count(int64_t m);
+size_t oak_sgpr_stats_work_bytes(int64_t m, int64_t chunk);
+/* Replaces the Kuf build + A A^T contraction of SGPR.elbo / get_model_sufficient_statistics
+ * (oak/utils.py:180-191; gpflow Kuf at utils.py:184).  Streams the local n points in chunks:
+ * Kuf chunk (M x chunk, L2 resident) -> Phi += Kuf Kuf^T (cuBLAS DSYRK), Kuf_y += Kuf y,
+ * sum_kdiag += sum K_diag(X), yty += y^T y.  Accumulates INTO d_stats (caller zeroes it). */
+int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
+                       const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
+                       double* d_stats, void* d_work, void* stream);
+
+/* M^3 tail of SGPR.elbo (gpflow 2.2.1; re-derived at oak/utils.py:187-198): Cholesky of
+ * Kuu + jitter I, whitening of Phi, Cholesky of B, c, the bound and alpha = L^-T LB^-T c.
+ * d_Kuu (M x M) and d_stats are overwritten.  d_out: [elbo, logdetB_half, trace_AAT, c^T c];
+ * d_alpha[M] may be NULL. */
+size_t oak_sgpr_finish_work_bytes(int64_t m);
+int oak_sgpr_finish_f64(double* d_Kuu, double* d_stats, int64_t m, int64_t n_total, double noise,
+                        double jitter, double* d_out, double* d_alpha, void* d_work,
+                        void* stream);
+
+/* GPR: log N(y; 0, K + noise I) and alpha = (K + noise I)^-1 y (oak/utils.py:206-211;
+ * gpflow GPR.log_marginal_likelihood).  d_K (n x n) is overwritten by its Cholesky factor. */
+size_t oak_gpr_finish_work_bytes(int64_t n);
+int oak_gpr_finish_f64(double* d_K, const double* d_y, int64_t n, double noise, double* d_lml,
+                       double* d_alpha, void* d_work, void* stream);
+
+/* ---- Sobol indices ------------------------------------------------------------------ */
+/* Replaces compute_L / compute_L_binary_kernel / compute_L_categorical_kernel /
+ * compute_L_empirical_measure (oak/utils.py:221-335): the m x m matrix L_d for sub-kernel
+ * `dim` at the conditioning points (unit order-variance; the caller's variance enters in
+ * oak_sobol_quadforms_f64).  d_Xcond is the raw (m x ldx) conditioning matrix. */
+int oak_sobol_L_f64(const oak_spec* spec, int32_t dim, const double* d_Xcond, int64_t m,
+                    int64_t ldx, double delta, double mu, double* d_L, int64_t ldl,
+                    void* d_work, void* stream);
+size_t oak_sobol_L_work_bytes(const oak_spec* spec, int32_t dim, int64_t m);
+/* Replaces the component loop of compute_sobol_oak (oak/utils.py:369-432):
+ * out[c] = scale[c] * alpha^T (prod_{d in S_c} L_d) alpha.  d_Lstack: (num_dims x m x m). */
+int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
+                            const int32_t* d_subsets, const double* d_scale,
+                            int32_t num_components, int32_t max_order, const double* d_alpha,
+                            double* d_out, void* stream);
+
+/* ---- measurement helpers ----------------------------------------------------------- */
+/* Dependent-chain DFMA microbenchmark: writes achieved FP64 issue slots / second to
+ * *h_slots_per_s (1 slot = one DFMA = 2 flop).  This is the measured FP64 roofline peak. */
+int oak_measure_fp64_peak(double seconds, double* h_slots_per_s, void* stream);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t oak_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OAK_B200_H */

@@ -1,0 +1,285 @@
+"""Device plumbing between the host classes and the C ABI.
+
+PyTorch is used for device memory, streams and ``torch.distributed`` only; every arithmetic
+operation of the hot path happens inside ``liboak_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import OakNativeError, Spec, check
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise OakNativeError("torch sees no CUDA device: the OAK B200 kernels have no CPU fallback")
+    return torch
+
+
+def stream_ptr() -> int:
+    return int(_torch().cuda.current_stream().cuda_stream)
+
+
+def to_device(X, ndim: int = 2):
+    """NumPy / array-like / torch tensor -> contiguous float64 CUDA tensor."""
+    torch = _torch()
+    if isinstance(X, torch.Tensor):
+        t = X.to(device="cuda", dtype=torch.float64)
+    else:
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(X, dtype=np.float64))).to("cuda", non_blocking=False)
+    if ndim == 2 and t.ndim == 1:
+        t = t.reshape(-1, 1)
+    return t.contiguous()
+
+
+def is_host(X) -> bool:
+    try:
+        import torch
+
+        if isinstance(X, torch.Tensor):
+            return not X.is_cuda
+    except Exception:  # pragma: no cover
+        pass
+    return True
+
+
+def from_device(t, like_host: bool):
+    """Returns NumPy when the caller handed in host data, the CUDA tensor otherwise."""
+    return t.cpu().numpy() if like_host else t
+
+
+def _p(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class Points:
+    """Prepared-point block of ``n`` points for one spec (see csrc/oak_prepare.cu)."""
+
+    def __init__(self, spec: Spec, Xd):
+        torch = _torch()
+        self.n = int(Xd.shape[0])
+        self.spec = spec
+        nbytes = spec.points_bytes(self.n)
+        self.buf = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=Xd.device)
+        if self.n > 0:
+            check(
+                _cabi.load().oak_prepare_points_f64(
+                    spec.handle, _p(Xd), self.n, int(Xd.stride(0)), _p(self.buf), C.c_void_p(stream_ptr())
+                ),
+                "oak_prepare_points_f64",
+            )
+
+
+def validate_discrete(Xd, columns: Sequence[int], counts: Sequence[int]):
+    """``tf.gather`` on CPU raises for out-of-range indices; do the same before the table gather."""
+    for col, cnt in zip(columns, counts):
+        if Xd.shape[0] == 0:
+            continue
+        v = Xd[:, col].trunc()
+        lo, hi = float(v.min()), float(v.max())
+        if lo < 0 or hi > cnt - 1:
+            raise ValueError(f"column {col}: category index outside [0, {cnt - 1}] (got [{lo}, {hi}])")
+
+
+def gram(spec: Spec, px: Points, px2: Optional[Points] = None, row_begin: int = 0,
+         row_end: Optional[int] = None, out=None):
+    torch = _torch()
+    n = px.n
+    n2 = n if px2 is None else px2.n
+    row_end = n if row_end is None else row_end
+    rows = row_end - row_begin
+    if out is None:
+        out = torch.empty((rows, n2), dtype=torch.float64, device=px.buf.device)
+    if rows > 0 and n2 > 0:
+        check(
+            _cabi.load().oak_gram_f64(
+                spec.handle, _p(px.buf), n, _p(None if px2 is None else px2.buf), n2, row_begin, row_end,
+                _p(out), int(out.stride(0)), C.c_void_p(stream_ptr()),
+            ),
+            "oak_gram_f64",
+        )
+    return out
+
+
+def gram_diag(spec: Spec, px: Points):
+    torch = _torch()
+    out = torch.empty((px.n,), dtype=torch.float64, device=px.buf.device)
+    if px.n > 0:
+        check(
+            _cabi.load().oak_gram_diag_f64(spec.handle, _p(px.buf), px.n, _p(out), C.c_void_p(stream_ptr())),
+            "oak_gram_diag_f64",
+        )
+    return out
+
+
+def component_gram(spec: Spec, subset: Sequence[int], px: Points, px2: Optional[Points] = None):
+    torch = _torch()
+    n = px.n
+    n2 = n if px2 is None else px2.n
+    out = torch.empty((n, n2), dtype=torch.float64, device=px.buf.device)
+    arr = (C.c_int32 * max(len(subset), 1))(*[int(s) for s in subset])
+    if n > 0 and n2 > 0:
+        check(
+            _cabi.load().oak_component_gram_f64(
+                spec.handle, arr, len(subset), _p(px.buf), n, _p(None if px2 is None else px2.buf), n2,
+                _p(out), int(out.stride(0)), C.c_void_p(stream_ptr()),
+            ),
+            "oak_component_gram_f64",
+        )
+    return out
+
+
+def component_diag(spec: Spec, subset: Sequence[int], px: Points):
+    torch = _torch()
+    out = torch.empty((px.n,), dtype=torch.float64, device=px.buf.device)
+    arr = (C.c_int32 * max(len(subset), 1))(*[int(s) for s in subset])
+    if px.n > 0:
+        check(
+            _cabi.load().oak_component_diag_f64(spec.handle, arr, len(subset), _p(px.buf), px.n, _p(out),
+                                                C.c_void_p(stream_ptr())),
+            "oak_component_diag_f64",
+        )
+    return out
+
+
+def additive_terms(mats, depth: int):
+    """e_0..e_depth of a stack of equally shaped arrays (num_mats, ...) -> (depth+1, ...)."""
+    torch = _torch()
+    m = mats.contiguous()
+    num = int(m.shape[0])
+    length = int(m[0].numel())
+    out = torch.empty((depth + 1,) + tuple(m.shape[1:]), dtype=torch.float64, device=m.device)
+    check(
+        _cabi.load().oak_additive_terms_f64(_p(m), num, int(depth), length, _p(out), C.c_void_p(stream_ptr())),
+        "oak_additive_terms_f64",
+    )
+    return out
+
+
+def component_predict(spec: Spec, subsets: Sequence[Sequence[int]], px: Points, pcond: Points, alpha):
+    """out[c, i] = sigma^2_|S_c| sum_j prod_{d in S_c} k_d(x_i, z_j) alpha_j."""
+    torch = _torch()
+    nc = len(subsets)
+    max_order = max([len(s) for s in subsets] + [1])
+    tab = np.full((nc, max_order), -1, dtype=np.int32)
+    for c, s in enumerate(subsets):
+        tab[c, : len(s)] = s
+    d_tab = torch.as_tensor(tab).to(px.buf.device)
+    out = torch.empty((nc, px.n), dtype=torch.float64, device=px.buf.device)
+    a = alpha.reshape(-1).contiguous()
+    if nc > 0 and px.n > 0:
+        check(
+            _cabi.load().oak_component_predict_f64(
+                spec.handle, _p(d_tab), nc, max_order, _p(px.buf), px.n, _p(pcond.buf), pcond.n, _p(a),
+                _p(out), C.c_void_p(stream_ptr()),
+            ),
+            "oak_component_predict_f64",
+        )
+    return out
+
+
+# ---- SGPR / GPR -------------------------------------------------------------------------
+def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 8192, stats=None):
+    """Accumulates Phi | Kuf y | sum K_diag | y^T y for the local points into ``stats``."""
+    torch = _torch()
+    lib = _cabi.load()
+    m = pz.n
+    count = int(lib.oak_sgpr_stats_count(m))
+    if stats is None:
+        stats = torch.zeros(count, dtype=torch.float64, device=pz.buf.device)
+    chunk = int(max(64, min(chunk, max(px.n, 64))))
+    chunk = (chunk + 63) // 64 * 64
+    work = torch.empty(max(int(lib.oak_sgpr_stats_work_bytes(m, chunk)) // 8, 1), dtype=torch.float64,
+                       device=pz.buf.device)
+    yv = y.reshape(-1).contiguous()
+    check(
+        lib.oak_sgpr_stats_f64(spec.handle, _p(pz.buf), m, _p(px.buf), _p(yv), px.n, chunk, _p(stats),
+                               _p(work), C.c_void_p(stream_ptr())),
+        "oak_sgpr_stats_f64",
+    )
+    return stats
+
+
+def sgpr_finish(Kuu, stats, n_total: int, noise: float, jitter: float, want_alpha=True):
+    """Returns (out[4] = elbo, sum log diag LB, tr(AAT), c^T c ; alpha[M] or None). Overwrites inputs."""
+    torch = _torch()
+    lib = _cabi.load()
+    m = int(Kuu.shape[0])
+    out = torch.empty(4, dtype=torch.float64, device=Kuu.device)
+    alpha = torch.empty(m, dtype=torch.float64, device=Kuu.device) if want_alpha else None
+    work = torch.empty(max(int(lib.oak_sgpr_finish_work_bytes(m)) // 8, 1), dtype=torch.float64, device=Kuu.device)
+    check(
+        lib.oak_sgpr_finish_f64(_p(Kuu), _p(stats), m, int(n_total), float(noise), float(jitter), _p(out),
+                                _p(alpha), _p(work), C.c_void_p(stream_ptr())),
+        "oak_sgpr_finish_f64",
+    )
+    return out, alpha
+
+
+def gpr_finish(K, y, noise: float):
+    """Returns (lml tensor[1], alpha[n]); K is overwritten by its Cholesky factor."""
+    torch = _torch()
+    lib = _cabi.load()
+    n = int(K.shape[0])
+    lml = torch.empty(1, dtype=torch.float64, device=K.device)
+    alpha = torch.empty(n, dtype=torch.float64, device=K.device)
+    work = torch.empty(max(int(lib.oak_gpr_finish_work_bytes(n)) // 8, 1), dtype=torch.float64, device=K.device)
+    yv = y.reshape(-1).contiguous()
+    check(
+        lib.oak_gpr_finish_f64(_p(K), _p(yv), n, float(noise), _p(lml), _p(alpha), _p(work),
+                               C.c_void_p(stream_ptr())),
+        "oak_gpr_finish_f64",
+    )
+    return lml, alpha
+
+
+# ---- Sobol ------------------------------------------------------------------------------
+def sobol_L(spec: Spec, dim: int, Xcond, delta: float, mu: float, out=None):
+    torch = _torch()
+    lib = _cabi.load()
+    m = int(Xcond.shape[0])
+    if out is None:
+        out = torch.empty((m, m), dtype=torch.float64, device=Xcond.device)
+    work = torch.empty(max(int(lib.oak_sobol_L_work_bytes(spec.handle, dim, m)) // 8, 1), dtype=torch.float64,
+                       device=Xcond.device)
+    check(
+        lib.oak_sobol_L_f64(spec.handle, int(dim), _p(Xcond), m, int(Xcond.stride(0)), float(delta), float(mu),
+                            _p(out), int(out.stride(0)), _p(work), C.c_void_p(stream_ptr())),
+        "oak_sobol_L_f64",
+    )
+    return out
+
+
+def sobol_quadforms(Lstack, subsets: Sequence[Sequence[int]], scale: Sequence[float], alpha):
+    torch = _torch()
+    nc = len(subsets)
+    max_order = max([len(s) for s in subsets] + [1])
+    tab = np.full((nc, max_order), -1, dtype=np.int32)
+    for c, s in enumerate(subsets):
+        tab[c, : len(s)] = s
+    dev = Lstack.device
+    d_tab = torch.as_tensor(tab).to(dev)
+    d_scale = torch.as_tensor(np.asarray(scale, dtype=np.float64)).to(dev)
+    out = torch.empty(nc, dtype=torch.float64, device=dev)
+    a = alpha.reshape(-1).contiguous()
+    check(
+        _cabi.load().oak_sobol_quadforms_f64(_p(Lstack), int(Lstack.shape[0]), int(Lstack.shape[1]), _p(d_tab),
+                                             _p(d_scale), nc, max_order, _p(a), _p(out),
+                                             C.c_void_p(stream_ptr())),
+        "oak_sobol_quadforms_f64",
+    )
+    return out
+
+
+def measure_fp64_peak(seconds: float = 1.0) -> float:
+    _torch()
+    v = C.c_double(0.0)
+    check(_cabi.load().oak_measure_fp64_peak(float(seconds), C.byref(v), C.c_void_p(stream_ptr())),
+          "oak_measure_fp64_peak")
+    return float(v.value)

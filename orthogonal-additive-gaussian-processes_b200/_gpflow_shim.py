@@ -1,0 +1,272 @@
+"""Minimal stand-in for the parts of the gpflow 2.2.1 object model the OAK hot path touches
+(``Parameter`` with positive / sigmoid transforms, ``Kernel.__call__`` / ``slice`` /
+``active_dims``, parameter discovery).  gpflow / TensorFlow are not installable next to this
+package; when a maintainer wires the kernels into real gpflow, only this file is replaced
+(see INTEGRATION.md).  Host-side bookkeeping only -- no kernel arithmetic lives here.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
+DEFAULT_POSITIVE_MINIMUM = 1e-6  # gpflow.config.default_positive_minimum()
+
+
+def default_float():
+    return np.float64
+
+
+def default_jitter() -> float:
+    return DEFAULT_JITTER
+
+
+# ---- transforms -------------------------------------------------------------------------
+class Identity:
+    def forward(self, u):
+        return u
+
+    def inverse(self, v):
+        return v
+
+
+class Softplus:
+    """``gpflow.utilities.positive()``: softplus shifted by the positive minimum."""
+
+    def __init__(self, lower: float = DEFAULT_POSITIVE_MINIMUM):
+        self.lower = lower
+
+    def forward(self, u):
+        return np.logaddexp(0.0, u) + self.lower
+
+    def inverse(self, v):
+        y = np.asarray(v, dtype=np.float64) - self.lower
+        return y + np.log(-np.expm1(-y))
+
+
+class Sigmoid:
+    """``tfp.bijectors.Sigmoid(low, high)`` as used by ``bounded_param`` (oak/oak_kernel.py:24-33)."""
+
+    def __init__(self, low: float, high: float):
+        self.low, self.high = float(low), float(high)
+
+    def forward(self, u):
+        return self.low + (self.high - self.low) / (1.0 + np.exp(-np.asarray(u, dtype=np.float64)))
+
+    def inverse(self, v):
+        y = (np.asarray(v, dtype=np.float64) - self.low) / (self.high - self.low)
+        return np.log(y) - np.log1p(-y)
+
+
+def positive(lower: Optional[float] = None):
+    return Softplus(DEFAULT_POSITIVE_MINIMUM if lower is None else lower)
+
+
+class Parameter:
+    """Constrained parameter holding its unconstrained representation (gpflow.Parameter)."""
+
+    def __init__(self, value, transform=None, trainable: bool = True, prior=None, dtype=np.float64, name=None):
+        if isinstance(value, Parameter):
+            value = value.numpy()
+        self.transform = transform if transform is not None else Identity()
+        self.trainable = trainable
+        self.prior = prior
+        self.name = name
+        self._u = np.asarray(self.transform.inverse(np.asarray(value, dtype=np.float64)), dtype=np.float64)
+
+    # gpflow API subset
+    def numpy(self):
+        return np.asarray(self.transform.forward(self._u), dtype=np.float64)
+
+    def assign(self, value):
+        self._u = np.asarray(self.transform.inverse(np.asarray(value, dtype=np.float64)), dtype=np.float64)
+        return self
+
+    @property
+    def unconstrained_variable(self):
+        return self._u
+
+    @unconstrained_variable.setter
+    def unconstrained_variable(self, u):
+        self._u = np.asarray(u, dtype=np.float64)
+
+    @property
+    def shape(self):
+        return self.numpy().shape
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def __float__(self):
+        return float(np.squeeze(self.numpy()))
+
+    def __repr__(self):
+        return f"Parameter({self.numpy()!r}, trainable={self.trainable})"
+
+    # arithmetic delegates to the constrained value
+    def __mul__(self, o):
+        return self.numpy() * np.asarray(o)
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        return self.numpy() + np.asarray(o)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        return self.numpy() - np.asarray(o)
+
+    def __rsub__(self, o):
+        return np.asarray(o) - self.numpy()
+
+    def __truediv__(self, o):
+        return self.numpy() / np.asarray(o)
+
+    def __rtruediv__(self, o):
+        return np.asarray(o) / self.numpy()
+
+    def __pow__(self, o):
+        return self.numpy() ** o
+
+    def __neg__(self):
+        return -self.numpy()
+
+
+def value_of(p) -> np.ndarray:
+    """Constrained value of a Parameter / constant tensor / python scalar as float64 ndarray."""
+    if isinstance(p, Parameter):
+        return p.numpy()
+    if hasattr(p, "detach"):
+        return p.detach().cpu().numpy().astype(np.float64)
+    return np.asarray(p, dtype=np.float64)
+
+
+def scalar_of(p) -> float:
+    return float(np.squeeze(value_of(p)))
+
+
+def set_trainable(obj, flag: bool):
+    for p in collect_parameters(obj):
+        p.trainable = flag
+
+
+def collect_parameters(obj, _seen=None) -> List[Parameter]:
+    """Depth-first parameter discovery over attributes, lists and tuples (tf.Module-like)."""
+    if _seen is None:
+        _seen = set()
+    out: List[Parameter] = []
+    if id(obj) in _seen:
+        return out
+    _seen.add(id(obj))
+    if isinstance(obj, Parameter):
+        return [obj]
+    if isinstance(obj, (list, tuple)):
+        for o in obj:
+            out += collect_parameters(o, _seen)
+        return out
+    if isinstance(obj, Module):
+        for key in sorted(vars(obj)):
+            if key.startswith("_"):
+                continue
+            out += collect_parameters(getattr(obj, key), _seen)
+    return out
+
+
+class Module:
+    @property
+    def parameters(self):
+        return tuple(collect_parameters(self))
+
+    @property
+    def trainable_parameters(self):
+        return tuple(p for p in collect_parameters(self) if p.trainable)
+
+
+class Kernel(Module):
+    """``gpflow.kernels.Kernel`` protocol: ``active_dims``, ``slice``, ``__call__``."""
+
+    def __init__(self, active_dims=None, name=None):
+        self._active_dims = self._normalize_active_dims(active_dims)
+        self.name = name
+
+    @staticmethod
+    def _normalize_active_dims(value):
+        if value is None:
+            value = slice(None, None, None)
+        if isinstance(value, range):
+            value = list(value)
+        if not isinstance(value, slice):
+            value = np.array(value, dtype=int).reshape(-1)
+        return value
+
+    @property
+    def active_dims(self):
+        return self._active_dims
+
+    @active_dims.setter
+    def active_dims(self, value):
+        self._active_dims = self._normalize_active_dims(value)
+
+    def slice(self, X, X2=None):
+        dims = self.active_dims
+        if isinstance(dims, slice):
+            X = X[..., dims]
+            if X2 is not None:
+                X2 = X2[..., dims]
+        else:
+            idx = dims.tolist() if isinstance(dims, np.ndarray) else dims
+            X = X[..., idx]
+            if X2 is not None:
+                X2 = X2[..., idx]
+        return X, X2
+
+    def K(self, X, X2=None):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def K_diag(self, X):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def __call__(self, X, X2=None, *, full_cov: bool = True, presliced: bool = False):
+        if (not full_cov) and (X2 is not None):
+            raise ValueError("Ambiguous inputs: `not full_cov` and `X2` are not compatible.")
+        if not presliced:
+            X, X2 = self.slice(X, X2)
+        if not full_cov:
+            return self.K_diag(X)
+        return self.K(X, X2)
+
+
+class InducingPoints(Module):
+    def __init__(self, Z):
+        self.Z = Parameter(np.asarray(Z, dtype=np.float64))
+
+    @property
+    def num_inducing(self):
+        return self.Z.numpy().shape[0]
+
+    def __len__(self):
+        return self.num_inducing
+
+
+class Gaussian(Module):
+    """Gaussian likelihood: only the noise variance is needed on this path."""
+
+    def __init__(self, variance: float = 1.0):
+        self.variance = Parameter(variance, transform=positive())
+
+
+class Gamma:
+    """Prior placeholder for ``tfd.Gamma(concentration, rate)`` (oak/model_utils.py:163-165)."""
+
+    def __init__(self, concentration: float, rate: float):
+        self.concentration, self.rate = float(concentration), float(rate)
+
+    def log_prob(self, x):
+        from math import lgamma
+
+        x = np.asarray(x, dtype=np.float64)
+        a, b = self.concentration, self.rate
+        return a * np.log(b) - lgamma(a) + (a - 1.0) * np.log(x) - b * x

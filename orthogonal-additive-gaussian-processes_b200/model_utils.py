@@ -1,0 +1,284 @@
+"""Model factory and the ``oak_model`` convenience API.
+
+Drop-in for the hot-path entry points of the reference's ``oak/model_utils.py``:
+``create_model_oak`` (:90-176) and ``oak_model.fit / predict / get_sobol`` (:194-524), with the same
+argument names, defaults and error behaviour.  Host-side preprocessing that the reference does with
+TFP normalising flows / sklearn (k-means inducing points, GMM fitting, plotting) is outside the
+hot path (out of scope); ``oak_model`` therefore supports
+``use_normalising_flow=False`` (standardised continuous inputs, :327-330) and takes inducing points
+from the data (``initialise_inducing_points=False``, :392-393) unless scikit-learn is present.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from . import _device
+from ._gpflow_shim import Gamma, InducingPoints, set_trainable
+from .input_measures import MOGMeasure
+from .models import GPR, SGPR
+from .oak_kernel import OAKKernel, get_list_representation
+from .ortho_rbf_kernel import RBF
+from .utils import compute_sobol_oak
+
+
+def create_model_oak(
+    data,
+    max_interaction_depth: int = 2,
+    constrain_orthogonal: bool = True,
+    inducing_pts: np.ndarray = None,
+    optimise=False,
+    zfixed=True,
+    p0=None,
+    p=None,
+    lengthscale_bounds=None,
+    empirical_locations: Optional[List[float]] = None,
+    empirical_weights: Optional[List[float]] = None,
+    use_sparsity_prior: bool = True,
+    gmm_measures: Optional[List[MOGMeasure]] = None,
+    share_var_across_orders: Optional[bool] = True,
+):
+    """GPR (or SGPR when ``inducing_pts`` is given) with an OAK kernel (model_utils.py:90-176)."""
+    num_dims = np.shape(data[0])[1]
+    if p0 is None:
+        p0 = [None] * num_dims
+    if p is None:
+        p = [None] * num_dims
+    base_kernels = [None] * num_dims
+    for dim in range(num_dims):
+        if (p0[dim] is None) and (p[dim] is None):
+            base_kernels[dim] = RBF
+
+    k = OAKKernel(
+        base_kernels,
+        num_dims=num_dims,
+        max_interaction_depth=max_interaction_depth,
+        constrain_orthogonal=constrain_orthogonal,
+        p0=p0,
+        p=p,
+        lengthscale_bounds=lengthscale_bounds,
+        empirical_locations=empirical_locations,
+        empirical_weights=empirical_weights,
+        gmm_measures=gmm_measures,
+        share_var_across_orders=share_var_across_orders,
+    )
+    if inducing_pts is not None:
+        model = SGPR(data, kernel=k, inducing_variable=InducingPoints(inducing_pts))
+        if zfixed:
+            set_trainable(model.inducing_variable, False)
+    else:
+        model = GPR(data, kernel=k)
+    if use_sparsity_prior and share_var_across_orders:
+        for prm in model.kernel.variances:  # Gamma(1, rate 0.2) prior (:163-165)
+            prm.prior = Gamma(1.0, 0.2)
+    # small initial noise to avoid the all-noise optimum (:167)
+    model.likelihood.variance.assign(0.01)
+    if optimise:
+        raise NotImplementedError(
+            "hyper-parameter optimisation needs kernel gradients (SURVEY.md section 8(f), next row 1)"
+        )
+    return model
+
+
+def _calculate_features(X, categorical_feature, binary_feature):
+    """Feature typing and discrete measures (model_utils.py:703-750): p0 = 1 - mean, p = frequencies."""
+    if binary_feature is None and categorical_feature is None:
+        return list(range(X.shape[1])), [], [], None, None
+    if binary_feature is not None and categorical_feature is not None:
+        overlap = set(binary_feature).intersection(categorical_feature)
+        if len(overlap) > 0:
+            raise ValueError(f"Overlapping feature set {overlap}")
+    binary_index, categorical_index, continuous_index, p0, p = [], [], [], [], []
+    for j in range(X.shape[1]):
+        if binary_feature is not None and j in binary_feature:
+            p0.append(1 - X[:, j].mean())
+            p.append(None)
+            binary_index.append(j)
+        elif categorical_feature is not None and j in categorical_feature:
+            p0.append(None)
+            vals, counts = np.unique(X[:, j], return_counts=True)
+            p.append((counts / len(X[:, j])).reshape(-1, 1))
+            assert np.abs(p[-1].sum() - 1) < 1e-6
+            categorical_index.append(j)
+        else:
+            p.append(None)
+            p0.append(None)
+            continuous_index.append(j)
+    return continuous_index, binary_index, categorical_index, p0, p
+
+
+class _Standardiser:
+    def fit(self, A):
+        self.mean_ = A.mean(0)
+        self.var_ = A.var(0)
+        self.scale_ = np.where(self.var_ > 0, np.sqrt(self.var_), 1.0)
+        return self
+
+    def transform(self, A):
+        return (A - self.mean_) / self.scale_
+
+    def inverse_transform(self, A):
+        return A * self.scale_ + self.mean_
+
+
+class oak_model:
+    """OAK model with fitting, prediction and attribution utilities (model_utils.py:194-524)."""
+
+    def __init__(
+        self,
+        max_interaction_depth=2,
+        num_inducing=200,
+        lengthscale_bounds=[1e-3, 1e3],
+        binary_feature: Optional[List[int]] = None,
+        categorical_feature: Optional[List[int]] = None,
+        empirical_measure: Optional[List[int]] = None,
+        use_sparsity_prior: bool = True,
+        gmm_measure: Optional[List[int]] = None,
+        sparse: bool = False,
+        use_normalising_flow: bool = True,
+        share_var_across_orders: bool = True,
+    ):
+        self.max_interaction_depth = max_interaction_depth
+        self.num_inducing = num_inducing
+        self.lengthscale_bounds = lengthscale_bounds
+        self.binary_feature = binary_feature
+        self.categorical_feature = categorical_feature
+        self.use_sparsity_prior = use_sparsity_prior
+        self.input_flows = None
+        self.scaler_y = None
+        self.Y_scaled = None
+        self.X_scaled = None
+        self.alpha = None
+        self.continuous_index = None
+        self.binary_index = None
+        self.categorical_index = None
+        self.empirical_measure = empirical_measure
+        self.empirical_locations = None
+        self.empirical_weights = None
+        self.gmm_measure = gmm_measure
+        self.estimated_gmm_measures = None
+        self.sparse = sparse
+        self.use_normalising_flow = use_normalising_flow
+        self.share_var_across_orders = share_var_across_orders
+
+    def fit(self, X, Y, optimise: bool = True, initialise_inducing_points: bool = True):
+        X = np.asarray(X, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64)
+        self.xmin, self.xmax = X.min(0), X.max(0)
+        self.num_dims = X.shape[1]
+        (self.continuous_index, self.binary_index, self.categorical_index, p0, p) = _calculate_features(
+            X, categorical_feature=self.categorical_feature, binary_feature=self.binary_feature
+        )
+        if self.empirical_measure is not None:
+            if not set(self.empirical_measure).issubset(self.continuous_index):
+                raise ValueError(
+                    f"Empirical measure={self.empirical_measure} should only be used on non-binary/categorical "
+                    f"inputs {self.continuous_index}"
+                )
+        if self.gmm_measure is not None:
+            if len(self.gmm_measure) != self.num_dims:
+                # the reference *returns* this error instead of raising it (:283); kept
+                return ValueError(f"Must specify number of components for each inputs dimension 1..{X.shape[0]}")
+            idx_gmm = np.flatnonzero(self.gmm_measure)
+            if not set(idx_gmm).issubset(self.continuous_index):
+                raise ValueError(
+                    f"GMM measure on inputs {idx_gmm} should only be used on continuous inputs {self.continuous_index}"
+                )
+            if len(idx_gmm) > 0:
+                raise NotImplementedError("GMM fitting (sklearn) is host preprocessing outside the hot path; "
+                                          "pass MOGMeasure objects to create_model_oak(gmm_measures=...)")
+        self.estimated_gmm_measures = [None] * self.num_dims
+        self.empirical_locations = [None] * self.num_dims
+        self.empirical_weights = [None] * self.num_dims
+        self.input_flows = [None] * self.num_dims
+        flow_dims = [i for i in self.continuous_index
+                     if not (self.empirical_measure is not None and i in self.empirical_measure)]
+        if self.use_normalising_flow and flow_dims:
+            raise NotImplementedError(
+                "normalising flows (TFP bijectors) are preprocessing outside the hot path "
+                "(SURVEY.md section 8(f), next row 3); construct oak_model(use_normalising_flow=False)"
+            )
+        self.alpha = None
+        self.scaler_y = _Standardiser().fit(Y)
+        self.Y_scaled = self.scaler_y.transform(Y)
+        if self.empirical_measure is not None:
+            self.scaler_X_empirical = _Standardiser().fit(X[:, self.empirical_measure])
+        if not self.use_normalising_flow:
+            self.scaler_X_continuous = _Standardiser().fit(X[:, self.continuous_index])
+        self.X_scaled = self._transform_x(X)
+
+        # empirical locations / weights from the scaled data (:334-344)
+        if self.empirical_measure is not None:
+            for ii in self.empirical_measure:
+                loc, cnt = np.unique(self.X_scaled[:, ii], return_counts=True)
+                self.empirical_weights[ii] = (cnt / cnt.sum()).reshape(-1, 1)
+                self.empirical_locations[ii] = loc.reshape(-1, 1)
+
+        Z = None
+        if X.shape[0] > 1000 or self.sparse:  # sparse GP switch (:373-374)
+            if initialise_inducing_points:
+                Z = self._kmeans_inducing(self.X_scaled, p0, p)
+            else:
+                Z = self.X_scaled[: self.num_inducing, :]
+        self.m = create_model_oak(
+            (self.X_scaled, self.Y_scaled),
+            max_interaction_depth=self.max_interaction_depth,
+            inducing_pts=Z,
+            optimise=optimise,
+            p0=p0,
+            p=p,
+            lengthscale_bounds=self.lengthscale_bounds,
+            use_sparsity_prior=self.use_sparsity_prior,
+            empirical_locations=self.empirical_locations,
+            empirical_weights=self.empirical_weights,
+            gmm_measures=self.estimated_gmm_measures,
+            share_var_across_orders=self.share_var_across_orders,
+        )
+
+    def _kmeans_inducing(self, Xs, p0, p):
+        """k-means inducing points (:377-391, utils.py:555-574): one-off host preprocessing."""
+        try:
+            from sklearn.cluster import KMeans
+        except Exception as exc:  # pragma: no cover
+            raise NotImplementedError("k-means initialisation needs scikit-learn; pass "
+                                      "initialise_inducing_points=False") from exc
+        if (p0 is None) and (p is None):
+            return KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs).cluster_centers_
+        Z = np.zeros([self.num_inducing, Xs.shape[1]])
+        for index in self.binary_index + self.categorical_index:
+            km = KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs[:, index][:, None])
+            Z[:, index] = km.cluster_centers_.astype(int)[:, 0]
+        km = KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs[:, self.continuous_index])
+        Z[:, self.continuous_index] = km.cluster_centers_
+        return Z
+
+    def _transform_x(self, X):
+        X = np.array(X, dtype=np.float64, copy=True)
+        if self.empirical_measure is not None:
+            X[:, self.empirical_measure] = self.scaler_X_empirical.transform(X[:, self.empirical_measure])
+        if not self.use_normalising_flow:
+            X[:, self.continuous_index] = self.scaler_X_continuous.transform(X[:, self.continuous_index])
+        return X
+
+    def predict(self, X, clip=False):
+        X = np.asarray(X, dtype=np.float64)
+        Xs = self._transform_x(np.clip(X, self.xmin, self.xmax)) if clip else self._transform_x(X)
+        y_pred = self.m.predict_f(Xs)[0]
+        return self.scaler_y.inverse_transform(np.asarray(y_pred))[:, 0]
+
+    def get_sobol(self, likelihood_variance=False):
+        """Normalised Sobol index of each additive term (:499-524)."""
+        delta, mu = 1, 0
+        selected_dims, _ = get_list_representation(self.m.kernel, num_dims=self.num_dims)
+        tuple_of_indices = selected_dims[1:]
+        model_indices, sobols = compute_sobol_oak(self.m, delta, mu,
+                                                  share_var_across_orders=self.share_var_across_orders)
+        sobols = np.asarray(sobols)
+        if likelihood_variance:
+            normalised = sobols / (np.sum(sobols) + float(self.m.likelihood.variance.numpy()))
+        else:
+            normalised = sobols / np.sum(sobols)
+        self.normalised_sobols = normalised
+        self.tuple_of_indices = tuple_of_indices
+        return normalised

@@ -1,0 +1,179 @@
+"""GPR / SGPR objectives on top of the fused OAK tiles.
+
+Stand-ins for the gpflow 2.2.1 model classes the reference instantiates
+(``oak/model_utils.py:149-159``): same attribute paths (``.data``, ``.kernel``,
+``.likelihood.variance``, ``.inducing_variable.Z``) and methods (``log_marginal_likelihood``,
+``elbo``, ``maximum_log_likelihood_objective``, ``training_loss``, ``predict_f``).  The Gram /
+Kuf tiles and the SGPR statistics run in ``liboak_b200.so``; the dense M^3 / N^3 tails go through
+cuSOLVER / cuBLAS inside the same library.  With ``torch.distributed`` initialised, each rank holds
+a shard of (X, y) and the packed statistics are combined by one all-reduce.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _device, parallel
+from ._gpflow_shim import (DEFAULT_JITTER, Gaussian, InducingPoints, Module, Parameter, collect_parameters,
+                           scalar_of, value_of)
+
+
+class GPModel(Module):
+    def __init__(self, data, kernel, mean_function=None, noise_variance: float = 1.0):
+        X, Y = data
+        self.data = (X, Y)
+        self.kernel = kernel
+        if mean_function is not None:
+            raise NotImplementedError("only the zero mean function is used by OAK (model_utils.py:152,159)")
+        self.mean_function = lambda X: 0.0
+        self.likelihood = Gaussian(noise_variance)
+        self._Xd = None
+        self._Yd = None
+
+    # ---- data on the device (moved once) --------------------------------------------------
+    def _device_data(self):
+        if self._Xd is None:
+            X, Y = self.data
+            self._Xd = _device.to_device(X)
+            self._Yd = _device.to_device(Y)
+            if self._Yd.shape[1] != 1:
+                raise NotImplementedError("single-output regression only (R = 1 on this path)")
+        return self._Xd, self._Yd
+
+    def _slice_for_kernel(self, Xd):
+        return self.kernel.slice(Xd, None)[0].contiguous()
+
+    # ---- gpflow-style objective API --------------------------------------------------------
+    def log_prior_density(self) -> float:
+        total = 0.0
+        for p in collect_parameters(self):
+            if p.prior is not None:
+                total += float(np.sum(p.prior.log_prob(p.numpy())))
+        return total
+
+    def maximum_log_likelihood_objective(self) -> float:
+        raise NotImplementedError
+
+    def training_loss(self) -> float:
+        return -(self.maximum_log_likelihood_objective() + self.log_prior_density())
+
+    def training_loss_closure(self):
+        return self.training_loss
+
+
+class GPR(GPModel):
+    """Exact GP regression: ``log N(y; 0, K + noise I)`` (gpflow ``GPR``; model_utils.py:159)."""
+
+    def __init__(self, data, kernel, mean_function=None, noise_variance: float = 1.0):
+        super().__init__(data, kernel, mean_function, noise_variance)
+
+    def _factorise(self):
+        Xd, Yd = self._device_data()
+        K = self.kernel._K_device(self._slice_for_kernel(Xd))
+        lml, alpha = _device.gpr_finish(K, Yd, scalar_of(self.likelihood.variance))
+        return K, lml, alpha  # K now holds the Cholesky factor (upper triangle, row-major)
+
+    def log_marginal_likelihood(self) -> float:
+        return float(self._factorise()[1].item())
+
+    def maximum_log_likelihood_objective(self) -> float:
+        return self.log_marginal_likelihood()
+
+    def sufficient_statistics(self):
+        """alpha = (K + noise I)^-1 y on the device, shape (N, 1) (oak/utils.py:206-211)."""
+        return self._factorise()[2].reshape(-1, 1)
+
+    def predict_f(self, Xnew, full_cov: bool = False) -> Tuple[object, object]:
+        import torch
+
+        host = _device.is_host(Xnew)
+        Xd, _ = self._device_data()
+        Xs = self._slice_for_kernel(Xd)
+        Xn = self._slice_for_kernel(_device.to_device(Xnew))
+        Kfac, _, alpha = self._factorise()
+        spec = self.kernel._make_spec()
+        try:
+            pn, px = _device.Points(spec, Xn), _device.Points(spec, Xs)
+            Kns = _device.gram(spec, pn, px)  # (N*, N)
+            kdiag = _device.gram_diag(spec, pn)
+        finally:
+            spec.close()
+        mean = Kns @ alpha.reshape(-1, 1)
+        # var = k** - |L^-1 k*|^2 ; Kfac holds L^T in its upper triangle (library triangular solve)
+        A = torch.linalg.solve_triangular(torch.triu(Kfac).T, Kns.T, upper=False)
+        var = (kdiag - (A * A).sum(0)).reshape(-1, 1)
+        return _device.from_device(mean, host), _device.from_device(var, host)
+
+
+class SGPR(GPModel):
+    """Titsias' sparse GP regression bound (gpflow 2.2.1 ``SGPR``; model_utils.py:150-155)."""
+
+    def __init__(self, data, kernel, inducing_variable, mean_function=None, noise_variance: float = 1.0,
+                 chunk: int = 8192, distributed: Optional[bool] = None):
+        super().__init__(data, kernel, mean_function, noise_variance)
+        if not isinstance(inducing_variable, InducingPoints):
+            inducing_variable = InducingPoints(inducing_variable)
+        self.inducing_variable = inducing_variable
+        self.chunk = int(chunk)
+        # each rank holds a shard of (X, y) when torch.distributed is initialised
+        self.distributed = parallel.is_distributed() if distributed is None else bool(distributed)
+        self.last_timings = {}
+
+    def _Z_device(self):
+        return self._slice_for_kernel(_device.to_device(value_of(self.inducing_variable.Z)))
+
+    def _statistics(self, want_alpha: bool):
+        """Returns (out[4], alpha, L-factor buffer, LB-factor buffer, n_total)."""
+        Xd, Yd = self._device_data()
+        Xs = self._slice_for_kernel(Xd)
+        Zs = self._Z_device()
+        spec = self.kernel._make_spec()
+        try:
+            self.kernel._check_discrete(Xs, spec._keep)
+            self.kernel._check_discrete(Zs, spec._keep)
+            pz, px = _device.Points(spec, Zs), _device.Points(spec, Xs)
+            stats = _device.sgpr_stats(spec, pz, px, Yd, chunk=self.chunk)
+            n_total = int(Xs.shape[0])
+            if self.distributed:
+                parallel.allreduce_sum_(stats)
+                n_total = parallel.allreduce_int(n_total)
+            Kuu = _device.gram(spec, pz)  # Kuu(iv, kernel); the jitter is added in the tail
+        finally:
+            spec.close()
+        out, alpha = _device.sgpr_finish(Kuu, stats, n_total, scalar_of(self.likelihood.variance),
+                                         DEFAULT_JITTER, want_alpha=want_alpha)
+        m = Kuu.shape[0]
+        return out, alpha, Kuu, stats[: m * m].view(m, m), n_total
+
+    def elbo(self) -> float:
+        return float(self._statistics(False)[0][0].item())
+
+    def maximum_log_likelihood_objective(self) -> float:
+        return self.elbo()
+
+    def sufficient_statistics(self):
+        """alpha = L^-T LB^-T c, shape (M, 1) (oak/utils.py:195-198)."""
+        return self._statistics(True)[1].reshape(-1, 1)
+
+    def predict_f(self, Xnew, full_cov: bool = False):
+        import torch
+
+        host = _device.is_host(Xnew)
+        out, alpha, Lbuf, LBbuf, _ = self._statistics(True)
+        Xn = self._slice_for_kernel(_device.to_device(Xnew))
+        Zs = self._Z_device()
+        spec = self.kernel._make_spec()
+        try:
+            pn, pz = _device.Points(spec, Xn), _device.Points(spec, Zs)
+            Kus = _device.gram(spec, pz, pn)  # (M, N*)
+            kdiag = _device.gram_diag(spec, pn)
+        finally:
+            spec.close()
+        mean = Kus.T @ alpha.reshape(-1, 1)
+        L = torch.triu(Lbuf).T
+        LB = torch.triu(LBbuf).T
+        tmp1 = torch.linalg.solve_triangular(L, Kus, upper=False)
+        tmp2 = torch.linalg.solve_triangular(LB, tmp1, upper=False)
+        var = (kdiag + (tmp2 * tmp2).sum(0) - (tmp1 * tmp1).sum(0)).reshape(-1, 1)
+        return _device.from_device(mean, host), _device.from_device(var, host)

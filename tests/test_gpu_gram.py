@@ -1,0 +1,226 @@
+"""GPU parity: fused CUDA Gram tiles (through the C ABI) vs the NumPy oracle on the same inputs.
+
+Tolerance: 1e-9 relative (north_star), measured as max|K - K_ref| / max|K_ref| and -- where no
+entry is close to zero -- element-wise.
+"""
+import numpy as np
+import pytest
+
+from helpers import RTOL, build_oracle, max_rel_err, mixed_config
+
+pytestmark = pytest.mark.gpu
+
+
+def _product(cfg):
+    from oak_b200.workloads import build_kernel
+
+    return build_kernel(cfg)
+
+
+def _gauss_cfg(n, D, depth, seed=0, share=True):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, D))
+    dims = [{"type": "rbf", "lengthscale": float(l), "variance": 1.0, "measure": ("gaussian", 0.0, 1.0)}
+            for l in rng.uniform(0.4, 3.0, D)]
+    var = list(rng.uniform(0.2, 1.5, depth + 1)) if share else [0.7]
+    return dict(X=X, dims=dims, depth=depth, variances=var, share_var=share)
+
+
+@pytest.mark.parametrize("depth", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 13])
+@pytest.mark.parametrize("algo", [0, 1])
+def test_gram_depths_vs_oracle(depth, algo):
+    D = max(depth, 3) if depth < 9 else depth + 1
+    cfg = _gauss_cfg(150, D, depth, seed=depth)
+    k = _product(cfg)
+    k.esp_algorithm = algo
+    ref = build_oracle(cfg)
+    X = cfg["X"]
+    K = k.K(X)
+    Kref = ref.K(X)
+    assert K.shape == Kref.shape
+    assert max_rel_err(K, Kref) < RTOL
+    np.testing.assert_array_equal(K, K.T)  # mirrored tiles are bit-identical
+    X2 = np.random.default_rng(99).standard_normal((77, D))
+    assert max_rel_err(k.K(X, X2), ref.K(X, X2)) < RTOL
+    assert max_rel_err(k.K_diag(X), ref.K_diag(X)) < RTOL
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 128, 129, 200, 513])
+def test_gram_ragged_sizes(n):
+    cfg = _gauss_cfg(n, 5, 3, seed=n)
+    k, ref = _product(cfg), build_oracle(cfg)
+    X = cfg["X"]
+    assert max_rel_err(k.K(X), ref.K(X)) < RTOL
+    X2 = np.random.default_rng(n + 1).standard_normal((max(n // 2, 1), 5))
+    assert max_rel_err(k.K(X, X2), ref.K(X, X2)) < RTOL
+    assert max_rel_err(k.K(X2, X), ref.K(X2, X)) < RTOL
+
+
+def test_gram_empty_inputs():
+    cfg = _gauss_cfg(10, 3, 2)
+    k = _product(cfg)
+    assert k.K(np.zeros((0, 3))).shape == (0, 0)
+    assert k.K(cfg["X"], np.zeros((0, 3))).shape == (10, 0)
+    assert k.K_diag(np.zeros((0, 3))).shape == (0,)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 5])
+@pytest.mark.parametrize("share", [True, False])
+def test_gram_mixed_kernels_and_measures(depth, share):
+    cfg = mixed_config(n=180, seed=depth, depth=depth, share=share)
+    k, ref = _product(cfg), build_oracle(cfg)
+    X = cfg["X"]
+    assert max_rel_err(k.K(X), ref.K(X)) < RTOL
+    assert max_rel_err(k.K(X, cfg["Z"]), ref.K(X, cfg["Z"])) < RTOL
+    assert max_rel_err(k.K_diag(X), ref.K_diag(X)) < RTOL
+    # the reference builds RBF with the expanded squared distance; same tolerance must hold
+    ref_exp = build_oracle(cfg, expanded=True)
+    assert max_rel_err(k.K(X), ref_exp.K(X)) < RTOL
+
+
+def test_gram_many_dims_chunked():
+    """D=50 exercises the dim-chunk pipeline (16 dims per stage) incl. a discrete tail."""
+    rng = np.random.default_rng(5)
+    cfg = _gauss_cfg(300, 50, 2, seed=5)
+    X = cfg["X"]
+    X[:, 48] = (rng.random(300) < 0.4)
+    X[:, 49] = rng.integers(0, 3, 300)
+    cfg["dims"][48] = {"type": "binary", "p0": 0.6, "variance": 1.0}
+    cfg["dims"][49] = {"type": "categorical", "p": [0.3, 0.3, 0.4], "W": rng.uniform(0, 1, (3, 2)),
+                       "kappa": np.ones(3), "variance": 1.0}
+    k, ref = _product(cfg), build_oracle(cfg)
+    assert max_rel_err(k.K(X), ref.K(X)) < RTOL
+    assert max_rel_err(k.K(X[:100], X), ref.K(X[:100], X)) < RTOL
+
+
+def test_gram_sub_kernels_standalone():
+    """test_kernel_1d of the reference (tests/test_kernel_properties.py:57-66) + oracle parity."""
+    from oak_b200.input_measures import EmpiricalMeasure, GaussianMeasure, MOGMeasure, UniformMeasure
+    from oak_b200.ortho_binary_kernel import OrthogonalBinary
+    from oak_b200.ortho_rbf_kernel import RBF, OrthogonalRBFKernel
+    from oracle import oak_oracle as oo
+
+    X = np.array([[0.1], [0.5], [0.5]])
+    pairs = [
+        (OrthogonalRBFKernel(RBF(), GaussianMeasure(0, 1)), oo.RBFDim(1.0, 1.0, oo.Gaussian(0, 1))),
+        (OrthogonalRBFKernel(RBF(), UniformMeasure(0, 1)), oo.RBFDim(1.0, 1.0, oo.Uniform(0, 1))),
+        (OrthogonalRBFKernel(RBF(), EmpiricalMeasure(X)), oo.RBFDim(1.0, 1.0, oo.Empirical(X))),
+        (OrthogonalRBFKernel(RBF(lengthscales=10), MOGMeasure(np.array([3.0, 2.0]), np.array([3.0, 10.0]),
+                                                              np.array([0.6, 0.4]))),
+         oo.RBFDim(10.0, 1.0, oo.MOG([3.0, 2.0], [3.0, 10.0], [0.6, 0.4]))),
+        (OrthogonalBinary(), oo.BinaryDim(0.5)),
+        (RBF(lengthscales=0.3, variance=2.0), oo.RBFDim(0.3, 2.0, None)),
+    ]
+    for k, ref in pairs:
+        Xi = X if not isinstance(k, OrthogonalBinary) else np.array([[0.0], [1.0], [1.0]])
+        K = k.K(Xi, Xi)
+        np.testing.assert_allclose(np.diag(K), k.K_diag(Xi), rtol=1e-12)
+        np.testing.assert_allclose(K, k(Xi, Xi), rtol=0, atol=0)
+        assert max_rel_err(K, ref.K(Xi, Xi)) < RTOL
+        assert max_rel_err(k.K_diag(Xi), ref.K_diag(Xi)) < RTOL
+
+
+def test_cov_X_s_and_var_s_closures():
+    from oak_b200.input_measures import GaussianMeasure, UniformMeasure
+    from oak_b200.ortho_rbf_kernel import RBF, OrthogonalRBFKernel
+    from oracle import oak_oracle as oo
+
+    x = np.random.default_rng(0).uniform(-1, 2, (40, 1))
+    for meas, omeas in ((GaussianMeasure(0.3, 2.0), oo.Gaussian(0.3, 2.0)), (UniformMeasure(-1, 2), oo.Uniform(-1, 2))):
+        k = OrthogonalRBFKernel(RBF(lengthscales=0.8, variance=1.7), meas)
+        ref = oo.RBFDim(0.8, 1.7, omeas)
+        assert abs(k.var_s() - ref.var_s()) / ref.var_s() < 1e-12
+        assert max_rel_err(k.cov_X_s(x), ref.cov_X_s(x)) < 1e-12
+
+
+def test_mog_equals_gaussian():
+    """tests/test_orthogonality.py:152-165 of the reference."""
+    from oak_b200.input_measures import GaussianMeasure, MOGMeasure
+    from oak_b200.ortho_rbf_kernel import RBF, OrthogonalRBFKernel
+
+    k_gmm = OrthogonalRBFKernel(RBF(lengthscales=10.0), MOGMeasure(np.array([3.0, 3.0]), np.array([5.0, 5.0]),
+                                                                    np.array([0.2, 0.8])))
+    k_g = OrthogonalRBFKernel(RBF(lengthscales=10.0), GaussianMeasure(3, 5))
+    xx = np.array([[-2], [2.0], [3.0]])
+    np.testing.assert_allclose(k_g.K(xx), k_gmm.K(xx), rtol=1e-7)
+
+
+def test_row_range_sharding_is_bit_identical():
+    """Row-block sharding: virtual ranks G in {2,4,8} reproduce the unsharded Gram."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.parallel import partition_rows
+
+    cfg = _gauss_cfg(1000, 6, 3, seed=3)
+    k = _product(cfg)
+    Xd = _device.to_device(cfg["X"])
+    spec = k._make_spec()
+    px = _device.Points(spec, Xd)
+    full = _device.gram(spec, px)
+    X2 = _device.to_device(np.random.default_rng(1).standard_normal((333, 6)))
+    px2 = _device.Points(spec, X2)
+    full2 = _device.gram(spec, px, px2)
+    for G in (2, 4, 8):
+        parts = [_device.gram(spec, px, None, b, e) for b, e in partition_rows(1000, G)]
+        assert torch.equal(torch.cat(parts, 0), full)
+        parts2 = [_device.gram(spec, px, px2, b, e) for b, e in partition_rows(1000, G)]
+        assert torch.equal(torch.cat(parts2, 0), full2)
+    spec.close()
+
+
+def test_torch_inputs_stay_on_device():
+    import torch
+
+    cfg = _gauss_cfg(70, 4, 2)
+    k, ref = _product(cfg), build_oracle(cfg)
+    Xd = torch.as_tensor(cfg["X"]).cuda()
+    K = k.K(Xd)
+    assert isinstance(K, torch.Tensor) and K.is_cuda
+    assert max_rel_err(K.cpu().numpy(), ref.K(cfg["X"])) < RTOL
+
+
+def test_small_lengthscale_underflow_is_clean():
+    """exp underflow (|x-y| / l huge) must give exact zeros for the RBF part, no NaN/garbage."""
+    cfg = _gauss_cfg(100, 3, 2, seed=8)
+    for d in cfg["dims"]:
+        d["lengthscale"] = 0.001
+    k, ref = _product(cfg), build_oracle(cfg)
+    K, Kref = k.K(cfg["X"]), ref.K(cfg["X"])
+    assert np.all(np.isfinite(K))
+    assert max_rel_err(K, Kref) < RTOL
+
+
+def test_invalid_category_raises():
+    cfg = mixed_config(n=50, depth=2)
+    k = _product(cfg)
+    X = cfg["X"].copy()
+    X[3, 5] = 7.0
+    with pytest.raises(ValueError):
+        k.K(X)
+
+
+def test_gram_host_pipeline_matches_device():
+    """oak_gram_host_f64 (host buffers, row-blocked, overlapped D2H) == device Gram."""
+    import ctypes as C
+
+    import torch
+
+    from oak_b200 import _cabi, _device
+
+    cfg = _gauss_cfg(700, 5, 3, seed=11)
+    k, ref = _product(cfg), build_oracle(cfg)
+    X = np.ascontiguousarray(cfg["X"])
+    spec = k._make_spec()
+    lib = _cabi.load()
+    for X2 in (None, np.ascontiguousarray(np.random.default_rng(2).standard_normal((130, 5)))):
+        cols = 700 if X2 is None else X2.shape[0]
+        out = torch.empty((700, cols), dtype=torch.float64).pin_memory()
+        wb = lib.oak_gram_host_work_bytes(spec.handle, 700, 0 if X2 is None else cols, 5, 128)
+        work = torch.empty(wb // 8 + 1, dtype=torch.float64, device="cuda")
+        rc = lib.oak_gram_host_f64(spec.handle, X.ctypes.data, 700, None if X2 is None else X2.ctypes.data,
+                                   0 if X2 is None else cols, 5, out.data_ptr(), cols, 128, work.data_ptr(),
+                                   C.c_void_p(_device.stream_ptr()))
+        assert rc == 0, _cabi.last_error()
+        assert max_rel_err(out.numpy(), ref.K(X, X2)) < RTOL
+    spec.close()
