@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- OAK Gram entries/sec (FP64) and SGPR ELBO evals/sec on B200, vs roofline.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` (under torchrun for N > 1) prints ONE
+JSON line on rank 0.  A *step* is one pass of the hot path over the workload:
+
+  headline   config B of BASELINE.json: K(X, X), N=65536, D=16, max_interaction_depth=4, FP64,
+             prepare + fused Gram kernel, inputs resident in HBM.  N=1: lower-triangle tiles +
+             mirrored stores (full matrix written).  N>1: folded row strips, each rank evaluates
+             the lower trapezoid of its strips (no collective) -> strong scaling of a fixed N.
+             value = unique entries N(N+1)/2 per evaluation / time (the work model of BASELINE.md).
+  e2e        the same metric through the host-buffer C-ABI call (oak_gram_host_f64): pinned NumPy
+             X in, H2D, prepare, row-blocked Gram, D2H of the rows into pinned host memory.
+  extra      config C: SGPR ELBO evals/s (N=1M, D=20, M=1024, depth 3), N axis sharded over ranks,
+             one all-reduce of M^2+M+2 doubles, M^3 tail timed separately.
+  roofline   FP64-pipe bound: algorithmic flop (306 slots x 2 per unique entry) / Gram-kernel time
+             (CUDA events on the launch stream) / measured DFMA peak of the same run.
+  cpu_baseline  the reference op sequence (oracle/cpu_baseline.py, torch-CPU FP64, all host cores)
+             on a bounded sample, rank 0 at N=1 only.
+
+``--impl reference`` times that CPU restatement alone (the reference itself needs TensorFlow /
+gpflow, which are not installable in this image -- see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SLOTS_B = 306.0  # BASELINE.md work model: FP64 issue slots per Gram entry at D=16, P=4
+SLOTS_C = 865.5  # per Kuf entry at D=20, P=3, M=1024 (tile 352 + SYRK 512.5 + Kuf y 1)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=65536, help="Gram size (config B: 8k..64k)")
+    ap.add_argument("--n-e2e", type=int, default=0, help="Gram size of the host-buffer leg (0 = auto)")
+    ap.add_argument("--n-cpu", type=int, default=4096, help="sample size of the CPU baseline")
+    ap.add_argument("--elbo-n", type=int, default=1_000_000)
+    ap.add_argument("--elbo-m", type=int, default=1024)
+    ap.add_argument("--no-elbo", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--algo", type=int, default=0, help="0 Newton-Girard (reference), 1 direct recurrence")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_gram_sample(n_cpu, reps, warm=0):
+    """Reference op sequence on the host cores: K(X, X) of config B at N=n_cpu. Returns
+    (unique entries/s, seconds per evaluation, threads)."""
+    import torch
+
+    from oak_b200.workloads import config_B
+    from oracle import cpu_baseline
+
+    cpu_baseline.tune_allocator()
+    cfg = config_B(n_cpu)
+    X = torch.as_tensor(cfg["X"])
+    cpu_baseline.gram(cfg, X[:512])  # warm the thread pool / allocator
+    for _ in range(warm):
+        cpu_baseline.gram(cfg, X)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        K = cpu_baseline.gram(cfg, X)
+        ts.append(time.perf_counter() - t0)
+        del K
+    ts.sort()
+    t = ts[len(ts) // 2]
+    return n_cpu * (n_cpu + 1) / 2 / t, t, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    n = args.n_cpu
+    val, t_eval, threads = cpu_gram_sample(n, args.steps, warm=args.warmup)
+    line = {
+        "impl": "reference",
+        "metric": "OAK Gram entries/sec (FP64)", "value": val, "unit": "unique entries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_eval * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"config B: OAK Gram K(X,X) D=16 depth=4 FP64; reference CPU op sequence on a "
+                               f"bounded sample N={n} (the unfused path needs ~(D+P+2) N^2 x 8 B)"},
+        "cpu_baseline": {"value": val, "unit": "unique entries/s", "cores": threads, "kind": "port",
+                         "sample": f"K(X,X) N={n}, D=16, depth=4, median of {args.steps} after {args.warmup} warm-ups; "
+                                   "TensorFlow/gpflow not installable -> oracle/cpu_baseline.py (torch-CPU FP64)"},
+        "e2e": {"value": val, "unit": "unique entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oak_b200 import _cabi, _device, parallel
+    from oak_b200.models import SGPR
+    from oak_b200.workloads import build_kernel, config_B, config_C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _cabi.require_device()
+    import ctypes as C
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- measured FP64 peak (roofline denominator) -------------------------------------------
+    peak_slots = _device.measure_fp64_peak(1.0)
+
+    # ---- headline: config B -------------------------------------------------------------------
+    n = args.n
+    cfg = config_B(n)
+    kern = build_kernel(cfg)
+    kern.esp_algorithm = args.algo
+    spec = kern._make_spec()
+    Xd = _device.to_device(cfg["X"])
+    if world == 1:
+        out = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        strips = [(0, n)]
+    else:
+        strips = [s for s in parallel.balanced_symmetric_rows(n, world)[rank] if s[1] > s[0]]
+        outs = [torch.empty((e - b, e), dtype=torch.float64, device="cuda") for b, e in strips]
+    kev = []  # (start, end) events bracketing the Gram kernel launches of each timed step
+
+    def step(record=False):
+        px = _device.Points(spec, Xd)  # per-point prologue (O(N D))
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if world == 1:
+            _device.gram(spec, px, out=out)
+        else:
+            for (b, e), o in zip(strips, outs):
+                _device.gram_lower(spec, px, b, e, out=o)
+        if record:
+            e1.record()
+            kev.append((e0, e1))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = _cabi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = _cabi.launch_count() - launches0
+    clocks = sampler.stop()
+    barrier()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    kern_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in kev) / len(kev))
+    unique = n * (n + 1) / 2
+    value = unique / (ms_step * 1e-3)
+    # per-rank algorithmic work of the dominant kernel (unique entries of this rank's strips)
+    my_unique = sum((e - b) * (b + e + 1) / 2 for b, e in strips)
+    my_unique = max_over_ranks(my_unique)
+    achieved_tflops = my_unique * SLOTS_B * 2 / (kern_ms * 1e-3) / 1e12
+    peak_tflops = 2 * peak_slots / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("gram_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    hbm_peak = 6521.4
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    out_bytes = (n * n if world == 1 else sum((e - b) * e for b, e in strips)) * 8.0
+    roofline = {
+        "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tflops / peak_tflops, "traffic": traffic,
+        "kernel": "oak::gram_kernel<4,4,4,NG>", "kernel_ms": kern_ms,
+        "peak_source": "measured in this run: oak_measure_fp64_peak (register-resident DFMA chains, burst); "
+                       "MEASURED_PEAKS.json has no FP64 entry",
+        "work_model": f"{SLOTS_B:.0f} FP64 issue slots (x2 flop) per unique entry (BASELINE.md section 3)",
+        "hbm": {"achieved": out_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": out_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                "note": "8 B per written entry; the kernel is FP64-pipe bound, not HBM bound"},
+    }
+
+    # ---- e2e: host buffers through oak_gram_host_f64 -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_e = args.n_e2e
+        if n_e == 0:
+            avail = mem_available_gb()
+            n_e = 32768 if avail > 40 * max(1, 1) else 16384
+        cfg_e = config_B(n_e)
+        kern_e = build_kernel(cfg_e)
+        kern_e.esp_algorithm = args.algo
+        spec_e = kern_e._make_spec()
+        rb, re_ = parallel.partition_rows(n_e, world)[rank]
+        rows = re_ - rb
+        Xh = torch.as_tensor(np.ascontiguousarray(cfg_e["X"])).pin_memory()
+        Xrows = Xh[rb:re_].contiguous().pin_memory() if world > 1 else Xh
+        Kh = torch.empty((max(rows, 1), n_e), dtype=torch.float64).pin_memory()
+        block = 2048
+        wb = lib.oak_gram_host_work_bytes(spec_e.handle, rows, n_e if world > 1 else 0, 16, block)
+        work = torch.empty(wb // 8 + 1, dtype=torch.float64, device="cuda")
+
+        def e2e_step():
+            rc = lib.oak_gram_host_f64(spec_e.handle, Xrows.data_ptr(), rows,
+                                       Xh.data_ptr() if world > 1 else None, n_e if world > 1 else 0, 16,
+                                       Kh.data_ptr(), n_e, block, work.data_ptr(),
+                                       C.c_void_p(_device.stream_ptr()))
+            assert rc == 0, _cabi.last_error()
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b_.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / e2e_steps
+        ms_e = max_over_ranks(max(a.elapsed_time(b_) / e2e_steps, wall * 1e3))
+        barrier()
+        e2e = {
+            "value": n_e * (n_e + 1) / 2 / (ms_e * 1e-3), "unit": "unique entries/s",
+            "h2d_bytes_per_step": int(Xrows.numel() * 8 + (Xh.numel() * 8 if world > 1 else 0)),
+            "d2h_bytes_per_step": int(rows * n_e * 8), "ms_per_step": ms_e,
+            "workload": f"oak_gram_host_f64: K(X,X) N={n_e} D=16 depth=4, pinned host X in, all {n_e}^2 entries "
+                        f"copied back to pinned host memory in {block}-row blocks overlapped with compute"
+                        + (f", rows partitioned over {world} ranks" if world > 1 else ""),
+        }
+        del Kh, work, Xh
+        spec_e.close()
+
+    # ---- extra: SGPR ELBO evals/s (config C) ---------------------------------------------------
+    elbo = None
+    if not args.no_elbo:
+        cfg_c = config_C(args.elbo_n, 20, args.elbo_m, 3)
+        b, e = parallel.partition_rows(args.elbo_n, world)[rank]
+        kc = build_kernel(cfg_c)
+        kc.esp_algorithm = args.algo
+        model = SGPR((cfg_c["X"][b:e], cfg_c["y"][b:e]), kernel=kc, inducing_variable=cfg_c["Z"], chunk=8192,
+                     distributed=(world > 1))
+        model.likelihood.variance.assign(cfg_c["noise"])
+        model._device_data()
+        model.elbo()
+        barrier()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k_e = max(2, min(args.steps, 5))
+        a.record()
+        vals = [model.elbo() for _ in range(k_e)]
+        b2.record()
+        torch.cuda.synchronize()
+        ms_elbo = max_over_ranks(a.elapsed_time(b2) / k_e)
+        # stats phase alone (tile generation + DSYRK + DGEMV), no tail, no collective
+        sp = kc._make_spec()
+        Xs, Ys = model._device_data()
+        pz = _device.Points(sp, model._Z_device())
+        pxs = _device.Points(sp, Xs)
+        _device.sgpr_stats(sp, pz, pxs, Ys)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(k_e):
+            _device.sgpr_stats(sp, pz, pxs, Ys)
+        b2.record()
+        torch.cuda.synchronize()
+        ms_stats = max_over_ranks(a.elapsed_time(b2) / k_e)
+        sp.close()
+        kuf_entries = float(args.elbo_m) * (e - b)
+        elbo = {
+            "metric": "SGPR ELBO evals/sec", "value": 1e3 / ms_elbo, "unit": "evals/s", "ms_per_eval": ms_elbo,
+            "ms_stats_phase": ms_stats, "ms_tail_and_collective": ms_elbo - ms_stats, "elbo": vals[-1],
+            "workload": f"config C: N={args.elbo_n}, D=20, M={args.elbo_m}, depth 3; N axis sharded over {world} "
+                        f"rank(s); all-reduce of {args.elbo_m ** 2 + args.elbo_m + 2} doubles",
+            "roofline_stats_phase": {
+                "bound": "fp64", "unit": "TFLOP/s", "peak": peak_tflops,
+                "achieved": kuf_entries * SLOTS_C * 2 / (ms_stats * 1e-3) / 1e12,
+                "frac": kuf_entries * SLOTS_C * 2 / (ms_stats * 1e-3) / 1e12 / peak_tflops,
+                "work_model": f"{SLOTS_C} slots per Kuf entry (tile 352 + DSYRK 512.5 + Kuf y 1)"},
+        }
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, t_eval, threads = cpu_gram_sample(args.n_cpu, 3)
+        cpu = {"value": v, "unit": "unique entries/s", "cores": threads, "kind": "port",
+               "sample": f"K(X,X) N={args.n_cpu}, D=16, depth=4 (reference op sequence, oracle/cpu_baseline.py, "
+                         f"torch-CPU FP64), median of 3: {t_eval:.2f} s per evaluation"}
+
+    if rank == 0:
+        line = {
+            "metric": "OAK Gram entries/sec (FP64)", "value": value, "unit": "unique entries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"config B: OAK Gram K(X,X), N={n}, D=16, max_interaction_depth=4, Gaussian measure, "
+                            "FP64; step = prepare + fused Gram kernel, X resident in HBM; "
+                            + ("lower-triangle tiles + mirrored stores, full N x N matrix written"
+                               if world == 1 else f"folded row strips over {world} ranks, lower trapezoids, no collective"),
+                "l2": f"output of {out_bytes / 1e9:.1f} GB per step >> 126 MB L2 (streaming stores); inputs 16 MB",
+                "esp": "newton_girard" if args.algo == 0 else "direct_recurrence",
+            },
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "extra": {"sgpr_elbo": elbo, "fp64_peak_slots_per_s": peak_slots},
+        }
+        print(json.dumps(line))
+    spec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -116,6 +116,14 @@ int oak_gram_f64(const oak_spec* spec, const void* d_points, int64_t n, const vo
                  int64_t n2, int64_t row_begin, int64_t row_end, double* d_K, int64_t ldk,
                  void* stream);
 
+/* Lower trapezoid of the symmetric Gram K(X, X): rows [row_begin,row_end) x columns
+ * [0,row_end), evaluating only tiles that intersect the lower triangle (entries above the
+ * diagonal outside the diagonal tiles are left untouched).  This is the per-rank unit of the
+ * row-strip sharded symmetric Gram; no mirroring, no collective.
+ * d_K[(i-row_begin)*ldk + j]. */
+int oak_gram_lower_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                       int64_t row_end, double* d_K, int64_t ldk, void* stream);
+
 /* Replaces OAKKernel.K_diag(X) (oak_kernel.py:267-278). d_out[n]. */
 int oak_gram_diag_f64(const oak_spec* spec, const void* d_points, int64_t n, double* d_out,
                       void* stream);

@@ -69,6 +69,7 @@ SIGNATURES = {
     "oak_points_bytes": (_sz, [_vp, _i64]),
     "oak_prepare_points_f64": (C.c_int, [_vp, _dp, _i64, _i64, _vp, _vp]),
     "oak_gram_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _dp, _i64, _vp]),
+    "oak_gram_lower_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _i64, _vp]),
     "oak_gram_diag_f64": (C.c_int, [_vp, _vp, _i64, _dp, _vp]),
     "oak_component_gram_f64": (C.c_int, [_vp, C.POINTER(_i32), _i32, _vp, _i64, _vp, _i64, _dp, _i64, _vp]),
     "oak_component_predict_f64": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _dp, _dp, _vp]),
@@ -177,6 +178,9 @@ class Spec:
             arr[i].lengthscale, arr[i].variance, arr[i].m0, arr[i].m1 = d.lengthscale, d.variance, d.m0, d.m1
             arr[i].v0, arr[i].v1, arr[i].v2 = _dptr(d.v0), _dptr(d.v1), _dptr(d.v2)
         var = np.ascontiguousarray(np.asarray(variances, dtype=np.float64).reshape(-1))
+        need = depth + 1 if share_var else 1
+        if var.shape[0] < need:
+            raise ValueError(f"need {need} order variances for depth {depth} (share_var={share_var}), got {var.shape[0]}")
         desc = KernelDesc(len(dims), int(depth), int(bool(share_var)), int(algorithm), _dptr(var), arr)
         handle = _vp()
         check(lib.oak_spec_create(C.byref(desc), _vp(stream), C.byref(handle)), "oak_spec_create")

@@ -107,6 +107,21 @@ def gram(spec: Spec, px: Points, px2: Optional[Points] = None, row_begin: int = 
     return out
 
 
+def gram_lower(spec: Spec, px: Points, row_begin: int, row_end: int, out=None):
+    """Rows [row_begin,row_end) x cols [0,row_end) of the symmetric Gram, lower-triangle tiles only."""
+    torch = _torch()
+    rows = row_end - row_begin
+    if out is None:
+        out = torch.empty((rows, row_end), dtype=torch.float64, device=px.buf.device)
+    if rows > 0:
+        check(
+            _cabi.load().oak_gram_lower_f64(spec.handle, _p(px.buf), px.n, row_begin, row_end, _p(out),
+                                            int(out.stride(0)), C.c_void_p(stream_ptr())),
+            "oak_gram_lower_f64",
+        )
+    return out
+
+
 def gram_diag(spec: Spec, px: Points):
     torch = _torch()
     out = torch.empty((px.n,), dtype=torch.float64, device=px.buf.device)

@@ -11,7 +11,8 @@ from typing import List, Optional
 import numpy as np
 
 DEFAULT_JITTER = 1e-6  # gpflow.config.default_jitter()
-DEFAULT_POSITIVE_MINIMUM = 1e-6  # gpflow.config.default_positive_minimum()
+DEFAULT_POSITIVE_MINIMUM = 0.0  # gpflow.config.default_positive_minimum()
+VARIANCE_LOWER_BOUND = 1e-6  # gpflow.likelihoods DEFAULT_VARIANCE_LOWER_BOUND
 
 
 def default_float():
@@ -255,7 +256,7 @@ class Gaussian(Module):
     """Gaussian likelihood: only the noise variance is needed on this path."""
 
     def __init__(self, variance: float = 1.0):
-        self.variance = Parameter(variance, transform=positive())
+        self.variance = Parameter(variance, transform=positive(lower=VARIANCE_LOWER_BOUND))
 
 
 class Gamma:

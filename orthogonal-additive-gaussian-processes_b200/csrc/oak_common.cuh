@@ -102,7 +102,7 @@ const double* exp_table_device();  // lazily uploaded per device; nullptr on fai
 int tile_rows_for_depth(int depth);
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
-                int64_t col_end, bool symmetric, double* K, int64_t ldk, cudaStream_t stream);
+                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream);
 int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_t n_pad,
                      double* out, cudaStream_t stream);
 

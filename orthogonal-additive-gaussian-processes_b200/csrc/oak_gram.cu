@@ -38,7 +38,8 @@ struct GramParams {
   int64_t row_begin, row_end, col_begin, n2;  // n2 = number of output columns
   int64_t tiles_n, num_tiles;
   int D, Dc;
-  int symmetric;
+  int symmetric;        // 0 general, 1 lower-triangle tiles + mirrored stores, 2 lower trapezoid only
+  int64_t tile_row0;    // global row-block index of row_begin (modes 1, 2)
 };
 
 template <int RM, int RN>
@@ -152,11 +153,14 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
 
   auto tile_coords = [&](int64_t t, int64_t& bi, int64_t& bj) {
     if (prm.symmetric) {
-      // tiles of the lower triangle, row-block major: t = bi (bi+1)/2 + bj
+      // tiles of the lower triangle, row-block major: t' = gbi (gbi+1)/2 + bj with the global
+      // row-block index gbi = tile_row0 + bi (tile_row0 > 0 for a sharded lower trapezoid)
+      const int64_t g0 = prm.tile_row0;
+      t += g0 * (g0 + 1) / 2;
       int64_t b = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
       while (b * (b + 1) / 2 > t) --b;
       while ((b + 1) * (b + 2) / 2 <= t) ++b;
-      bi = b;
+      bi = b - g0;
       bj = t - b * (b + 1) / 2;
     } else {
       bi = t / prm.tiles_n;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
     const int64_t row0 = bi * TM;  // relative to row_begin
     const int64_t col0 = bj * TN;
     const int64_t nrows = prm.row_end - prm.row_begin;
-    const bool mirror = prm.symmetric && (bi != bj);
+    const bool mirror = prm.symmetric == 1 && (bi + prm.tile_row0 != bj);
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
       const int64_t row = row0 + ty + 16 * r;
@@ -326,7 +330,7 @@ static int sm_count(int device) {
 
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
-                int64_t col_end, bool symmetric, double* K, int64_t ldk, cudaStream_t stream) {
+                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream) {
   GramParams prm;
   for (int p = 0; p <= OAK_MAX_DEPTH; ++p) prm.sigma2[p] = spec->sigma2[p];
   prm.pts_row = prow;
@@ -351,9 +355,10 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
               "gram: row/column range must start on a multiple of the tile size (64)");
   const int64_t tiles_m = (row_end - row_begin + T - 1) / T;
   const int64_t tiles_n = (prm.n2 + T - 1) / T;
-  prm.symmetric = symmetric ? 1 : 0;
+  prm.symmetric = mode;
+  prm.tile_row0 = mode ? row_begin / T : 0;
   prm.tiles_n = tiles_n;
-  prm.num_tiles = prm.symmetric ? tiles_m * (tiles_m + 1) / 2 : tiles_m * tiles_n;
+  prm.num_tiles = mode ? tiles_m * (prm.tile_row0 + 1) + tiles_m * (tiles_m - 1) / 2 : tiles_m * tiles_n;
   const int sms = sm_count(spec->device);
   const int algo = spec->algo;
   switch (depth) {
@@ -391,5 +396,19 @@ extern "C" int oak_gram_f64(const oak_spec* spec, const void* d_points, int64_t 
   const bool symmetric = same && row_begin == 0 && row_end == n;
   return gram_launch(spec, (const double2*)d_points, padded(n), row_begin, row_end,
                      same ? (const double2*)d_points : (const double2*)d_points2, padded(n2), 0, n2,
-                     symmetric, d_K, ldk, (cudaStream_t)stream_);
+                     symmetric ? 1 : 0, d_K, ldk, (cudaStream_t)stream_);
+}
+
+extern "C" int oak_gram_lower_f64(const oak_spec* spec, const void* d_points, int64_t n,
+                                  int64_t row_begin, int64_t row_end, double* d_K, int64_t ldk,
+                                  void* stream_) {
+  OAK_REQUIRE(spec && d_points, "oak_gram_lower_f64: null argument");
+  OAK_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n,
+              "oak_gram_lower_f64: row range outside [0, n]");
+  if (row_end == row_begin) return 0;
+  OAK_REQUIRE(d_K, "oak_gram_lower_f64: null output");
+  OAK_REQUIRE(ldk >= row_end, "oak_gram_lower_f64: ldk smaller than row_end");
+  return gram_launch(spec, (const double2*)d_points, padded(n), row_begin, row_end,
+                     (const double2*)d_points, padded(n), 0, row_end, 2, d_K, ldk,
+                     (cudaStream_t)stream_);
 }

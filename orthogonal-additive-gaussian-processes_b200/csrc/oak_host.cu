@@ -79,7 +79,7 @@ extern "C" int oak_gram_host_f64(const oak_spec* spec, const double* h_X, int64_
     if (cudaStreamWaitEvent(stream, copied[b], 0) != cudaSuccess) rc = 1;
     if (rc == 0)
       rc = gram_launch(spec, (const double2*)pX, padded(n), r0, r1,
-                       same ? (const double2*)pX : (const double2*)pX2, padded(cols), 0, cols, false,
+                       same ? (const double2*)pX : (const double2*)pX2, padded(cols), 0, cols, 0,
                        blk[b], cols, stream);
     if (rc) break;
     cudaEventRecord(computed[b], stream);

@@ -217,7 +217,7 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
   for (int64_t c0 = 0; c0 < n_local; c0 += chunk) {
     const int64_t nc = (n_local - c0 < chunk) ? (n_local - c0) : chunk;
     // Kuf chunk = K(Z, X[c0:c0+nc])    (gpflow Kuf, oak/utils.py:184)
-    if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, false, kuf, chunk, stream))
+    if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream))
       return rc;
     // Phi += Kuf Kuf^T.  Row-major (M x nc, ld=chunk) == column-major (nc x M, lda=chunk) A';
     // Phi = A'^T A'  ->  DSYRK(trans = T).  Only one triangle is updated.
