@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboak_b200.so")
+LIB_PATH = os.environ.get("OAK_B200_LIB") or os.path.join(_HERE, "liboak_b200.so")  # env: dev builds only
 
 OAK_MAX_DEPTH = 16
 DIM_RBF, DIM_BINARY, DIM_CATEGORICAL = 0, 1, 2

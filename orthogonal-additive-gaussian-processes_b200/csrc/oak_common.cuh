@@ -114,14 +114,52 @@ int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_
 // inside the 1e-9 parity budget.  `tab` points at this lane's replica of the table in
 // shared memory: entry j lives at tab[j * 16] so that a half-warp never conflicts.
 #ifdef __CUDACC__
+// Variant used by the Gram tile.  Measured on B200 (scripts/ubench): a DFMA blocks the issue
+// port for two cycles and integer-ALU instructions (LOP3/SHF/LEA/IADD3) compete with it, while
+// IMAD (FMA pipe) co-issues for free.  The index math is therefore phrased as
+//   off = ((n << 7) & 0x7F80) | lane_bits          IMAD.SHL + one LOP3
+//   hi  = n * 4096 + T'hi[j]                        one IMAD
+// where the table's high words are stored pre-compensated, T'hi[j] = hi(2^(j/256)) - (j << 12),
+// so that adding n << 12 = (k << 20) + (j << 12) inserts the binary exponent k without masking.
+// `tab_bytes` is the table base in shared memory, `lane_bits` = (lane % 16) * 8.
+__device__ __forceinline__ double exp_neg_tile(double z, const unsigned char* __restrict__ tab_bytes,
+                                               unsigned lane_bits) {
+  constexpr double kMagic = 6755399441055744.0;     // 1.5 * 2^52
+  constexpr double kScale = -369.3299304675746271;  // -256 / ln 2
+  constexpr double kStep = 0.0027076061740622863;   // ln 2 / 256
+  constexpr int kHiClamp = 0x40862000;              // hi word of 708.0
+  int hi = __double2hiint(z);
+  hi = min(hi, kHiClamp);  // z <= 708 (sign bit set => negative int => untouched)
+  z = __hiloint2double(hi, __double2loint(z));
+  const double nd = fma(z, kScale, kMagic);
+  const int ni = __double2loint(nd);
+  const double n = nd - kMagic;
+  const double rp = fma(n, kStep, z);  // = -r
+  double p = fma(rp, 1.0 / 24.0, -1.0 / 6.0);
+  p = fma(p, rp, 0.5);
+  p = fma(p, rp, -1.0);
+  const double q = p * rp;  // e^r - 1
+  const unsigned off = (((unsigned)ni * 128u) & 0x7F80u) | lane_bits;
+  const uint2 tv = *reinterpret_cast<const uint2*>(tab_bytes + off);
+  int thi;
+  asm("mad.lo.s32 %0, %1, 4096, %2;" : "=r"(thi) : "r"(ni), "r"((int)tv.y));
+  const double t = __hiloint2double(thi, (int)tv.x);
+  return fma(t, q, t);
+}
+
 __device__ __forceinline__ double exp_neg(double z, const double* __restrict__ tab) {
   constexpr double kMagic = 6755399441055744.0;            // 1.5 * 2^52
   constexpr double kScale = -369.3299304675746271;         // -256 / ln 2
   constexpr double kStep = 0.0027076061740622863;          // ln 2 / 256
   constexpr int kHiClamp = 0x40862000;                     // hi word of 708.0
+#ifndef OAK_ABLATE
+#define OAK_ABLATE 0  // development only: 1 no clamp, 2 no table load, 3 no table + no exponent
+#endif
+#if OAK_ABLATE != 1
   int hi = __double2hiint(z);
   hi = min(hi, kHiClamp);  // z <= 708 (sign bit set => negative int => untouched)
   z = __hiloint2double(hi, __double2loint(z));
+#endif
   double nd = fma(z, kScale, kMagic);
   int ni = __double2loint(nd);
   double n = nd - kMagic;
@@ -130,9 +168,15 @@ __device__ __forceinline__ double exp_neg(double z, const double* __restrict__ t
   p = fma(p, rp, 0.5);
   p = fma(p, rp, -1.0);
   double q = p * rp;             // e^r - 1
+#if OAK_ABLATE == 2 || OAK_ABLATE == 3
+  double t = tab[0];
+#else
   double t = tab[(ni & (kExpTab - 1)) * 16];
+#endif
+#if OAK_ABLATE != 3
   int thi = __double2hiint(t) + ((ni >> 8) << 20);
   t = __hiloint2double(thi, __double2loint(t));
+#endif
   return fma(t, q, t);
 }
 #endif

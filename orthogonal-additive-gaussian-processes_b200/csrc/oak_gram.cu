@@ -19,11 +19,12 @@
 //     mirrored stores are coalesced.
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "oak_common.cuh"
 
 namespace oak {
 
-constexpr int kThreads = 256;
 constexpr int kDimChunk = 16;  // dims per pipeline stage
 
 struct GramParams {
@@ -42,9 +43,9 @@ struct GramParams {
   int64_t tile_row0;    // global row-block index of row_begin (modes 1, 2)
 };
 
-template <int RM, int RN>
+template <int TXD, int TYD, int RM, int RN>
 struct SmemLayout {
-  static constexpr int TM = 16 * RM, TN = 16 * RN;
+  static constexpr int TM = TYD * RM, TN = TXD * RN;
   static constexpr int kTabDoubles = kExpTab * 16;
   static constexpr int kStageDouble2 = kDimChunk * (TM + TN);
   static constexpr int kMirrorStride = TM + 1;  // odd stride: conflict-free column reads
@@ -131,10 +132,12 @@ __device__ __forceinline__ double finish(const double (&a)[P], const double* __r
   return r;
 }
 
-template <int P, int RM, int RN, int ALGO>
-__global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm) {
-  using L = SmemLayout<RM, RN>;
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO>
+__global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm) {
+  using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int TM = L::TM, TN = L::TN;
+  constexpr int kThreads = TXD * TYD;
+  static_assert(TXD % 16 == 0, "the exp-table replicas are indexed by lane % 16");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sTab = reinterpret_cast<double*>(smem_raw);
   double2* sStage = reinterpret_cast<double2*>(sTab + L::kTabDoubles);
@@ -142,11 +145,17 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
   double* sMirror = sAux + 2 * kDimChunk;
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int tx = tid % TXD, ty = tid / TXD;
 
   // replicate the exp table: entry j, replica r at sTab[j*16 + r]
-  for (int i = tid; i < L::kTabDoubles; i += kThreads) sTab[i] = prm.exptab[i >> 4];
-  const double* tab = sTab + tx;
+  // (high words pre-compensated by -(j << 12), see exp_neg_tile)
+  for (int i = tid; i < L::kTabDoubles; i += kThreads) {
+    const int j = i >> 4;
+    const double v = prm.exptab[j];
+    sTab[i] = __hiloint2double(__double2hiint(v) - (j << 12), __double2loint(v));
+  }
+  const unsigned char* tab_bytes = smem_raw;
+  const unsigned lane_bits = (unsigned)(tx & 15) * 8u;
 
   const int D = prm.D, Dc = prm.Dc;
   const int num_chunks = (D + kDimChunk - 1) / kDimChunk;
@@ -224,16 +233,16 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
         const double nls = aux[dl];
         double2 rv[RM], cv[RN];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty + 16 * r];
+        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty + TYD * r];
 #pragma unroll
-        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + 16 * c];
+        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + TXD * c];
 #pragma unroll
         for (int r = 0; r < RM; ++r)
 #pragma unroll
           for (int c = 0; c < RN; ++c) {
             const double d = rv[r].x - cv[c].x;
             const double z = fma(d, d, nls);            // (x-y)^2 / (2 l^2) - ln s^2
-            const double e = exp_neg(z, tab);           // s^2 exp(-(x-y)^2 / (2 l^2))
+            const double e = exp_neg_tile(z, tab_bytes, lane_bits);  // s^2 exp(-(x-y)^2/(2 l^2))
             const double k = fma(-rv[r].y, cv[c].y, e); // - cov_X_s(x) cov_X_s(y) / var_s
             accumulate<P, ALGO>(acc[r][c], k);
           }
@@ -245,9 +254,9 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
         const double* tbl = prm.tables + (int)__double_as_longlong(aux[dl]);
         int ro[RM], co[RN];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty + 16 * r].x);
+        for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty + TYD * r].x);
 #pragma unroll
-        for (int c = 0; c < RN; ++c) co[c] = __double2loint(colp[tx + 16 * c].x);
+        for (int c = 0; c < RN; ++c) co[c] = __double2loint(colp[tx + TXD * c].x);
 #pragma unroll
         for (int r = 0; r < RM; ++r)
 #pragma unroll
@@ -265,13 +274,13 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
     const bool mirror = prm.symmetric == 1 && (bi + prm.tile_row0 != bj);
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
-      const int64_t row = row0 + ty + 16 * r;
+      const int64_t row = row0 + ty + TYD * r;
 #pragma unroll
       for (int c = 0; c < RN; ++c) {
-        const int64_t col = col0 + tx + 16 * c;
+        const int64_t col = col0 + tx + TXD * c;
         const double v = finish<P, ALGO>(acc[r][c], prm.sigma2);
         if (row < nrows && col < prm.n2) __stcs(prm.K + row * prm.ldk + col, v);
-        if (mirror) sMirror[(tx + 16 * c) * L::kMirrorStride + (ty + 16 * r)] = v;
+        if (mirror) sMirror[(tx + TXD * c) * L::kMirrorStride + (ty + TYD * r)] = v;
       }
     }
     if (mirror) {
@@ -293,11 +302,12 @@ __global__ void __launch_bounds__(kThreads, 1) gram_kernel(const GramParams prm)
 }
 
 // ---- launch plumbing -------------------------------------------------------------------
-template <int P, int RM, int RN, int ALGO>
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO>
 static int launch_gram(const GramParams& prm, int sms, cudaStream_t stream) {
-  using L = SmemLayout<RM, RN>;
-  const size_t smem = L::bytes(prm.symmetric != 0);
-  auto kern = gram_kernel<P, RM, RN, ALGO>;
+  using L = SmemLayout<TXD, TYD, RM, RN>;
+  constexpr int kThreads = TXD * TYD;
+  const size_t smem = L::bytes(prm.symmetric == 1);
+  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO>;
   OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)L::bytes(true)));
   int per_sm = 1;
@@ -310,10 +320,29 @@ static int launch_gram(const GramParams& prm, int sms, cudaStream_t stream) {
   return 0;
 }
 
-template <int P, int RM, int RN>
+template <int P, int TXD, int TYD, int RM, int RN>
 static int launch_algo(const GramParams& prm, int algo, int sms, cudaStream_t stream) {
-  if (algo == OAK_ESP_DIRECT) return launch_gram<P, RM, RN, OAK_ESP_DIRECT>(prm, sms, stream);
-  return launch_gram<P, RM, RN, OAK_ESP_NEWTON_GIRARD>(prm, sms, stream);
+  if (algo == OAK_ESP_DIRECT)
+    return launch_gram<P, TXD, TYD, RM, RN, OAK_ESP_DIRECT>(prm, sms, stream);
+  return launch_gram<P, TXD, TYD, RM, RN, OAK_ESP_NEWTON_GIRARD>(prm, sms, stream);
+}
+
+// depth <= 4: 64x64 tiles; two geometries (selected by OAK_GRAM_VARIANT for experiments):
+//   0: 256 threads (16x16), 4x4 micro-tile, ~226 registers, 8 warps / SM
+//   1: 512 threads (32x16), 4x2 micro-tile, <= 128 registers, 16 warps / SM
+static int gram_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OAK_GRAM_VARIANT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+template <int P>
+static int launch_small_depth(const GramParams& prm, int algo, int sms, cudaStream_t stream) {
+  if (gram_variant() == 0) return launch_algo<P, 16, 16, 4, 4>(prm, algo, sms, stream);
+  return launch_algo<P, 32, 16, 4, 2>(prm, algo, sms, stream);
 }
 
 int tile_rows_for_depth(int depth) { return depth <= 4 ? 64 : 32; }
@@ -363,17 +392,17 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
   const int algo = spec->algo;
   switch (depth) {
     case 0:
-    case 1: return launch_algo<1, 4, 4>(prm, algo, sms, stream);
-    case 2: return launch_algo<2, 4, 4>(prm, algo, sms, stream);
-    case 3: return launch_algo<3, 4, 4>(prm, algo, sms, stream);
-    case 4: return launch_algo<4, 4, 4>(prm, algo, sms, stream);
-    case 5: return launch_algo<5, 2, 2>(prm, algo, sms, stream);
-    case 6: return launch_algo<6, 2, 2>(prm, algo, sms, stream);
-    case 7: return launch_algo<7, 2, 2>(prm, algo, sms, stream);
-    case 8: return launch_algo<8, 2, 2>(prm, algo, sms, stream);
+    case 1: return launch_small_depth<1>(prm, algo, sms, stream);
+    case 2: return launch_small_depth<2>(prm, algo, sms, stream);
+    case 3: return launch_small_depth<3>(prm, algo, sms, stream);
+    case 4: return launch_small_depth<4>(prm, algo, sms, stream);
+    case 5: return launch_algo<5, 16, 16, 2, 2>(prm, algo, sms, stream);
+    case 6: return launch_algo<6, 16, 16, 2, 2>(prm, algo, sms, stream);
+    case 7: return launch_algo<7, 16, 16, 2, 2>(prm, algo, sms, stream);
+    case 8: return launch_algo<8, 16, 16, 2, 2>(prm, algo, sms, stream);
     default:
-      if (depth <= 12) return launch_algo<12, 2, 2>(prm, algo, sms, stream);
-      return launch_algo<16, 2, 2>(prm, algo, sms, stream);
+      if (depth <= 12) return launch_algo<12, 16, 16, 2, 2>(prm, algo, sms, stream);
+      return launch_algo<16, 16, 16, 2, 2>(prm, algo, sms, stream);
   }
 }
 
