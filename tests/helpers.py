@@ -71,3 +71,28 @@ def mixed_config(n=200, seed=0, depth=3, share=True):
     y = (np.sin(X[:, 0]) + X[:, 4] + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
     return dict(X=X, y=y, Z=X[: max(n // 4, 3)].copy(), dims=dims, depth=depth, variances=var, share_var=share,
                 noise=0.05)
+
+
+def load_golden(name):
+    """(cfg, arrays) of a golden file produced by tests/golden/make_golden.py from the reference."""
+    import json
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    z = np.load(path, allow_pickle=False)
+    cfg = json.loads(str(z["cfg"]))
+
+    def fix(c):
+        for d in c.get("dims", []):
+            if d.get("measure") is not None:
+                d["measure"] = tuple(np.asarray(v) if isinstance(v, list) else v for v in d["measure"])
+            for key in ("p", "W", "kappa"):
+                if key in d:
+                    d[key] = np.asarray(d[key], dtype=np.float64)
+        return c
+
+    if "dims" in cfg:
+        cfg = fix(cfg)
+    else:
+        cfg = {k: fix(v) for k, v in cfg.items()}
+    return cfg, {k: z[k] for k in z.files if k != "cfg"}

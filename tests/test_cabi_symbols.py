@@ -1,0 +1,61 @@
+"""The C-ABI library loads without a GPU and exports exactly what include/oak_b200.h declares;
+compute calls fail loudly without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "oak_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(oak_[A-Za-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from oak_b200 import _cabi
+
+    lib = _cabi.load()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/oak_b200.h but not exported"
+    assert sorted(_cabi.SIGNATURES) == names, "ctypes signatures out of sync with the header"
+    assert lib.oak_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from oak_b200 import _cabi
+
+    assert ctypes.sizeof(_cabi.DimDesc) == 6 * 4 + 4 * 8 + 3 * 8
+    assert ctypes.sizeof(_cabi.KernelDesc) == 4 * 4 + 2 * 8
+
+
+def test_compute_fails_loudly_without_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from oak_b200 import _cabi
+    from oak_b200.oak_kernel import OAKKernel
+    from oak_b200.ortho_rbf_kernel import RBF
+
+    assert _cabi.load().oak_device_count() == 0
+    k = OAKKernel([RBF, RBF], num_dims=2, max_interaction_depth=2, constrain_orthogonal=True)
+    with pytest.raises(_cabi.OakNativeError):
+        k.K(np.zeros((4, 2)))
+    with pytest.raises(_cabi.OakNativeError):
+        _cabi.Spec([_cabi.DimSpec(_cabi.DIM_RBF, 0, measure=_cabi.MEASURE_GAUSSIAN, m1=1.0)], 1, [0.0, 1.0])
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "orthogonal-additive-gaussian-processes_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

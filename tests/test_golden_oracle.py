@@ -1,0 +1,77 @@
+"""Pins the NumPy oracle against the golden vectors produced by the reference's own sources
+(tests/golden/make_golden.py).  CPU only."""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import build_oracle, load_golden, max_rel_err
+from oracle import oak_oracle as oo
+
+TIGHT = 1e-12  # same formulas, same op order (expanded RBF): rounding-level agreement
+KERNEL_CASES = ["g1_gaussian_d5_p3", "g2_mixed_p2", "g3_no_share_var", "g4_unconstrained"]
+
+
+@pytest.mark.parametrize("name", KERNEL_CASES)
+def test_oracle_kernel_matches_reference(name):
+    cfg, g = load_golden(name)
+    ref = build_oracle(cfg, expanded=True)
+    X, X2 = g["X"], g["X2"]
+    assert max_rel_err(ref.K(X), g["K"]) < TIGHT
+    assert max_rel_err(ref.K(X, X2), g["K_cross"]) < TIGHT
+    assert max_rel_err(ref.K_diag(X), g["K_diag"]) < TIGHT
+    subsets = json.loads(str(g["subsets_json"]))
+    assert subsets == oo.subsets(X.shape[1], cfg["depth"])
+    for slot, ci in enumerate(g["component_index"]):
+        S = subsets[int(ci)]
+        assert max_rel_err(ref.component_K(S, X, X2), g["component_K"][slot]) < TIGHT
+        assert max_rel_err(ref.component_K_diag(S, X), g["component_K_diag"][slot]) < TIGHT
+    # the direct (x-y)^2 form used by the CUDA tiles agrees with the reference's expanded form
+    assert max_rel_err(build_oracle(cfg, expanded=False).K(X, X2), g["K_cross"]) < 1e-11
+
+
+def test_oracle_single_kernels_match_reference():
+    cfgs, g = load_golden("g5_single_kernels")
+    for name in ("gaussian", "uniform", "empirical", "mog"):
+        k = build_oracle(cfgs[name], expanded=True).dims[0]
+        xin = g["xe"] if name == "empirical" else g["x"]
+        assert max_rel_err(k.K(xin, g["x2"]), g[f"{name}_K"]) < TIGHT
+        assert max_rel_err(k.K_diag(xin), g[f"{name}_Kdiag"]) < TIGHT
+        assert max_rel_err(k.cov_X_s(xin), g[f"{name}_cov"]) < TIGHT
+        assert abs(k.var_s() - float(g[f"{name}_var"])) < TIGHT * abs(float(g[f"{name}_var"]))
+
+
+def test_oracle_models_and_sobol_match_reference():
+    cfg, g = load_golden("g6_models_sobol")
+    ref = build_oracle(cfg, expanded=True)
+    X, Y, Z, Xt, noise = g["X"], g["Y"], g["Z"], g["Xtest"], float(g["noise"])
+    a_gpr = oo.gpr_alpha(ref, X, Y, noise)
+    a_sgpr = oo.sgpr_alpha(ref, X, Y, Z, noise)
+    assert max_rel_err(a_gpr, g["gpr_alpha"]) < 1e-9
+    assert max_rel_err(a_sgpr, g["sgpr_alpha"]) < 1e-7
+    idx, sob = oo.sobol_oak(ref, X, g["gpr_alpha"])
+    assert idx == json.loads(str(g["gpr_sobol_index_json"]))
+    assert max_rel_err(sob, g["gpr_sobol"]) < 1e-10
+    _, sob = oo.sobol_oak(ref, Z, g["sgpr_alpha"])
+    assert max_rel_err(sob, g["sgpr_sobol"]) < 1e-10
+    assert max_rel_err(np.array(oo.predict_components(ref, X, g["gpr_alpha"], Xt)), g["gpr_components"]) < 1e-10
+    assert max_rel_err(np.array(oo.predict_components(ref, Z, g["sgpr_alpha"], Xt)), g["sgpr_components"]) < 1e-10
+    assert abs(oo.gpr_log_marginal_likelihood(ref, X, Y, noise) - float(g["restated_gpr_objective"])) < 1e-9
+    assert abs(oo.sgpr_elbo(ref, X, Y, Z, noise) - float(g["restated_sgpr_objective"])) < 1e-8
+    assert max_rel_err(oo.gpr_predict_mean(ref, X, Y, noise, Xt), g["restated_gpr_predict_mean"]) < 1e-9
+    assert max_rel_err(oo.sgpr_predict_mean(ref, X, Y, Z, noise, Xt), g["restated_sgpr_predict_mean"]) < 1e-8
+    # individual L builders
+    assert max_rel_err(oo.L_gaussian(X[:, 0], 1.3, 2.0, 1.0, 0.0), g["L_gaussian"]) < TIGHT
+    assert max_rel_err(oo.L_binary(X[:, 2], 0.6, 2.0), g["L_binary"]) < TIGHT
+    p3 = np.asarray(cfg["dims"][3]["p"]).reshape(-1, 1)
+    assert max_rel_err(oo.L_categorical(X[:, 3], np.array([[0.2, 0.9], [0.7, 0.1], [0.5, 0.6]]),
+                                        np.array([1.0, 0.8, 1.2]), p3, 2.0), g["L_categorical"]) < TIGHT
+
+
+def test_oracle_empirical_sobol_matches_reference():
+    cfg, g = load_golden("g7_empirical_sobol")
+    ref = build_oracle(cfg, expanded=True)
+    _, sob = oo.sobol_oak(ref, g["Z"], g["alpha"])
+    assert max_rel_err(sob, g["sobol"]) < 1e-10
+    assert max_rel_err(oo.sgpr_alpha(ref, g["X"], g["Y"], g["Z"], float(g["noise"])), g["alpha"]) < 1e-6
+    assert abs(oo.sgpr_elbo(ref, g["X"], g["Y"], g["Z"], float(g["noise"])) - float(g["restated_objective"])) < 1e-7 * abs(float(g["restated_objective"]))

@@ -1,0 +1,142 @@
+"""Host-side logic that needs no GPU: parameter transforms, kernel construction and its error
+behaviour (mirrors the reference's checks), spec packing, row partitioning."""
+import numpy as np
+import pytest
+
+from oak_b200 import _cabi
+from oak_b200._gpflow_shim import Parameter, Sigmoid, collect_parameters, positive
+from oak_b200.input_measures import EmpiricalMeasure, GaussianMeasure, MOGMeasure, UniformMeasure
+from oak_b200.oak_kernel import KernelComponenent, OAKKernel, bounded_param, get_list_representation
+from oak_b200.ortho_binary_kernel import OrthogonalBinary
+from oak_b200.ortho_categorical_kernel import OrthogonalCategorical
+from oak_b200.ortho_rbf_kernel import RBF, OrthogonalRBFKernel
+from oak_b200.parallel import balanced_symmetric_rows, partition_rows
+
+
+def test_parameter_transforms_round_trip():
+    p = Parameter(1.0, transform=positive())
+    assert abs(float(p) - 1.0) < 1e-15
+    p.assign(1e-16)
+    assert abs(float(p) - 1e-16) < 1e-25
+    b = bounded_param(1e-3, 1e3, 1.0)
+    assert abs(float(b) - 1.0) < 1e-12
+    b.assign(500.0)
+    assert abs(float(b) - 500.0) < 1e-9
+    assert isinstance(b.transform, Sigmoid)
+
+
+def test_oak_kernel_structure_matches_reference_constructor():
+    p_cat = np.array([0.2, 0.3, 0.5]).reshape(-1, 1)
+    loc = np.array([[0.1], [0.5], [0.9]])
+    k = OAKKernel([RBF, RBF, None, None, RBF], num_dims=5, max_interaction_depth=2, constrain_orthogonal=True,
+                  p0=[None, None, 0.3, None, None], p=[None, None, None, p_cat, None],
+                  lengthscale_bounds=[1e-3, 1e3],
+                  empirical_locations=[None, loc, None, None, None], empirical_weights=None,
+                  gmm_measures=[None, None, None, None, MOGMeasure(np.array([0.0, 1.0]), np.array([1.0, 2.0]),
+                                                                   np.array([0.5, 0.5]))])
+    kinds = [type(s).__name__ for s in k.kernels]
+    assert kinds == ["OrthogonalRBFKernel", "OrthogonalRBFKernel", "OrthogonalBinary", "OrthogonalCategorical",
+                     "OrthogonalRBFKernel"]
+    assert isinstance(k.kernels[0].measure, GaussianMeasure) and k.kernels[0].measure.var == 1
+    assert isinstance(k.kernels[1].measure, EmpiricalMeasure)
+    assert isinstance(k.kernels[4].measure, MOGMeasure)
+    assert len(k.variances) == 3
+    # Gaussian-measure dims get a constant unit variance, empirical / MOG dims keep a Parameter
+    assert isinstance(k.kernels[0].base_kernel.variance, np.ndarray)
+    assert isinstance(k.kernels[1].base_kernel.variance, Parameter)
+    assert isinstance(k.kernels[0].base_kernel.lengthscales.transform, Sigmoid)
+    specs = k._dim_specs()
+    assert [s.type for s in specs] == [0, 0, 1, 2, 0]
+    assert [s.column for s in specs] == [0, 1, 2, 3, 4]
+    assert [s.measure for s in specs] == [_cabi.MEASURE_GAUSSIAN, _cabi.MEASURE_EMPIRICAL, 0, 0, _cabi.MEASURE_MOG]
+    assert specs[3].count == 3 and specs[3].rank == 2 and specs[1].count == 3
+    # trainable parameters: 3 lengthscales, 2 base variances, W, kappa, binary/cat variance are constants
+    names = collect_parameters(k)
+    assert len(names) == 3 + 2 + 2 + 3
+
+
+def test_share_var_false_has_single_variance():
+    k = OAKKernel([RBF] * 3, num_dims=3, max_interaction_depth=3, constrain_orthogonal=True,
+                  share_var_across_orders=False)
+    assert len(k.variances) == 1
+    assert all(isinstance(s.base_kernel.variance, Parameter) for s in k.kernels)
+
+
+def test_constructor_errors_match_reference():
+    with pytest.raises(ValueError):  # both empirical and GMM measure on one input (oak_kernel.py:136-138)
+        OAKKernel([RBF], num_dims=1, max_interaction_depth=1, constrain_orthogonal=True,
+                  empirical_locations=[np.array([[0.0], [1.0]])], empirical_weights=None,
+                  gmm_measures=[MOGMeasure(np.array([0.0]), np.array([1.0]), np.array([1.0]))])
+    with pytest.raises(AssertionError):  # duplicate active dims (:80-82)
+        OAKKernel([RBF, RBF], num_dims=2, max_interaction_depth=1, active_dims=[[0], [0]])
+    with pytest.raises(AssertionError):  # empirical locations without the orthogonal constraint (:192-197)
+        OAKKernel([RBF], num_dims=1, max_interaction_depth=1, constrain_orthogonal=False,
+                  empirical_locations=[np.array([[0.0]])])
+    with pytest.raises(NotImplementedError):  # non-RBF base kernel (ortho_rbf_kernel.py:34-35)
+        OrthogonalRBFKernel(OrthogonalBinary(), GaussianMeasure(0, 1))
+    with pytest.raises(NotImplementedError):  # unknown measure (:36-45)
+        OrthogonalRBFKernel(RBF(), object())
+    with pytest.raises(AssertionError):  # weights must sum to one (input_measures.py:53-55)
+        EmpiricalMeasure(np.zeros((3, 1)), np.ones((3, 1)))
+    with pytest.raises(AssertionError):
+        MOGMeasure(np.array([0.0, 1.0]), np.array([1.0, 1.0]), np.array([0.7, 0.7]))
+    with pytest.raises(ValueError):  # depth beyond what the register-tiled kernels support
+        OAKKernel([RBF] * 20, num_dims=20, max_interaction_depth=17)
+
+
+def test_shape_validation_of_sub_kernels():
+    k = OrthogonalRBFKernel(RBF(), UniformMeasure(0, 1))
+    with pytest.raises(ValueError):
+        k.K(np.zeros((4, 2)))
+    with pytest.raises(ValueError):
+        OrthogonalBinary().K(np.zeros((4, 2)))
+    with pytest.raises(ValueError):
+        OrthogonalCategorical(p=np.array([[0.5], [0.5]])).K_diag(np.zeros((4,)))
+    with pytest.raises(ValueError):  # full_cov=False with X2 (gpflow Kernel.__call__)
+        k(np.zeros((3, 1)), np.zeros((3, 1)), full_cov=False)
+
+
+def test_list_representation_order():
+    k = OAKKernel([RBF] * 4, num_dims=4, max_interaction_depth=3, constrain_orthogonal=True)
+    sel, kl = get_list_representation(k, num_dims=4)
+    assert sel[:6] == [[], [0], [1], [2], [3], [0, 1]]
+    assert len(sel) == 1 + 4 + 6 + 4 and len(kl) == len(sel)
+    assert all(isinstance(c, KernelComponenent) for c in kl)
+    assert [len(c.kernels) for c in kl] == [len(s) for s in sel]
+    k0 = OAKKernel([RBF], num_dims=1, max_interaction_depth=0, constrain_orthogonal=True)
+    assert get_list_representation(k0, num_dims=1)[0] == [[]]
+
+
+def test_spec_variance_count_is_validated():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("needs the no-device path to stay cheap")
+    with pytest.raises((_cabi.OakNativeError, ValueError)):
+        _cabi.Spec([_cabi.DimSpec(_cabi.DIM_RBF, 0)], 3, [1.0], share_var=True)
+
+
+@pytest.mark.parametrize("n,world", [(0, 1), (1, 4), (63, 2), (64, 2), (1000, 8), (65536, 8), (1_000_000, 8), (129, 3)])
+def test_partition_rows_covers_and_aligns(n, world):
+    parts = partition_rows(n, world)
+    assert len(parts) == world
+    assert parts[0][0] == 0 and parts[-1][1] == n
+    for (b0, e0), (b1, e1) in zip(parts, parts[1:]):
+        assert e0 == b1
+    for b, e in parts:
+        assert b <= e and (b % 64 == 0 or b == n)
+    sizes = [e - b for b, e in parts]
+    assert max(sizes) - min(sizes) <= 64 or n < 64 * world
+
+
+@pytest.mark.parametrize("n,world", [(1100, 2), (65536, 8), (4096, 4)])
+def test_balanced_symmetric_rows_balance_the_triangle(n, world):
+    strips = balanced_symmetric_rows(n, world)
+    seen = sorted(s for r in strips for s in r if s[1] > s[0])
+    assert seen[0][0] == 0 and seen[-1][1] == n
+    for (b0, e0), (b1, e1) in zip(seen, seen[1:]):
+        assert e0 == b1
+    work = [sum((e - b) * (b + e + 1) / 2 for b, e in r) for r in strips]
+    assert sum(work) == n * (n + 1) / 2
+    if n >= 4096:
+        assert max(work) / min(work) < 1.1
