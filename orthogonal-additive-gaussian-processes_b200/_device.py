@@ -200,7 +200,7 @@ def component_predict(spec: Spec, subsets: Sequence[Sequence[int]], px: Points, 
 
 
 # ---- SGPR / GPR -------------------------------------------------------------------------
-def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 8192, stats=None):
+def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 65536, stats=None):
     """Accumulates Phi | Kuf y | sum K_diag | y^T y for the local points into ``stats``."""
     torch = _torch()
     lib = _cabi.load()

@@ -48,11 +48,9 @@ struct SmemLayout {
   static constexpr int TM = TYD * RM, TN = TXD * RN;
   static constexpr int kTabDoubles = kExpTab * 16;
   static constexpr int kStageDouble2 = kDimChunk * (TM + TN);
-  static constexpr int kMirrorStride = TM + 1;  // odd stride: conflict-free column reads
-  static constexpr size_t bytes(bool symmetric) {
+  static constexpr size_t bytes(bool /*symmetric*/) {
     return sizeof(double) * kTabDoubles + 2 * sizeof(double2) * kStageDouble2 +
-           2 * sizeof(double) * kDimChunk +
-           (symmetric ? sizeof(double) * (size_t)TN * kMirrorStride : 0);
+           2 * sizeof(double) * kDimChunk;
   }
 };
 
@@ -142,7 +140,6 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
   double* sTab = reinterpret_cast<double*>(smem_raw);
   double2* sStage = reinterpret_cast<double2*>(sTab + L::kTabDoubles);
   double* sAux = reinterpret_cast<double*>(sStage + 2 * L::kStageDouble2);
-  double* sMirror = sAux + 2 * kDimChunk;
 
   const int tid = threadIdx.x;
   const int tx = tid % TXD, ty = tid / TXD;
@@ -233,7 +230,7 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
         const double nls = aux[dl];
         double2 rv[RM], cv[RN];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty + TYD * r];
+        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
 #pragma unroll
         for (int c = 0; c < RN; ++c) cv[c] = colp[tx + TXD * c];
 #pragma unroll
@@ -254,7 +251,7 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
         const double* tbl = prm.tables + (int)__double_as_longlong(aux[dl]);
         int ro[RM], co[RN];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty + TYD * r].x);
+        for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty * RM + r].x);
 #pragma unroll
         for (int c = 0; c < RN; ++c) co[c] = __double2loint(colp[tx + TXD * c].x);
 #pragma unroll
@@ -272,30 +269,34 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
     const int64_t col0 = bj * TN;
     const int64_t nrows = prm.row_end - prm.row_begin;
     const bool mirror = prm.symmetric == 1 && (bi + prm.tile_row0 != bj);
+    // A thread owns RM consecutive rows (ty*RM + r): in the mirrored (transposed) tile these
+    // are RM consecutive columns, i.e. whole 32-byte sectors per thread, written straight from
+    // registers with 16-byte streaming stores -- no shared-memory transpose, no extra barrier.
+    const bool vec_ok = (RM % 2 == 0) && ((prm.ldk & 1) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(prm.K) & 15) == 0);
 #pragma unroll
-    for (int r = 0; r < RM; ++r) {
-      const int64_t row = row0 + ty + TYD * r;
+    for (int c = 0; c < RN; ++c) {
+      const int64_t col = col0 + tx + TXD * c;
+      double v[RM];
 #pragma unroll
-      for (int c = 0; c < RN; ++c) {
-        const int64_t col = col0 + tx + TXD * c;
-        const double v = finish<P, ALGO>(acc[r][c], prm.sigma2);
-        if (row < nrows && col < prm.n2) __stcs(prm.K + row * prm.ldk + col, v);
-        if (mirror) sMirror[(tx + TXD * c) * L::kMirrorStride + (ty + TYD * r)] = v;
+      for (int r = 0; r < RM; ++r) {
+        const int64_t row = row0 + ty * RM + r;
+        v[r] = finish<P, ALGO>(acc[r][c], prm.sigma2);
+        if (row < nrows && col < prm.n2) __stcs(prm.K + row * prm.ldk + col, v[r]);
       }
-    }
-    if (mirror) {
-      __syncthreads();
-      // transposed tile: row (col0 + cc) of K, columns row0 .. row0+TM
-      const int warp = tid >> 5, lane = tid & 31;
-      for (int cc = warp; cc < TN; cc += kThreads / 32) {
-        const int64_t orow = col0 + cc;
-        if (orow >= nrows) break;
-        for (int rr = lane; rr < TM; rr += 32) {
-          const int64_t ocol = row0 + rr;
-          if (ocol < prm.n2) __stcs(prm.K + orow * prm.ldk + ocol, sMirror[cc * L::kMirrorStride + rr]);
+      if (mirror && col < nrows) {
+        const int64_t ocol0 = row0 + ty * RM;  // columns of the mirrored row `col`
+        double* dst = prm.K + col * prm.ldk + ocol0;
+        if (vec_ok && ocol0 + RM <= prm.n2) {
+#pragma unroll
+          for (int r = 0; r + 1 < RM; r += 2)
+            __stcs(reinterpret_cast<double2*>(dst + r), make_double2(v[r], v[r + 1]));
+        } else {
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+            if (ocol0 + r < prm.n2) __stcs(dst + r, v[r]);
         }
       }
-      // the next stage's __syncthreads orders these reads before the next tile's writes
     }
   }
   cp_async_wait_all();
@@ -334,7 +335,7 @@ static int gram_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("OAK_GRAM_VARIANT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;  // measured: variant 0 is 2-3 % faster on B200 (profiles/)
   }
   return v;
 }

@@ -13,6 +13,7 @@
 #include <cusolverDn.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 #include "oak_common.cuh"
@@ -173,6 +174,48 @@ __global__ void gpr_lml_kernel(const double* scalars, const double* y, const dou
 // work layout shared by the finish functions: [int devInfo | pad][8 scalars][potrf workspace]
 constexpr size_t kFinishHeader = 16 + 8 * sizeof(double);
 
+// C(lower, column-major M x M) += A'^T A' with A' column-major (k x M, lda).  cuBLAS DSYRK runs
+// at full-GEMM cost on this shape (measured on B200), so the triangle is cut recursively into
+// off-diagonal rectangles (plain DGEMM, the efficient path) and small diagonal blocks:
+//   OAK_SYRK_MODE=0 one DSYRK | 1,2,3 recursion depth (default 1) | 9 one full DGEMM
+static int syrk_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OAK_SYRK_MODE");
+    v = e ? atoi(e) : 1;  // measured on B200 (scripts/quick_sgpr.py): depth 1 is fastest
+  }
+  return v;
+}
+
+static int syrk_rec(cublasHandle_t cb, int off, int m, int k, const double* A, int lda, double* C,
+                    int ldc, int depth) {
+  const double one = 1.0;
+  if (depth == 0 || m < 128 || (m & 1)) {
+    OAK_CUBLAS(cublasDsyrk(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, m, k, &one, A + (size_t)off * lda, lda,
+                           &one, C + (size_t)off * ldc + off, ldc));
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  const int h = m / 2;
+  // C[off+h : off+m, off : off+h] += A'[:, off+h:off+m]^T A'[:, off:off+h]
+  OAK_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, m - h, h, k, &one, A + (size_t)(off + h) * lda, lda,
+                         A + (size_t)off * lda, lda, &one, C + (size_t)off * ldc + off + h, ldc));
+  g_launches.fetch_add(1);
+  if (int rc = syrk_rec(cb, off, h, k, A, lda, C, ldc, depth - 1)) return rc;
+  return syrk_rec(cb, off + h, m - h, k, A, lda, C, ldc, depth - 1);
+}
+
+static int syrk_lower_accumulate(cublasHandle_t cb, int m, int k, const double* A, int lda, double* C) {
+  const int mode = syrk_mode();
+  if (mode == 9) {
+    const double one = 1.0;
+    OAK_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, m, m, k, &one, A, lda, A, lda, &one, C, m));
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  return syrk_rec(cb, 0, m, k, A, lda, C, m, mode);
+}
+
 static int potrf_lwork(cusolverDnHandle_t cs, int n, int* lwork) {
   OAK_CUSOLVER(cusolverDnDpotrf_bufferSize(cs, CUBLAS_FILL_MODE_LOWER, n, nullptr, n, lwork));
   return 0;
@@ -221,9 +264,7 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
       return rc;
     // Phi += Kuf Kuf^T.  Row-major (M x nc, ld=chunk) == column-major (nc x M, lda=chunk) A';
     // Phi = A'^T A'  ->  DSYRK(trans = T).  Only one triangle is updated.
-    OAK_CUBLAS(cublasDsyrk(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, (int)m, (int)nc, &one, kuf,
-                           (int)chunk, &one, phi, (int)m));
-    g_launches.fetch_add(1);
+    if (int rc = syrk_lower_accumulate(cb, (int)m, (int)nc, kuf, (int)chunk, phi)) return rc;
     // Kuf_y += Kuf y_chunk = A'^T y
     OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, (int)nc, (int)m, &one, kuf, (int)chunk, d_y + c0, 1, &one,
                            kufy, 1));

@@ -85,8 +85,13 @@ def test_cuda_sobol_quadforms_with_reference_alpha():
     from oak_b200 import _device
     from oak_b200.workloads import build_kernel
 
-    for name, key_a, key_s, key_x in (("g6_models_sobol", "sgpr_alpha", "sgpr_sobol", "Z"),
-                                      ("g7_empirical_sobol", "alpha", "sobol", "Z")):
+    # g7 (empirical measure, variances 1e-3/90/15, lengthscales 2 and 5 on unit-scale data) is
+    # ill-conditioned: k~ = k - c c'/v cancels ~4 digits, and the reference's own float64 result
+    # (expanded squared distance) sits 1.2e-7 away from an np.longdouble evaluation of the same
+    # formulas (1.43422282 vs 1.43422264; see DESIGN.md "conditioning").  The CUDA tiles use the
+    # direct (x-y)^2 form and land between the two, so this case is held to 1e-6, not 1e-9.
+    for name, key_a, key_s, key_x, tol in (("g6_models_sobol", "sgpr_alpha", "sgpr_sobol", "Z", RTOL),
+                                           ("g7_empirical_sobol", "alpha", "sobol", "Z", 1e-6)):
         cfg, g = load_golden(name)
         k = build_kernel(cfg)
         spec = k._make_spec()
@@ -102,4 +107,4 @@ def test_cuda_sobol_quadforms_with_reference_alpha():
             scales.append(v if cfg["dims"][S[0]]["type"] == "binary" else v ** 2)
         sob = _device.sobol_quadforms(Ls, comps, scales, _device.to_device(g[key_a])).cpu().numpy()
         spec.close()
-        assert max_rel_err(sob, g[key_s]) < RTOL
+        assert max_rel_err(sob, g[key_s]) < tol
