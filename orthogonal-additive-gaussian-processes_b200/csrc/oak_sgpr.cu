@@ -91,19 +91,21 @@ __global__ void symmetrize_kernel(double* A, int64_t n) {
 }
 
 // B = AAT / noise + I in place; scalars[1] = trace(AAT / noise)
-__global__ void __launch_bounds__(1024) scale_add_identity_kernel(double* A, int64_t n,
-                                                                  double inv_noise, double* scalars) {
+__global__ void scale_add_identity_kernel(double* A, int64_t n, double inv_noise) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int64_t r = idx / n, c = idx - r * n;
+  double v = A[idx] * inv_noise;
+  if (r == c) v += 1.0;
+  A[idx] = v;
+}
+
+// scalars[1] = trace(A) * inv_noise (fixed summation order, one block)
+__global__ void __launch_bounds__(1024) scaled_trace_kernel(const double* A, int64_t n,
+                                                            double inv_noise, double* scalars) {
   __shared__ double sh[1024];
   double tr = 0.0;
-  for (int64_t idx = threadIdx.x; idx < n * n; idx += 1024) {
-    const int64_t r = idx / n, c = idx - r * n;
-    double v = A[idx] * inv_noise;
-    if (r == c) {
-      tr += v;
-      v += 1.0;
-    }
-    A[idx] = v;
-  }
+  for (int64_t i = threadIdx.x; i < n; i += 1024) tr += A[i * n + i] * inv_noise;
   sh[threadIdx.x] = tr;
   __syncthreads();
   for (int s = 512; s > 0; s >>= 1) {
@@ -332,7 +334,9 @@ extern "C" int oak_sgpr_finish_f64(double* d_Kuu, double* d_stats, int64_t m, in
   OAK_CUBLAS(cublasDtrsm(cb, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T,
                          CUBLAS_DIAG_NON_UNIT, M, M, &one, d_Kuu, M, phi, M));
   // B = AAT + I, trace(AAT); LB = chol(B)   (utils.py:190-193)
-  scale_add_identity_kernel<<<1, 1024, 0, stream>>>(phi, m, 1.0 / noise, scalars);
+  scaled_trace_kernel<<<1, 1024, 0, stream>>>(phi, m, 1.0 / noise, scalars);
+  OAK_LAUNCHED();
+  scale_add_identity_kernel<<<(unsigned)((m * m + 255) / 256), 256, 0, stream>>>(phi, m, 1.0 / noise);
   OAK_LAUNCHED();
   OAK_CUSOLVER(cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, M, phi, M, potrf_ws, lwork, info));
   log_diag_sum_kernel<<<1, 1024, 0, stream>>>(phi, m, m, scalars, 0);
