@@ -56,6 +56,7 @@ struct DimDev {
                       // C-entry diagonal follows it
   int32_t orig;       // index of this sub-kernel in the caller's ordering
   double inv_sqrt2_l; // 1 / (sqrt(2) l)
+  double xscale;      // sqrt(256 / ln 2) / (sqrt(2) l): factor of the prepared coordinate
   double neg_log_s2;  // -ln(s^2)
   double s2;          // base variance
   double lengthscale;
@@ -88,7 +89,8 @@ struct oak_spec {
   double* d_sobolG = nullptr;
   oak::DimDev* d_dims = nullptr;
   double* d_inv_sqrt_v = nullptr;      // [D] 1/sqrt(var_s) per RBF dim (0 if unconstrained)
-  double* d_neg_log_s2 = nullptr;      // [D]
+  double* d_neg_log_s2 = nullptr;      // [D] RBF: -ln s^2 ; discrete: bits(table offset)
+  double* d_gram_aux = nullptr;        // [D] RBF: -ln(s^2) 256/ln2 ; discrete: bits(table offset)
   double* d_tables = nullptr;          // discrete tables blob
   int tables_len = 0;
   double* d_blob = nullptr;            // per-measure arrays
@@ -100,46 +102,73 @@ const double* exp_table_device();  // lazily uploaded per device; nullptr on fai
 
 // Internal launchers shared between translation units (device pointers; see oak_gram.cu).
 int tile_rows_for_depth(int depth);
+// `prow` / `pcol` are the BASES of two prepared-point blocks (their min/max keys follow the
+// coordinates, see points_minmax); row/column ranges select the part to evaluate.
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream);
+// per-dimension min / max keys of the prepared coordinate: [D] min keys then [D] max keys
+inline const unsigned long long* points_minmax(const oak_spec* spec, const double2* pts, int64_t n_pad) {
+  return reinterpret_cast<const unsigned long long*>(pts + (int64_t)spec->D * n_pad);
+}
 int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_t n_pad,
                      double* out, cudaStream_t stream);
 
-// ---- fast FP64 exp(-z) ---------------------------------------------------------------
-// Table-driven: -z = n ln2/256 + r, |r| <= ln2/512, exp(-z) = 2^(n>>8) * T[n&255] * e^r with a
-// degree-4 Taylor polynomial (truncation 3.8e-17 relative).  8 FP64-pipe instructions; the
-// index arithmetic, the clamp and the exponent insertion run on the integer pipe.  The
-// single-step reduction leaves |z| * 1.1e-16 relative error (<= 8e-14 at the clamp), far
-// inside the 1e-9 parity budget.  `tab` points at this lane's replica of the table in
-// shared memory: entry j lives at tab[j * 16] so that a half-warp never conflicts.
+// ---- fast FP64 exp(-z) on pre-scaled distances ---------------------------------------
+// Prepared RBF coordinates carry the factor sqrt(256 / ln 2): with d = a_i - b_j,
+//   d^2 = z * 256 / ln 2,  z = (x - y)^2 / (2 l^2)
+// so that n = -round(d^2) is the table/exponent index and w = d^2 + n (|w| <= 1/2, EXACT: both
+// products are fused) gives the reduced argument r = -w ln2/256:
+//   exp(-z) = 2^(n >> 8) * T[n & 255] * e^r,   e^r - 1 = w (C1 + w (C2 + w (C3 + w C4)))
+// 256-entry table of 2^(j/256), degree-4 polynomial (truncation 3.8e-17 relative).
+// Fast form: 9 FP64-pipe instructions from d (was 10 from z), no clamp; valid for d^2 <= 261120
+// (z <= 707), which the launcher proves per dimension from the min/max of the prepared coordinates.
+// General form (s^2 != 1 or unbounded distance): zs = d^2 - ln(s^2) 256/ln2 clamped at 261120.
+//
+// Measured on B200 (scripts/ubench, profiles/): integer-ALU instructions (LOP3/SHF/LEA/IADD3/
+// VIMNMX) steal issue cycles from the FP64 pipe, IMAD (FMA pipe) does not.  The index math is
+// therefore IMAD only:
+//   off = mulhi(n << 24, 2^15) + lane_bits = (n & 255) * 128 + lane_bits   IMAD.SHL + IMAD.HI
+//   hi  = n * 4096 + T'hi[j]                                               IMAD
+// with the table's high words stored pre-compensated, T'hi[j] = hi(2^(j/256)) - (j << 12), so
+// that adding n << 12 = (k << 20) + (j << 12) inserts the binary exponent k without masking.
+// `tab_bytes` is the table base in shared memory (entry j, replica lane % 16 at j*128 + (lane%16)*8:
+// a half-warp never bank-conflicts), `lane_bits` = (lane % 16) * 8.
+constexpr double kXScale = 19.217958540583197;      // sqrt(256 / ln 2)
+constexpr double kXScale2 = 369.3299304675746271;   // 256 / ln 2
+constexpr double kLn2Over256 = 0.0027076061740622863;
+constexpr double kFastSpan = 510.0;                 // |d| bound of the clamp-free form (d^2 <= 260100)
 #ifdef __CUDACC__
-// Variant used by the Gram tile.  Measured on B200 (scripts/ubench): a DFMA blocks the issue
-// port for two cycles and integer-ALU instructions (LOP3/SHF/LEA/IADD3) compete with it, while
-// IMAD (FMA pipe) co-issues for free.  The index math is therefore phrased as
-//   off = ((n << 7) & 0x7F80) | lane_bits          IMAD.SHL + one LOP3
-//   hi  = n * 4096 + T'hi[j]                        one IMAD
-// where the table's high words are stored pre-compensated, T'hi[j] = hi(2^(j/256)) - (j << 12),
-// so that adding n << 12 = (k << 20) + (j << 12) inserts the binary exponent k without masking.
-// `tab_bytes` is the table base in shared memory, `lane_bits` = (lane % 16) * 8.
-__device__ __forceinline__ double exp_neg_tile(double z, const unsigned char* __restrict__ tab_bytes,
-                                               unsigned lane_bits) {
-  constexpr double kMagic = 6755399441055744.0;     // 1.5 * 2^52
-  constexpr double kScale = -369.3299304675746271;  // -256 / ln 2
-  constexpr double kStep = 0.0027076061740622863;   // ln 2 / 256
-  constexpr int kHiClamp = 0x40862000;              // hi word of 708.0
-  int hi = __double2hiint(z);
-  hi = min(hi, kHiClamp);  // z <= 708 (sign bit set => negative int => untouched)
-  z = __hiloint2double(hi, __double2loint(z));
-  const double nd = fma(z, kScale, kMagic);
-  const int ni = __double2loint(nd);
-  const double n = nd - kMagic;
-  const double rp = fma(n, kStep, z);  // = -r
-  double p = fma(rp, 1.0 / 24.0, -1.0 / 6.0);
-  p = fma(p, rp, 0.5);
-  p = fma(p, rp, -1.0);
-  const double q = p * rp;  // e^r - 1
-  const unsigned off = (((unsigned)ni * 128u) & 0x7F80u) | lane_bits;
+__device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char* __restrict__ tab_bytes,
+                                           unsigned lane_bits) {
+  constexpr double C1 = -0.0027076061740622863;
+  constexpr double C2 = 3.6655655969101062e-06;
+  constexpr double C3 = -3.3083026805413713e-09;
+  constexpr double C4 = 2.239395190875157e-12;
+  double p = fma(w, C4, C3);
+  p = fma(p, w, C2);
+  p = fma(p, w, C1);
+  const double q = p * w;  // e^r - 1
+#ifndef OAK_IDX_MODE
+#define OAK_IDX_MODE 0  // development switch, see scripts/ubench/fp64_mix3.cu
+#endif
+  unsigned off;
+#if OAK_IDX_MODE == 0    // IMAD.SHL + LEA.HI
+  asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(off) : "r"((unsigned)ni * 16777216u), "r"(lane_bits));
+#elif OAK_IDX_MODE == 1  // IMAD.SHL + IMAD.HI.U32 (multiplier kept opaque in a register)
+  unsigned m15;
+  asm volatile("mov.u32 %0, 32768;" : "=r"(m15));
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(off) : "r"((unsigned)ni * 16777216u), "r"(m15), "r"(lane_bits));
+#elif OAK_IDX_MODE == 2  // IMAD.SHL + IMAD.WIDE.U32, high word
+  unsigned m15;
+  asm volatile("mov.u32 %0, 32768;" : "=r"(m15));
+  unsigned long long wide;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(wide) : "r"((unsigned)ni * 16777216u), "r"(m15),
+      "l"((unsigned long long)lane_bits << 32));
+  off = (unsigned)(wide >> 32);
+#else                    // IMAD.SHL + LOP3 (round-1 form)
+  off = (((unsigned)ni * 128u) & 0x7F80u) | lane_bits;
+#endif
   const uint2 tv = *reinterpret_cast<const uint2*>(tab_bytes + off);
   int thi;
   asm("mad.lo.s32 %0, %1, 4096, %2;" : "=r"(thi) : "r"(ni), "r"((int)tv.y));
@@ -147,37 +176,38 @@ __device__ __forceinline__ double exp_neg_tile(double z, const unsigned char* __
   return fma(t, q, t);
 }
 
-__device__ __forceinline__ double exp_neg(double z, const double* __restrict__ tab) {
-  constexpr double kMagic = 6755399441055744.0;            // 1.5 * 2^52
-  constexpr double kScale = -369.3299304675746271;         // -256 / ln 2
-  constexpr double kStep = 0.0027076061740622863;          // ln 2 / 256
-  constexpr int kHiClamp = 0x40862000;                     // hi word of 708.0
-#ifndef OAK_ABLATE
-#define OAK_ABLATE 0  // development only: 1 no clamp, 2 no table load, 3 no table + no exponent
-#endif
-#if OAK_ABLATE != 1
-  int hi = __double2hiint(z);
-  hi = min(hi, kHiClamp);  // z <= 708 (sign bit set => negative int => untouched)
-  z = __hiloint2double(hi, __double2loint(z));
-#endif
-  double nd = fma(z, kScale, kMagic);
-  int ni = __double2loint(nd);
-  double n = nd - kMagic;
-  double rp = fma(n, kStep, z);  // = -r
-  double p = fma(rp, 1.0 / 24.0, -1.0 / 6.0);
-  p = fma(p, rp, 0.5);
-  p = fma(p, rp, -1.0);
-  double q = p * rp;             // e^r - 1
-#if OAK_ABLATE == 2 || OAK_ABLATE == 3
-  double t = tab[0];
-#else
-  double t = tab[(ni & (kExpTab - 1)) * 16];
-#endif
-#if OAK_ABLATE != 3
-  int thi = __double2hiint(t) + ((ni >> 8) << 20);
-  t = __hiloint2double(thi, __double2loint(t));
-#endif
-  return fma(t, q, t);
+// exp(-d^2 ln2/256) for |d| <= kFastSpan
+__device__ __forceinline__ double exp_neg_sq_fast(double d, const unsigned char* __restrict__ tab_bytes,
+                                                  unsigned lane_bits) {
+  constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  const double nd = fma(-d, d, kMagic);
+  const double n = nd - kMagic;   // -round(d^2)
+  const double w = fma(d, d, n);  // exact
+  return exp_tail(w, __double2loint(nd), tab_bytes, lane_bits);
+}
+
+// exp(-zs ln2/256), zs = d^2 + aux, clamped at zs <= ~261121 (z ~ 707)
+__device__ __forceinline__ double exp_neg_scaled(double zs, const unsigned char* __restrict__ tab_bytes,
+                                                 unsigned lane_bits) {
+  constexpr double kMagic = 6755399441055744.0;
+  constexpr int kHiClamp = 0x410fe000;  // hi word of 261120.0
+  int hi = __double2hiint(zs);
+  hi = min(hi, kHiClamp);  // (sign bit set => negative int => untouched)
+  zs = __hiloint2double(hi, __double2loint(zs));
+  const double nd = kMagic - zs;
+  const double n = nd - kMagic;
+  const double w = zs + n;
+  return exp_tail(w, __double2loint(nd), tab_bytes, lane_bits);
+}
+
+// monotone uint64 keys for atomicMin / atomicMax on doubles
+__device__ __forceinline__ unsigned long long order_key(double x) {
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ULL));
+}
+__device__ __forceinline__ double order_key_decode(unsigned long long k) {
+  const long long b = (k & 0x8000000000000000ULL) ? (long long)(k ^ 0x8000000000000000ULL) : (long long)~k;
+  return __longlong_as_double(b);
 }
 #endif
 

@@ -26,8 +26,8 @@ __device__ __forceinline__ double dim_value(bool discrete, double aux, const dou
     const double* tbl = tables + (int)__double_as_longlong(aux);
     return tbl[__double2hiint(a.x) + __double2loint(b.x)];
   }
-  const double t = a.x - b.x;
-  return fma(-a.y, b.y, exp(-fma(t, t, aux)));
+  const double t = a.x - b.x;  // prepared coordinates carry sqrt(256/ln2)
+  return fma(-a.y, b.y, exp(-fma(t * t, kLn2Over256, aux)));
 }
 
 __global__ void component_gram_kernel(SubsetParams sp, const double* __restrict__ tables,

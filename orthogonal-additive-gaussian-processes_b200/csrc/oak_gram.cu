@@ -17,6 +17,7 @@
 //   * symmetric mode (X2 = X, full row range): only tiles that intersect the lower triangle are
 //     evaluated; each is also written transposed through a padded shared-memory tile so that the
 //     mirrored stores are coalesced.
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_pipeline.h>
 
 #include <cstdlib>
@@ -38,21 +39,51 @@ struct GramParams {
   int64_t n_row_pad, n_col_pad, ldk;
   int64_t row_begin, row_end, col_begin, n2;  // n2 = number of output columns
   int64_t tiles_n, num_tiles;
-  int D, Dc;
+  int D, Dc, device;
   int symmetric;        // 0 general, 1 lower-triangle tiles + mirrored stores, 2 lower trapezoid only
-  int64_t tile_row0;    // global row-block index of row_begin (modes 1, 2)
+  int64_t tile_row0;    // global TN-row-block index of row_begin (modes 1, 2)
+  const unsigned long long* mm_row;  // [2 D] min / max keys of the prepared coordinates, or null
+  const unsigned long long* mm_col;
+  int use_tma;  // symmetric mode: the transposed tile leaves through shared memory + 2-D TMA stores
+                // (needs an even leading dimension and a 16-byte aligned K)
+  alignas(64) CUtensorMap tm_mir;  // K as (cols, rows) f64 tensor, box 16 x TN, 128-byte swizzle
 };
+
+constexpr int kFastWords = 8;  // clamp-free exp flags for the first 256 continuous dims
 
 template <int TXD, int TYD, int RM, int RN>
 struct SmemLayout {
   static constexpr int TM = TYD * RM, TN = TXD * RN;
   static constexpr int kTabDoubles = kExpTab * 16;
   static constexpr int kStageDouble2 = kDimChunk * (TM + TN);
-  static constexpr size_t bytes(bool /*symmetric*/) {
-    return sizeof(double) * kTabDoubles + 2 * sizeof(double2) * kStageDouble2 +
-           2 * sizeof(double) * kDimChunk;
-  }
+  // Staging of the transposed tile (symmetric mode) for the TMA stores: TM/16 sub-tiles of
+  // [TN rows][16 doubles] in the 128-byte swizzle the tensor map declares; two buffers,
+  // 1024-byte aligned.
+  static constexpr int kOutBytes = TM * TN * (int)sizeof(double);
+  static constexpr size_t base_bytes = sizeof(double) * kTabDoubles + 2 * sizeof(double2) * kStageDouble2 +
+                                       2 * sizeof(double) * kDimChunk + sizeof(unsigned) * kFastWords;
+  static constexpr size_t bytes(bool tma) { return base_bytes + (tma ? 1024 + 2 * (size_t)kOutBytes : 0); }
 };
+
+// ---- bulk (TMA) shared -> global copies ---------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, unsigned smem_addr) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(smem_addr)
+               : "memory");
+}
+__device__ __forceinline__ void sts64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(unsigned addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -130,22 +161,28 @@ __device__ __forceinline__ double finish(const double (&a)[P], const double* __r
   return r;
 }
 
-template <int P, int TXD, int TYD, int RM, int RN, int ALGO>
-__global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm) {
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB>
+__global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_constant__ GramParams prm) {
   using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int TM = L::TM, TN = L::TN;
+  constexpr int RS = TN / TM;  // row sub-tiles per TN-sized triangle block (symmetric modes)
   constexpr int kThreads = TXD * TYD;
   static_assert(TXD % 16 == 0, "the exp-table replicas are indexed by lane % 16");
+  static_assert(TN % TM == 0, "triangle blocks are TN x TN");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sTab = reinterpret_cast<double*>(smem_raw);
   double2* sStage = reinterpret_cast<double2*>(sTab + L::kTabDoubles);
   double* sAux = reinterpret_cast<double*>(sStage + 2 * L::kStageDouble2);
+  unsigned* sFast = reinterpret_cast<unsigned*>(sAux + 2 * kDimChunk);
+  // output staging (TMA path only), 1024-byte aligned shared-window addresses
+  const unsigned out_mir = ((unsigned)__cvta_generic_to_shared(smem_raw + L::base_bytes) + 1023u) & ~1023u;
+  int mirror_buf = 0;
 
   const int tid = threadIdx.x;
   const int tx = tid % TXD, ty = tid / TXD;
 
   // replicate the exp table: entry j, replica r at sTab[j*16 + r]
-  // (high words pre-compensated by -(j << 12), see exp_neg_tile)
+  // (high words pre-compensated by -(j << 12), see exp_tail)
   for (int i = tid; i < L::kTabDoubles; i += kThreads) {
     const int j = i >> 4;
     const double v = prm.exptab[j];
@@ -157,38 +194,95 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
   const int D = prm.D, Dc = prm.Dc;
   const int num_chunks = (D + kDimChunk - 1) / kDimChunk;
 
-  auto tile_coords = [&](int64_t t, int64_t& bi, int64_t& bj) {
+  // Which continuous dims may take the clamp-free exp: s^2 == 1 and every |a_i - b_j| of the two
+  // point sets inside kFastSpan (from the min/max keys written by the prepare kernel).
+  for (int i = tid; i < kFastWords; i += kThreads) sFast[i] = 0u;
+  __syncthreads();
+  if (prm.mm_row != nullptr) {
+    for (int d = tid; d < min(Dc, kFastWords * 32); d += kThreads) {
+      const double rmin = order_key_decode(prm.mm_row[d]), rmax = order_key_decode(prm.mm_row[D + d]);
+      const double cmin = order_key_decode(prm.mm_col[d]), cmax = order_key_decode(prm.mm_col[D + d]);
+      const double span = fmax(rmax - cmin, cmax - rmin);
+      if (prm.dim_aux[d] == 0.0 && span <= kFastSpan) atomicOr(&sFast[d >> 5], 1u << (d & 31));
+    }
+  }
+  // (made visible by the first __syncthreads of the stage loop)
+
+  // Tile enumeration.  Symmetric modes: TN x TN blocks of the lower triangle, row-block major
+  // (t' = gb (gb+1)/2 + bj with the global row-block index gb; tile_row0 > 0 for a sharded lower
+  // trapezoid), each block cut into RS row sub-tiles of TM rows.  General mode: row-major tiles.
+  // The closed form (one FP64 sqrt / one 64-bit division) runs once per CTA; a CTA then advances
+  // by gridDim.x tiles with a few integer operations.
+  int64_t tb = 0, tj = 0;  // block row (global) / block column, or tile row / tile column
+  int th = 0;              // row sub-tile inside a triangle block
+  int64_t step_q = 0, step_r = 0;
+  {
+    const int64_t u0 = blockIdx.x, G = gridDim.x;
     if (prm.symmetric) {
-      // tiles of the lower triangle, row-block major: t' = gbi (gbi+1)/2 + bj with the global
-      // row-block index gbi = tile_row0 + bi (tile_row0 > 0 for a sharded lower trapezoid)
+      int64_t t = u0 / RS;
+      th = (int)(u0 - t * RS);
       const int64_t g0 = prm.tile_row0;
       t += g0 * (g0 + 1) / 2;
       int64_t b = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
       while (b * (b + 1) / 2 > t) --b;
       while ((b + 1) * (b + 2) / 2 <= t) ++b;
-      bi = b - g0;
-      bj = t - b * (b + 1) / 2;
+      tb = b;
+      tj = t - b * (b + 1) / 2;
+      step_q = G / RS;
+      step_r = G - step_q * RS;
     } else {
-      bi = t / prm.tiles_n;
-      bj = t - bi * prm.tiles_n;
+      const int64_t tn = prm.tiles_n > 0 ? prm.tiles_n : 1;
+      tb = u0 / tn;
+      tj = u0 - tb * tn;
+      step_q = G / tn;
+      step_r = G - step_q * tn;
+    }
+  }
+  auto tile_origin = [&](int64_t& row0, int64_t& col0, bool& diag) {
+    if (prm.symmetric) {
+      row0 = (tb - prm.tile_row0) * TN + th * TM;  // relative to row_begin
+      col0 = tj * TN;
+      diag = (tb == tj);
+    } else {
+      row0 = tb * TM;
+      col0 = tj * TN;
+      diag = false;
+    }
+  };
+  auto tile_advance = [&]() {
+    if (prm.symmetric) {
+      th += (int)step_r;
+      tj += step_q;
+      if (th >= RS) {
+        th -= RS;
+        ++tj;
+      }
+      while (tj > tb) {
+        tj -= tb + 1;
+        ++tb;
+      }
+    } else {
+      tj += step_r;
+      tb += step_q;
+      if (tj >= prm.tiles_n) {
+        tj -= prm.tiles_n;
+        ++tb;
+      }
     }
   };
 
-  auto issue_stage = [&](int64_t t, int ch, int buf) {
-    int64_t bi, bj;
-    tile_coords(t, bi, bj);
+  // (row0, col0) of a tile are relative to (row_begin, col_begin)
+  auto issue_stage = [&](int64_t row0, int64_t col0, int ch, int buf) {
     const int d0 = ch * kDimChunk;
     const int nd = min(kDimChunk, D - d0);
     double2* dst = sStage + buf * L::kStageDouble2;
-    const int64_t row0 = prm.row_begin + bi * TM;  // global row index (rows are never padded
-    const int64_t col0 = prm.col_begin + bj * TN;  // beyond n_pad because TM,TN divide 128)
-    for (int i = tid; i < nd * (TM + TN); i += kThreads) {
-      const int dl = i / (TM + TN);
-      const int o = i - dl * (TM + TN);
-      const double2* src = (o < TM)
-                               ? prm.pts_row + (int64_t)(d0 + dl) * prm.n_row_pad + row0 + o
-                               : prm.pts_col + (int64_t)(d0 + dl) * prm.n_col_pad + col0 + (o - TM);
-      cp_async16(dst + dl * (TM + TN) + o, src);
+    row0 += prm.row_begin;  // global row index (tiles never leave the padded block because
+    col0 += prm.col_begin;  // TM, TN divide kPointPad)
+    for (int o = tid; o < TM + TN; o += kThreads) {
+      const double2* src = (o < TM) ? prm.pts_row + (int64_t)d0 * prm.n_row_pad + row0 + o
+                                    : prm.pts_col + (int64_t)d0 * prm.n_col_pad + col0 + (o - TM);
+      const int64_t stride = (o < TM) ? prm.n_row_pad : prm.n_col_pad;
+      for (int dl = 0; dl < nd; ++dl) cp_async16(dst + dl * (TM + TN) + o, src + dl * stride);
     }
     if (tid < nd) cp_async8(sAux + buf * kDimChunk + tid, prm.dim_aux + d0 + tid);
     cp_async_commit();
@@ -196,11 +290,18 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
 
   double acc[RM][RN][P];
 
-  int64_t t = blockIdx.x;
+  int64_t u = blockIdx.x;
   int buf = 0;
-  if (t < prm.num_tiles) issue_stage(t, 0, 0);
+  int64_t nxt_row0 = 0, nxt_col0 = 0;
+  bool nxt_diag = false;
+  if (u < prm.num_tiles) {
+    tile_origin(nxt_row0, nxt_col0, nxt_diag);
+    issue_stage(nxt_row0, nxt_col0, 0, 0);
+  }
 
-  for (; t < prm.num_tiles; t += gridDim.x) {
+  for (; u < prm.num_tiles; u += gridDim.x) {
+    const int64_t row0 = nxt_row0, col0 = nxt_col0;
+    const bool diag = nxt_diag;
 #pragma unroll
     for (int r = 0; r < RM; ++r)
 #pragma unroll
@@ -212,37 +313,69 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
       cp_async_wait_all();
       __syncthreads();  // stage landed; everyone is done with the other buffer
       // prefetch the next stage into the other buffer
-      if (ch + 1 < num_chunks)
-        issue_stage(t, ch + 1, buf ^ 1);
-      else if (t + gridDim.x < prm.num_tiles)
-        issue_stage(t + gridDim.x, 0, buf ^ 1);
+      if (ch + 1 < num_chunks) {
+        issue_stage(row0, col0, ch + 1, buf ^ 1);
+      } else if (u + gridDim.x < prm.num_tiles) {
+        tile_advance();
+        tile_origin(nxt_row0, nxt_col0, nxt_diag);
+        issue_stage(nxt_row0, nxt_col0, 0, buf ^ 1);
+      }
 
       const double2* sRow = sStage + buf * L::kStageDouble2;
       const double* aux = sAux + buf * kDimChunk;
       const int d0 = ch * kDimChunk;
       const int nd = min(kDimChunk, D - d0);
       const int nc = max(0, min(nd, Dc - d0));  // continuous dims in this chunk
+      const unsigned fast_bits =
+          (d0 < kFastWords * 32) ? __funnelshift_r(sFast[d0 >> 5], (d0 >> 5) + 1 < kFastWords ? sFast[(d0 >> 5) + 1] : 0u, d0 & 31)
+                                 : 0u;
 
+      // One decision per stage (16 dims): the clamp-free body when every continuous dim of the
+      // stage qualifies, else the general body (valid for all dims).  Keeping the branch outside
+      // the dim loops leaves them straight-line (uniform loop counter, no reconvergence points).
+      const unsigned cmask = nc >= 32 ? 0xffffffffu : ((1u << nc) - 1u);
+      if (nc > 0 && (fast_bits & cmask) == cmask) {
 #pragma unroll 1
-      for (int dl = 0; dl < nc; ++dl) {
-        const double2* rowp = sRow + dl * (TM + TN);
-        const double2* colp = rowp + TM;
-        const double nls = aux[dl];
-        double2 rv[RM], cv[RN];
+        for (int dl = 0; dl < nc; ++dl) {
+          const double2* rowp = sRow + dl * (TM + TN);
+          const double2* colp = rowp + TM;
+          double2 rv[RM], cv[RN];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
+          for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
 #pragma unroll
-        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + TXD * c];
+          for (int c = 0; c < RN; ++c) cv[c] = colp[tx + TXD * c];
 #pragma unroll
-        for (int r = 0; r < RM; ++r)
+          for (int r = 0; r < RM; ++r)
 #pragma unroll
-          for (int c = 0; c < RN; ++c) {
-            const double d = rv[r].x - cv[c].x;
-            const double z = fma(d, d, nls);            // (x-y)^2 / (2 l^2) - ln s^2
-            const double e = exp_neg_tile(z, tab_bytes, lane_bits);  // s^2 exp(-(x-y)^2/(2 l^2))
-            const double k = fma(-rv[r].y, cv[c].y, e); // - cov_X_s(x) cov_X_s(y) / var_s
-            accumulate<P, ALGO>(acc[r][c], k);
-          }
+            for (int c = 0; c < RN; ++c) {
+              const double d = rv[r].x - cv[c].x;
+              const double e = exp_neg_sq_fast(d, tab_bytes, lane_bits);  // exp(-(x-y)^2/(2 l^2))
+              const double k = fma(-rv[r].y, cv[c].y, e);  // - cov_X_s(x) cov_X_s(y) / var_s
+              accumulate<P, ALGO>(acc[r][c], k);
+            }
+        }
+      } else {
+#pragma unroll 1
+        for (int dl = 0; dl < nc; ++dl) {
+          const double2* rowp = sRow + dl * (TM + TN);
+          const double2* colp = rowp + TM;
+          const double ax = aux[dl];  // -ln(s^2) 256/ln2
+          double2 rv[RM], cv[RN];
+#pragma unroll
+          for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
+#pragma unroll
+          for (int c = 0; c < RN; ++c) cv[c] = colp[tx + TXD * c];
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c) {
+              const double d = rv[r].x - cv[c].x;
+              const double zs = fma(d, d, ax);
+              const double e = exp_neg_scaled(zs, tab_bytes, lane_bits);  // s^2 exp(-(x-y)^2/(2 l^2))
+              const double k = fma(-rv[r].y, cv[c].y, e);
+              accumulate<P, ALGO>(acc[r][c], k);
+            }
+        }
       }
 #pragma unroll 1
       for (int dl = nc; dl < nd; ++dl) {  // discrete dims: table gather
@@ -263,57 +396,149 @@ __global__ void __launch_bounds__(TXD * TYD, 1) gram_kernel(const GramParams prm
     }
 
     // ---- epilogue: Newton-Girard + variance-weighted sum, stores -------------------------
-    int64_t bi, bj;
-    tile_coords(t, bi, bj);
-    const int64_t row0 = bi * TM;  // relative to row_begin
-    const int64_t col0 = bj * TN;
+    // All RM x RN results first (independent recurrences -> ILP), kept in acc[r][c][0].
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+      for (int c = 0; c < RN; ++c) acc[r][c][0] = finish<P, ALGO>(acc[r][c], prm.sigma2);
+
+    const bool mirror = prm.symmetric == 1 && !diag;
     const int64_t nrows = prm.row_end - prm.row_begin;
-    const bool mirror = prm.symmetric == 1 && (bi + prm.tile_row0 != bj);
-    // A thread owns RM consecutive rows (ty*RM + r): in the mirrored (transposed) tile these
-    // are RM consecutive columns, i.e. whole 32-byte sectors per thread, written straight from
-    // registers with 16-byte streaming stores -- no shared-memory transpose, no extra barrier.
-    const bool vec_ok = (RM % 2 == 0) && ((prm.ldk & 1) == 0) &&
-                        ((reinterpret_cast<uintptr_t>(prm.K) & 15) == 0);
+    const int64_t ldk = prm.ldk;
+    const int64_t trow = row0 + ty * RM;  // first row / first column of this thread
+    const int64_t tcol = col0 + tx;
+    double* const kp = prm.K + trow * ldk + tcol;
+    const bool interior = row0 + TM <= nrows && col0 + TN <= prm.n2;
+    // the tile itself: straight from registers (a warp store covers two 128-byte row segments)
+    if (interior) {
 #pragma unroll
-    for (int c = 0; c < RN; ++c) {
-      const int64_t col = col0 + tx + TXD * c;
-      double v[RM];
+      for (int r = 0; r < RM; ++r)
 #pragma unroll
-      for (int r = 0; r < RM; ++r) {
-        const int64_t row = row0 + ty * RM + r;
-        v[r] = finish<P, ALGO>(acc[r][c], prm.sigma2);
-        if (row < nrows && col < prm.n2) __stcs(prm.K + row * prm.ldk + col, v[r]);
-      }
-      if (mirror && col < nrows) {
-        const int64_t ocol0 = row0 + ty * RM;  // columns of the mirrored row `col`
-        double* dst = prm.K + col * prm.ldk + ocol0;
-        if (vec_ok && ocol0 + RM <= prm.n2) {
+        for (int c = 0; c < RN; ++c) __stcs(kp + r * ldk + TXD * c, acc[r][c][0]);
+    } else {
 #pragma unroll
-          for (int r = 0; r + 1 < RM; r += 2)
-            __stcs(reinterpret_cast<double2*>(dst + r), make_double2(v[r], v[r + 1]));
-        } else {
+      for (int r = 0; r < RM; ++r)
 #pragma unroll
-          for (int r = 0; r < RM; ++r)
-            if (ocol0 + r < prm.n2) __stcs(dst + r, v[r]);
+        for (int c = 0; c < RN; ++c)
+          if (trow + r < nrows && tcol + TXD * c < prm.n2) __stcs(kp + r * ldk + TXD * c, acc[r][c][0]);
+    }
+    if (mirror) {
+      if (prm.use_tma) {
+        // The transposed tile would cost every warp 16 partial lines per store instruction.
+        // Instead: registers -> swizzled shared-memory staging (double buffered) -> TM/16 2-D TMA
+        // stores of [TN rows][16 doubles], one issued by lane 0 of each of the first TM/16 warps.
+        // The tensor map clips partial tiles.  Buffer reuse: the issuing lanes leave only their
+        // newest group pending before they reach the next stage barrier.
+        static_assert(RM % 2 == 0, "the transposed tile is staged as 16-byte pairs of consecutive rows");
+        static_assert(kThreads / 32 >= TM / 16, "one issuing warp per 16-column box");
+        const unsigned stage = out_mir + (unsigned)mirror_buf * L::kOutBytes;
+#pragma unroll
+        for (int c = 0; c < RN; ++c)
+#pragma unroll
+          for (int r = 0; r + 1 < RM; r += 2) {
+            const int i = ty * RM + r, j = tx + TXD * c;
+            const unsigned off = (unsigned)((i >> 4) * (TN * 128) + j * 128 + ((((i & 15) >> 1) ^ (j & 7)) << 4));
+            sts128(stage + off, acc[r][c][0], acc[r + 1][c][0]);
+          }
+        fence_async_smem();
+        __syncthreads();
+        const int q = tid >> 5;
+        if ((tid & 31) == 0 && q < TM / 16) {
+          tma_store_2d(&prm.tm_mir, (int)row0 + 16 * q, (int)col0, stage + q * (TN * 128));
+          bulk_commit();
+          bulk_wait_read<1>();
+        }
+        mirror_buf ^= 1;
+      } else {
+        // direct mirrored stores (odd leading dimension / unaligned output)
+        double* const mp = prm.K + tcol * ldk + trow;  // row = column index, column = row index
+#pragma unroll
+        for (int c = 0; c < RN; ++c) {
+          if (tcol + TXD * c < nrows) {
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+              if (trow + r < prm.n2) __stcs(mp + (int64_t)(TXD * c) * ldk + r, acc[r][c][0]);
+          }
         }
       }
     }
   }
   cp_async_wait_all();
+  if ((tid & 31) == 0) bulk_wait_all();
 }
 
 // ---- launch plumbing -------------------------------------------------------------------
-template <int P, int TXD, int TYD, int RM, int RN, int ALGO>
-static int launch_gram(const GramParams& prm, int sms, cudaStream_t stream) {
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// K viewed as a (cols, rows) FP64 tensor with row pitch ldk; box = 16 columns x box_rows rows,
+// 128-byte swizzle (the staging layout of the kernel's epilogue).  Returns 0 on success.
+static int encode_output_map(CUtensorMap* tm, double* K, int64_t cols, int64_t rows, int64_t ldk, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return 1;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ldk * sizeof(double)};
+  const cuuint32_t box[2] = {16u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, K, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB>
+static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream) {
   using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int kThreads = TXD * TYD;
-  const size_t smem = L::bytes(prm.symmetric == 1);
-  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO>;
-  OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)L::bytes(true)));
-  int per_sm = 1;
-  OAK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-  if (per_sm < 1) per_sm = 1;
+  constexpr int TM = L::TM, TN = L::TN;
+  const int64_t rows = prm.row_end - prm.row_begin;
+  if (prm.symmetric) {
+    const int64_t blocks_m = (rows + TN - 1) / TN;
+    prm.tile_row0 = prm.row_begin / TN;
+    prm.tiles_n = 0;
+    prm.num_tiles = (blocks_m * (prm.tile_row0 + 1) + blocks_m * (blocks_m - 1) / 2) * (TN / TM);
+  } else {
+    prm.tile_row0 = 0;
+    prm.tiles_n = (prm.n2 + TN - 1) / TN;
+    prm.num_tiles = ((rows + TM - 1) / TM) * prm.tiles_n;
+  }
+  // 2-D TMA stores need a 16-byte aligned output with an even leading dimension
+  static const int no_tma = env_int("OAK_GRAM_NOTMA", 0);
+  prm.use_tma = 0;
+  if (prm.symmetric == 1 && !no_tma && (prm.ldk % 2 == 0) && (reinterpret_cast<uintptr_t>(prm.K) % 16 == 0) &&
+      (TM % 16 == 0) && kThreads / 32 >= TM / 16 && prm.n2 < (1ll << 31) && rows < (1ll << 31)) {
+    if (encode_output_map(&prm.tm_mir, prm.K, prm.n2, rows, prm.ldk, TN) == 0) prm.use_tma = 1;
+  }
+  const size_t smem = L::bytes(prm.use_tma != 0);
+  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO, MINB>;
+  static int cached_per_sm[64][2] = {{0}};  // per instantiation, device and shared-memory footprint
+  const int fp = prm.use_tma ? 1 : 0;
+  int per_sm = (device >= 0 && device < 64) ? cached_per_sm[device][fp] : 0;
+  if (per_sm == 0) {
+    OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes(true)));
+    OAK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (device >= 0 && device < 64) cached_per_sm[device][fp] = per_sm;
+  }
   const int64_t resident = (int64_t)sms * per_sm;
   const int64_t grid = prm.num_tiles < resident ? prm.num_tiles : resident;
   kern<<<(unsigned)grid, kThreads, smem, stream>>>(prm);
@@ -321,29 +546,35 @@ static int launch_gram(const GramParams& prm, int sms, cudaStream_t stream) {
   return 0;
 }
 
-template <int P, int TXD, int TYD, int RM, int RN>
+template <int P, int TXD, int TYD, int RM, int RN, int MINB>
 static int launch_algo(const GramParams& prm, int algo, int sms, cudaStream_t stream) {
+  const int device = prm.device;
   if (algo == OAK_ESP_DIRECT)
-    return launch_gram<P, TXD, TYD, RM, RN, OAK_ESP_DIRECT>(prm, sms, stream);
-  return launch_gram<P, TXD, TYD, RM, RN, OAK_ESP_NEWTON_GIRARD>(prm, sms, stream);
+    return launch_gram<P, TXD, TYD, RM, RN, OAK_ESP_DIRECT, MINB>(prm, sms, device, stream);
+  return launch_gram<P, TXD, TYD, RM, RN, OAK_ESP_NEWTON_GIRARD, MINB>(prm, sms, device, stream);
 }
 
-// depth <= 4: 64x64 tiles; two geometries (selected by OAK_GRAM_VARIANT for experiments):
-//   0: 256 threads (16x16), 4x4 micro-tile, ~226 registers, 8 warps / SM
-//   1: 512 threads (32x16), 4x2 micro-tile, <= 128 registers, 16 warps / SM
+// depth <= 4, 4x4 register micro-tile.  Geometries (OAK_GRAM_VARIANT, for A/B experiments):
+//   0: 256 threads (16x16), 64x64 tile, 1 CTA / SM
+//   1: 512 threads (32x16), 4x2 micro-tile, 64x64 tile, <= 128 registers
+//   2: 128 threads (16x8), 32x64 tile, 2 CTAs / SM: the two CTAs run out of phase, so the
+//      latency-bound epilogue (Newton-Girard + stores) of one overlaps the FP64 loop of the other
+//   3: 256 threads (16x16), 2x4 micro-tile, 32x64 tile, 2 CTAs / SM
+//   4: 256 threads (32x8), 4x2 micro-tile, 32x64 tile, 2 CTAs / SM
 static int gram_variant() {
   static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("OAK_GRAM_VARIANT");
-    v = e ? atoi(e) : 0;  // measured: variant 0 is 2-3 % faster on B200 (profiles/)
-  }
+  if (v < 0) v = env_int("OAK_GRAM_VARIANT", 0);
   return v;
 }
 
 template <int P>
 static int launch_small_depth(const GramParams& prm, int algo, int sms, cudaStream_t stream) {
-  if (gram_variant() == 0) return launch_algo<P, 16, 16, 4, 4>(prm, algo, sms, stream);
-  return launch_algo<P, 32, 16, 4, 2>(prm, algo, sms, stream);
+  switch (gram_variant()) {
+    case 0: return launch_algo<P, 16, 16, 4, 4, 1>(prm, algo, sms, stream);
+    case 1: return launch_algo<P, 32, 16, 4, 2, 1>(prm, algo, sms, stream);
+    case 2: return launch_algo<P, 16, 8, 4, 4, 2>(prm, algo, sms, stream);
+    default: return launch_algo<P, 16, 16, 4, 4, 1>(prm, algo, sms, stream);
+  }
 }
 
 int tile_rows_for_depth(int depth) { return depth <= 4 ? 64 : 32; }
@@ -357,7 +588,6 @@ static int sm_count(int device) {
   return n;
 }
 
-
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream) {
@@ -367,7 +597,7 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
   prm.pts_col = pcol;
   prm.n_row_pad = n_row_pad;
   prm.n_col_pad = n_col_pad;
-  prm.dim_aux = spec->d_neg_log_s2;
+  prm.dim_aux = spec->d_gram_aux;
   prm.tables = spec->d_tables;
   prm.exptab = spec->d_exptab;
   prm.K = K;
@@ -378,17 +608,19 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
   prm.n2 = col_end - col_begin;
   prm.D = spec->D;
   prm.Dc = spec->Dc;
+  prm.device = spec->device;
+  static const int no_fast = env_int("OAK_GRAM_NOFAST", 0);
+  prm.mm_row = no_fast ? nullptr : points_minmax(spec, prow, n_row_pad);
+  prm.mm_col = no_fast ? nullptr : points_minmax(spec, pcol, n_col_pad);
   const int depth = spec->depth;
   const int T = tile_rows_for_depth(depth);
   // tile origins must sit on tile boundaries so that tile loads stay inside the padded block
   OAK_REQUIRE(row_begin % T == 0 && col_begin % T == 0,
               "gram: row/column range must start on a multiple of the tile size (64)");
-  const int64_t tiles_m = (row_end - row_begin + T - 1) / T;
-  const int64_t tiles_n = (prm.n2 + T - 1) / T;
   prm.symmetric = mode;
-  prm.tile_row0 = mode ? row_begin / T : 0;
-  prm.tiles_n = tiles_n;
-  prm.num_tiles = mode ? tiles_m * (prm.tile_row0 + 1) + tiles_m * (tiles_m - 1) / 2 : tiles_m * tiles_n;
+  prm.tile_row0 = 0;
+  prm.tiles_n = 0;
+  prm.num_tiles = 0;
   const int sms = sm_count(spec->device);
   const int algo = spec->algo;
   switch (depth) {
@@ -397,13 +629,13 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
     case 2: return launch_small_depth<2>(prm, algo, sms, stream);
     case 3: return launch_small_depth<3>(prm, algo, sms, stream);
     case 4: return launch_small_depth<4>(prm, algo, sms, stream);
-    case 5: return launch_algo<5, 16, 16, 2, 2>(prm, algo, sms, stream);
-    case 6: return launch_algo<6, 16, 16, 2, 2>(prm, algo, sms, stream);
-    case 7: return launch_algo<7, 16, 16, 2, 2>(prm, algo, sms, stream);
-    case 8: return launch_algo<8, 16, 16, 2, 2>(prm, algo, sms, stream);
+    case 5: return launch_algo<5, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
+    case 6: return launch_algo<6, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
+    case 7: return launch_algo<7, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
+    case 8: return launch_algo<8, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
     default:
-      if (depth <= 12) return launch_algo<12, 16, 16, 2, 2>(prm, algo, sms, stream);
-      return launch_algo<16, 16, 16, 2, 2>(prm, algo, sms, stream);
+      if (depth <= 12) return launch_algo<12, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
+      return launch_algo<16, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
   }
 }
 

@@ -1,9 +1,11 @@
 // Per-point prologue and K_diag.
 //
 // Prepared-point block ("points"): double2 pts[D][n_pad], feature-major, kernel order (RBF dims
-// first).  RBF dim:   .x = x / (sqrt(2) l)          .y = cov_X_s(x) / sqrt(var_s())
-//          discrete:  .x = bits{lo: idx, hi: idx*C}  .y = B_diag[idx]
+// first).  RBF dim:   .x = x sqrt(256/ln2) / (sqrt(2) l)   .y = cov_X_s(x) / sqrt(var_s())
+//          discrete:  .x = bits{lo: idx, hi: idx*C}         .y = B_diag[idx]
 // Padding rows (n <= i < n_pad) hold zeros so that tiles can be loaded without bounds checks.
+// The block ends with 2 D uint64 keys: per-dimension min and max of .x over the n real points
+// (order_key encoding); the Gram kernel uses them to prove that the clamp-free exp is safe.
 #include "oak_common.cuh"
 
 namespace oak {
@@ -14,16 +16,18 @@ __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
                                       const double* __restrict__ inv_sqrt_v,
                                       const double* __restrict__ tables,
                                       const double* __restrict__ X, int64_t n, int64_t n_pad,
-                                      int64_t ldx, double2* __restrict__ pts) {
+                                      int64_t ldx, double2* __restrict__ pts,
+                                      unsigned long long* __restrict__ minmax, int D) {
   const int k = blockIdx.y;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
   double2 out = make_double2(0.0, 0.0);
+  double lo = INFINITY, hi = -INFINITY;
   if (i < n) {
     const DimDev d = dims[k];
     const double x = X[i * ldx + d.column];
     if (d.type == OAK_DIM_RBF) {
-      out.x = x * d.inv_sqrt2_l;
+      out.x = x * d.xscale;
+      lo = hi = out.x;
       double c = 0.0;
       switch (d.measure) {
         case OAK_MEASURE_GAUSSIAN: {  // ortho_rbf_kernel.py:82-92
@@ -49,7 +53,7 @@ __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
           double acc = 0.0;
           const int cnt = d.count <= kSmallEmpirical ? d.count : 0;  // large: tiled kernel below
           for (int q = 0; q < cnt; ++q) {
-            const double t = out.x - d.v0[q] * d.inv_sqrt2_l;
+            const double t = (x - d.v0[q]) * d.inv_sqrt2_l;
             acc = fma(d.v1[q], exp(-t * t), acc);
           }
           c = d.c0 * acc;
@@ -68,7 +72,29 @@ __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
       out.y = tables[d.table_off + d.count * d.count + idx];
     }
   }
-  pts[(int64_t)k * n_pad + i] = out;
+  if (i < n_pad) pts[(int64_t)k * n_pad + i] = out;
+  // block-wide min / max of the prepared coordinate -> one atomic pair per block
+  // (NaNs compare false and are skipped; they poison the Gram entries on either exp path)
+  __shared__ double s_lo[8], s_hi[8];
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_lo[threadIdx.x >> 5] = lo;
+    s_hi[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      lo = fmin(lo, s_lo[w]);
+      hi = fmax(hi, s_hi[w]);
+    }
+    if (lo <= hi) {
+      atomicMin(minmax + k, order_key(lo));
+      atomicMax(minmax + D + k, order_key(hi));
+    }
+  }
 }
 
 // Tiled variant for empirical measures with many locations: the locations/weights of the dim
@@ -83,7 +109,8 @@ __global__ void prepare_empirical_kernel(const DimDev* __restrict__ dims, int k,
   double* sw = sh + tile;
   const DimDev d = dims[k];
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const double a = (i < n) ? X[i * ldx + d.column] * d.inv_sqrt2_l : 0.0;
+  const double x = (i < n) ? X[i * ldx + d.column] : 0.0;
+  const double a = x * d.inv_sqrt2_l;
   double acc = 0.0;
   for (int base = 0; base < d.count; base += tile) {
     const int j = base + threadIdx.x;
@@ -99,7 +126,7 @@ __global__ void prepare_empirical_kernel(const DimDev* __restrict__ dims, int k,
   }
   if (i < n_pad) {
     double2 out = make_double2(0.0, 0.0);
-    if (i < n) out = make_double2(a, d.c0 * acc * inv_sqrt_v[k]);
+    if (i < n) out = make_double2(x * d.xscale, d.c0 * acc * inv_sqrt_v[k]);
     pts[(int64_t)k * n_pad + i] = out;
   }
 }
@@ -176,22 +203,28 @@ using namespace oak;
 
 extern "C" size_t oak_points_bytes(const oak_spec* spec, int64_t n) {
   if (!spec || n < 0) return 0;
-  return (size_t)spec->D * (size_t)padded(n) * sizeof(double2);
+  return (size_t)spec->D * (size_t)padded(n) * sizeof(double2) +
+         2 * (size_t)spec->D * sizeof(unsigned long long);
 }
 
 extern "C" int oak_prepare_points_f64(const oak_spec* spec, const double* d_X, int64_t n,
                                       int64_t ldx, void* d_points, void* stream_) {
   OAK_REQUIRE(spec && d_points, "oak_prepare_points_f64: null argument");
   OAK_REQUIRE(n >= 0, "oak_prepare_points_f64: negative n");
-  if (n == 0) return 0;
-  OAK_REQUIRE(d_X, "oak_prepare_points_f64: null X");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t n_pad = padded(n);
+  const int D = spec->D;
+  // min keys start at +max, max keys at 0 (an empty block never qualifies for the fast exp)
+  unsigned long long* minmax = (unsigned long long*)((double2*)d_points + (int64_t)D * n_pad);
+  OAK_CUDA(cudaMemsetAsync(minmax, 0xFF, (size_t)D * sizeof(unsigned long long), stream));
+  OAK_CUDA(cudaMemsetAsync(minmax + D, 0x00, (size_t)D * sizeof(unsigned long long), stream));
+  if (n == 0) return 0;
+  OAK_REQUIRE(d_X, "oak_prepare_points_f64: null X");
   const int threads = 256;
-  dim3 grid((unsigned)((n_pad + threads - 1) / threads), (unsigned)spec->D);
+  dim3 grid((unsigned)((n_pad + threads - 1) / threads), (unsigned)D);
   prepare_points_kernel<<<grid, threads, 0, stream>>>(spec->d_dims, spec->d_inv_sqrt_v,
                                                       spec->d_tables, d_X, n, n_pad, ldx,
-                                                      (double2*)d_points);
+                                                      (double2*)d_points, minmax, D);
   OAK_LAUNCHED();
   // large empirical measures: overwrite with the tiled kernel
   for (int k = 0; k < spec->Dc; ++k) {

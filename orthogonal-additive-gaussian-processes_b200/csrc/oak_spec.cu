@@ -164,6 +164,7 @@ extern "C" int oak_spec_destroy(oak_spec* spec) {
   cudaFree(spec->d_dims);
   cudaFree(spec->d_inv_sqrt_v);
   cudaFree(spec->d_neg_log_s2);
+  cudaFree(spec->d_gram_aux);
   cudaFree(spec->d_tables);
   cudaFree(spec->d_blob);
   cudaFree(spec->d_sobolG);
@@ -229,6 +230,7 @@ extern "C" int oak_spec_create(const oak_kernel_desc* desc, void* stream_, oak_s
       }
       const double l = d.lengthscale, s2 = d.variance;
       dd.inv_sqrt2_l = 1.0 / (std::sqrt(2.0) * l);
+      dd.xscale = kXScale / (std::sqrt(2.0) * l);
       dd.neg_log_s2 = -std::log(s2);
       nls[k] = dd.neg_log_s2;
       switch (d.measure) {
@@ -342,6 +344,13 @@ extern "C" int oak_spec_create(const oak_kernel_desc* desc, void* stream_, oak_s
                       stream) != cudaSuccess)
     return fail("cudaMemcpyAsync");
   if (cudaMemcpyAsync(s->d_neg_log_s2, nls.data(), D * sizeof(double), cudaMemcpyHostToDevice,
+                      stream) != cudaSuccess)
+    return fail("cudaMemcpyAsync");
+  // Gram-tile flavour: the exponent of the RBF dims in units of ln2/256 (0 when s^2 == 1)
+  std::vector<double> gaux(nls);
+  for (int k = 0; k < s->Dc; ++k) gaux[k] = (s->h_dims[k].s2 == 1.0) ? 0.0 : nls[k] * kXScale2;
+  if (cudaMalloc(&s->d_gram_aux, D * sizeof(double)) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMemcpyAsync(s->d_gram_aux, gaux.data(), D * sizeof(double), cudaMemcpyHostToDevice,
                       stream) != cudaSuccess)
     return fail("cudaMemcpyAsync");
   if (s->tables_len > 0) {
