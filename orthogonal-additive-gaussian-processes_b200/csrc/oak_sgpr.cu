@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "oak_common.cuh"
 
@@ -179,12 +180,12 @@ constexpr size_t kFinishHeader = 16 + 8 * sizeof(double);
 // C(lower, column-major M x M) += A'^T A' with A' column-major (k x M, lda).  cuBLAS DSYRK runs
 // at full-GEMM cost on this shape (measured on B200), so the triangle is cut recursively into
 // off-diagonal rectangles (plain DGEMM, the efficient path) and small diagonal blocks:
-//   OAK_SYRK_MODE=0 one DSYRK | 1,2,3 recursion depth (default 1) | 9 one full DGEMM
+//   OAK_SYRK_MODE=0 one DSYRK | 1,2,3 recursion depth | 9 one full DGEMM | 20 batched blocks (default)
 static int syrk_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("OAK_SYRK_MODE");
-    v = e ? atoi(e) : 1;  // measured on B200 (scripts/quick_sgpr.py): depth 1 is fastest
+    v = e ? atoi(e) : 20;  // measured on B200 (scripts/quick_sgpr.py, profiles/)
   }
   return v;
 }
@@ -207,8 +208,71 @@ static int syrk_rec(cublasHandle_t cb, int off, int m, int k, const double* A, i
   return syrk_rec(cb, off + h, m - h, k, A, lda, C, ldc, depth - 1);
 }
 
-static int syrk_lower_accumulate(cublasHandle_t cb, int m, int k, const double* A, int lda, double* C) {
+// Default: the lower triangle in 128 x 128 blocks as ONE batched DGEMM (diagonal blocks computed in
+// full: 590 k instead of 525 k block entries at M = 1024, against 786 k for DGEMM + 2 DSYRK).
+// Measured on B200 (profiles/): 2.4 ms per 1024 x 65536 chunk against 3.4 ms.  A ragged last
+// block row (M % 128 rows) goes through one DGEMM + one small DSYRK.
+struct BatchPtrs {
+  const double** dev = nullptr;  // [3][kMaxBatch]: A_i, A_j, C_ij
+  const double* A = nullptr;
+  double* C = nullptr;
+  int m = 0, lda = 0, count = 0;
+};
+constexpr int kMaxBatch = 8192;
+constexpr int kSyrkBlock = 128;
+static BatchPtrs g_batch[64];
+
+static int syrk_batched(cublasHandle_t cb, int m, int k, const double* A, int lda, double* C,
+                        cudaStream_t stream) {
+  const double one = 1.0;
+  const int bs = kSyrkBlock;
+  const int nb = m / bs, rem = m - nb * bs;
+  const int cnt = nb * (nb + 1) / 2;
+  if (cnt > kMaxBatch) return -1;  // caller falls back
+  int dev = 0;
+  OAK_CUDA(cudaGetDevice(&dev));
+  if (cnt > 0) {
+    BatchPtrs& bp = g_batch[dev];
+    if (!bp.dev) OAK_CUDA(cudaMalloc(&bp.dev, 3 * kMaxBatch * sizeof(double*)));
+    if (bp.A != A || bp.C != C || bp.m != m || bp.lda != lda) {
+      std::vector<const double*> h(3 * (size_t)cnt);
+      int c = 0;
+      for (int j = 0; j < nb; ++j)
+        for (int i = j; i < nb; ++i, ++c) {
+          h[c] = A + (size_t)i * bs * lda;                            // rows of the block (op T)
+          h[cnt + c] = A + (size_t)j * bs * lda;                      // columns of the block
+          h[2 * (size_t)cnt + c] = C + (size_t)j * bs * m + (size_t)i * bs;  // column-major, lower
+        }
+      // pageable source: the copy is staged before the call returns, `h` may die afterwards
+      OAK_CUDA(cudaMemcpyAsync(bp.dev, h.data(), h.size() * sizeof(double*), cudaMemcpyHostToDevice, stream));
+      bp.A = A; bp.C = C; bp.m = m; bp.lda = lda; bp.count = cnt;
+    }
+    OAK_CUBLAS(cublasDgemmBatched(cb, CUBLAS_OP_T, CUBLAS_OP_N, bs, bs, k, &one, bp.dev, lda, bp.dev + cnt, lda,
+                                  &one, (double**)(bp.dev + 2 * (size_t)cnt), m, cnt));
+    g_launches.fetch_add(1);
+  }
+  if (rem > 0) {
+    const int off = nb * bs;
+    if (off > 0) {
+      OAK_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, rem, off, k, &one, A + (size_t)off * lda, lda, A, lda,
+                             &one, C + off, m));
+      g_launches.fetch_add(1);
+    }
+    OAK_CUBLAS(cublasDsyrk(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, rem, k, &one, A + (size_t)off * lda, lda, &one,
+                           C + (size_t)off * m + off, m));
+    g_launches.fetch_add(1);
+  }
+  return 0;
+}
+
+static int syrk_lower_accumulate(cublasHandle_t cb, int m, int k, const double* A, int lda, double* C,
+                                 cudaStream_t stream) {
   const int mode = syrk_mode();
+  if (mode == 20) {
+    const int rc = syrk_batched(cb, m, k, A, lda, C, stream);
+    if (rc >= 0) return rc;
+    return syrk_rec(cb, 0, m, k, A, lda, C, m, 1);
+  }
   if (mode == 9) {
     const double one = 1.0;
     OAK_CUBLAS(cublasDgemm(cb, CUBLAS_OP_T, CUBLAS_OP_N, m, m, k, &one, A, lda, A, lda, &one, C, m));
@@ -266,7 +330,7 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
       return rc;
     // Phi += Kuf Kuf^T.  Row-major (M x nc, ld=chunk) == column-major (nc x M, lda=chunk) A';
     // Phi = A'^T A'  ->  DSYRK(trans = T).  Only one triangle is updated.
-    if (int rc = syrk_lower_accumulate(cb, (int)m, (int)nc, kuf, (int)chunk, phi)) return rc;
+    if (int rc = syrk_lower_accumulate(cb, (int)m, (int)nc, kuf, (int)chunk, phi, stream)) return rc;
     // Kuf_y += Kuf y_chunk = A'^T y
     OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, (int)nc, (int)m, &one, kuf, (int)chunk, d_y + c0, 1, &one,
                            kufy, 1));
