@@ -481,12 +481,16 @@ def L_empirical(location, weights, kern: RBFDim, zcol):
     return (w * kxu.T) @ kxu
 
 
-def sobol_oak(kern: OakOracle, Xcond, alpha, delta=1.0, mu=0.0, share_var_across_orders=True):
+def sobol_oak(kern: OakOracle, Xcond, alpha, delta=1.0, mu=0.0, share_var_across_orders=True, only=None):
     """``compute_sobol_oak`` (oak/utils.py:338-435). ``Xcond`` is Z for SGPR/SVGP and the
-    training inputs for GPR (:361-364). Returns (list of subsets without the constant, values)."""
+    training inputs for GPR (:361-364). Returns (list of subsets without the constant, values).
+    ``only`` (test aid): indices into that list -- evaluate just those components (the reference
+    rebuilds every L matrix per subset, which takes minutes at D=50 or depth 8)."""
     Xcond = np.asarray(Xcond, dtype=np.float64)
     n = Xcond.shape[0]
     comps = subsets(len(kern.dims), kern.depth)[1:]
+    if only is not None:
+        comps = [comps[i] for i in only]
     out = []
     for S in comps:
         L = np.ones((n, n))

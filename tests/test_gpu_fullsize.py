@@ -1,0 +1,243 @@
+"""BASELINE.json's configurations at their FULL sizes on the GPU.
+
+The oracle cannot build a 65 536^2 Gram or a 1024 x 10^6 Kuf in seconds, so at full size the CUDA
+path is checked (a) against the oracle on corners / random samples of the big result and (b) through
+size-independent properties: exact symmetry (mirrored tiles are copies), diag(K) = K_diag,
+bit-identical row sharding, linearity in the order variances, additivity of the SGPR statistics over
+N-shards, independent recomputation of tr(Phi) and Kuf y, Sobol indices summing to the explained
+variance.  Tolerance: 1e-9 relative (north_star); bit-exact where the path only moves data."""
+import numpy as np
+import pytest
+
+from helpers import RTOL, build_oracle, max_rel_err
+from oracle import oak_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample_vs_oracle(K, X, ref, rng, corner=1536, samples=200_000, X2=None):
+    """Corner block + random entries of a device matrix against the oracle."""
+    import torch
+
+    n, n2 = K.shape
+    Xc = X if X2 is None else X2
+    c = min(corner, n, n2)
+    want = ref.K(X[:c], Xc[:c])
+    assert max_rel_err(K[:c, :c].cpu().numpy(), want) < RTOL
+    # random entries: evaluate the oracle on (row subset) x (col subset) blocks and gather
+    side = int(np.sqrt(samples))
+    ri = np.sort(rng.choice(n, size=min(side, n), replace=False))
+    ci = np.sort(rng.choice(n2, size=min(side, n2), replace=False))
+    got = K[torch.as_tensor(ri, device=K.device)][:, torch.as_tensor(ci, device=K.device)].cpu().numpy()
+    assert max_rel_err(got, ref.K(X[ri], Xc[ci])) < RTOL
+
+
+def test_config_B_full_gram_65536():
+    """K(X, X) at N = 65 536, D = 16, depth 4 (34 GB): oracle samples + symmetry + diagonal + sharding."""
+    import torch
+
+    from oak_b200 import _device, parallel
+    from oak_b200.workloads import build_kernel, config_B
+
+    n = 65536
+    cfg = config_B(n)
+    k, ref = build_kernel(cfg), build_oracle(cfg)
+    spec = k._make_spec()
+    Xd = _device.to_device(cfg["X"])
+    px = _device.Points(spec, Xd)
+    K = _device.gram(spec, px)
+    rng = np.random.default_rng(0)
+    _sample_vs_oracle(K, cfg["X"], ref, rng)
+    # mirrored tiles are copies of the computed ones: exact symmetry, checked on row/column strips
+    for lo in (0, 20480, 65536 - 4096):
+        a = K[lo:lo + 4096, :]
+        b = K[:, lo:lo + 4096].T
+        assert torch.equal(a, b)
+    # diagonal of the Gram equals K_diag (two different kernels: tile vs per-point recurrence)
+    kd = _device.gram_diag(spec, px)
+    assert max_rel_err(torch.diagonal(K).cpu().numpy(), kd.cpu().numpy()) < 1e-12
+    assert max_rel_err(kd[:4096].cpu().numpy(), ref.K_diag(cfg["X"][:4096])) < RTOL
+    # folded row strips of the 8-GPU layout: lower trapezoids are bit-identical to the full matrix
+    for strips in parallel.balanced_symmetric_rows(n, 8)[:3]:
+        for b, e in strips:
+            if e > b:
+                part = _device.gram_lower(spec, px, b, e)
+                low = torch.tril(part, diagonal=b)
+                assert torch.equal(low, torch.tril(K[b:e, :e], diagonal=b))
+                del part, low
+    spec.close()
+    del K
+    torch.cuda.empty_cache()
+
+
+def test_config_B_linearity_in_order_variances():
+    """K is linear in (sigma^2_0..P): K(a) + K(b) = K(a + b) on a 16k cross block."""
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel, config_B
+
+    cfg = config_B(16384)
+    Xd = _device.to_device(cfg["X"])
+    outs = []
+    va, vb = [1.0, 1.0, 0.5, 0.25, 0.125], [0.3, 0.0, 2.0, 0.5, 1.5]
+    for v in (va, vb, [x + y for x, y in zip(va, vb)]):
+        c = dict(cfg)
+        c["variances"] = v
+        k = build_kernel(c)
+        spec = k._make_spec()
+        px = _device.Points(spec, Xd)
+        outs.append(_device.gram(spec, px, _device.Points(spec, Xd[:8192].contiguous())))
+        spec.close()
+    assert max_rel_err((outs[0] + outs[1]).cpu().numpy(), outs[2].cpu().numpy()) < 1e-13
+
+
+def test_config_C_sgpr_statistics_1M():
+    """N = 10^6, D = 20, M = 1024, depth 3: shard additivity, tr(Phi), Kuf y, oracle ELBO on a slice."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.models import SGPR
+    from oak_b200.parallel import partition_rows
+    from oak_b200.workloads import build_kernel, config_C
+
+    n, m = 1_000_000, 1024
+    cfg = config_C(n, 20, m, 3)
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    Xd, Zd, yd = _device.to_device(cfg["X"]), _device.to_device(cfg["Z"]), _device.to_device(cfg["y"])
+    pz, px = _device.Points(spec, Zd), _device.Points(spec, Xd)
+    full = _device.sgpr_stats(spec, pz, px, yd, chunk=65536)
+    # (1) the 8-rank N-sharding adds up to the unsharded statistics (what the all-reduce does)
+    acc = torch.zeros_like(full)
+    for b, e in partition_rows(n, 8):
+        acc += _device.sgpr_stats(spec, pz, _device.Points(spec, Xd[b:e].contiguous()), yd[b:e].contiguous(),
+                                  chunk=65536)
+    assert max_rel_err(acc.cpu().numpy(), full.cpu().numpy()) < 1e-12
+    # (2) independent recomputation from Kuf tiles: diag(Phi) = sum_n Kuf^2, Kuf y, yTy, sum K_diag
+    Phi = full[: m * m].reshape(m, m)
+    diag = torch.zeros(m, dtype=torch.float64, device="cuda")
+    kufy = torch.zeros(m, dtype=torch.float64, device="cuda")
+    step = 131072
+    for b in range(0, n, step):
+        e = min(b + step, n)
+        Kuf = _device.gram(spec, pz, _device.Points(spec, Xd[b:e].contiguous()))
+        diag += (Kuf * Kuf).sum(1)
+        kufy += Kuf @ yd[b:e, 0]
+        del Kuf
+    assert max_rel_err(torch.diagonal(Phi).cpu().numpy(), diag.cpu().numpy()) < 1e-11
+    assert max_rel_err(full[m * m: m * m + m].cpu().numpy(), kufy.cpu().numpy()) < 1e-11
+    assert abs(float(full[m * m + m + 1]) - float((yd * yd).sum())) < 1e-11 * float((yd * yd).sum())
+    kd = _device.gram_diag(spec, px)
+    assert abs(float(full[m * m + m]) - float(kd.sum())) < 1e-11 * float(kd.sum())
+    # lower triangle of Phi is what the contraction guarantees; it must be symmetric-consistent with
+    # a direct product on a row block
+    Kuf = _device.gram(spec, pz, _device.Points(spec, Xd[:65536].contiguous()))
+    blk = _device.sgpr_stats(spec, pz, _device.Points(spec, Xd[:65536].contiguous()), yd[:65536].contiguous(),
+                             chunk=65536)[: m * m].reshape(m, m)
+    direct = Kuf @ Kuf.T
+    # stored column-major lower == row-major upper
+    assert max_rel_err(torch.triu(blk).cpu().numpy(), torch.triu(direct).cpu().numpy()) < 1e-12
+    spec.close()
+    # (3) ELBO through the public model API vs the oracle on a 20 000-point slice (same Z, M = 1024)
+    ns = 20_000
+    sub = dict(cfg)
+    sub["X"], sub["y"] = cfg["X"][:ns], cfg["y"][:ns]
+    model = SGPR((sub["X"], sub["y"]), kernel=build_kernel(sub), inducing_variable=cfg["Z"], chunk=8192)
+    model.likelihood.variance.assign(cfg["noise"])
+    elbo = model.elbo()
+    elbo_ref = oo.sgpr_elbo(build_oracle(sub), sub["X"], sub["y"], cfg["Z"], cfg["noise"])
+    assert abs(elbo - elbo_ref) < RTOL * abs(elbo_ref)
+    # and the full-size ELBO is finite and reproducible
+    big = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=65536)
+    big.likelihood.variance.assign(cfg["noise"])
+    e1, e2 = big.elbo(), big.elbo()
+    assert np.isfinite(e1) and e1 == e2
+
+
+def test_config_D_mixed_inputs_50k():
+    """N = 50 000, D = 12 (Gaussian + empirical measure RBF, binary, categorical), depth 2."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.models import SGPR
+    from oak_b200.workloads import build_kernel, config_D
+
+    cfg = config_D()
+    n = cfg["X"].shape[0]
+    k, ref = build_kernel(cfg), build_oracle(cfg)
+    spec = k._make_spec()
+    Xd = _device.to_device(cfg["X"])
+    px = _device.Points(spec, Xd)
+    K = _device.gram(spec, px)
+    rng = np.random.default_rng(1)
+    _sample_vs_oracle(K, cfg["X"], ref, rng, corner=1024, samples=90_000)
+    assert torch.equal(K[:4096, :], K[:, :4096].T)
+    kd = _device.gram_diag(spec, px)
+    assert max_rel_err(torch.diagonal(K).cpu().numpy(), kd.cpu().numpy()) < 1e-12
+    del K
+    torch.cuda.empty_cache()
+    # Kuf (M = 512) against the oracle on random columns, and the ELBO on a 6 000-point slice
+    pz = _device.Points(spec, _device.to_device(cfg["Z"]))
+    Kuf = _device.gram(spec, pz, px)
+    ci = np.sort(rng.choice(n, size=2000, replace=False))
+    got = Kuf[:, torch.as_tensor(ci, device="cuda")].cpu().numpy()
+    assert max_rel_err(got, ref.K(cfg["Z"], cfg["X"][ci])) < RTOL
+    spec.close()
+    ns = 6000
+    sub = dict(cfg)
+    sub["X"], sub["y"] = cfg["X"][:ns], cfg["y"][:ns]
+    model = SGPR((sub["X"], sub["y"]), kernel=build_kernel(sub), inducing_variable=cfg["Z"], chunk=2048)
+    model.likelihood.variance.assign(cfg["noise"])
+    elbo = model.elbo()
+    elbo_ref = oo.sgpr_elbo(build_oracle(sub), sub["X"], sub["y"], cfg["Z"], cfg["noise"])
+    assert abs(elbo - elbo_ref) < RTOL * abs(elbo_ref)
+
+
+def test_config_E_sobol_d50_200k():
+    """D = 50, depth 2, N = 200 000, M = 512: 50 + 1225 Sobol indices vs the oracle (same alpha)."""
+    from oak_b200.models import SGPR
+    from oak_b200.utils import compute_sobol_oak
+    from oak_b200.workloads import build_kernel, config_E
+
+    cfg = config_E()
+    k, ref = build_kernel(cfg), build_oracle(cfg)
+    model = SGPR((cfg["X"], cfg["y"]), kernel=k, inducing_variable=cfg["Z"], chunk=65536)
+    model.likelihood.variance.assign(cfg["noise"])
+    sel, sob = compute_sobol_oak(model, 1.0, 0.0)
+    sob = np.asarray(sob, dtype=np.float64)
+    assert len(sob) == 50 + 1225 and np.all(np.isfinite(sob)) and np.all(sob > -1e-9 * np.abs(sob).max())
+    alpha = model.sufficient_statistics()
+    alpha = alpha.cpu().numpy() if hasattr(alpha, "cpu") else np.asarray(alpha)
+    # the oracle rebuilds every L per subset (as the reference does): all 50 first-order indices and a
+    # random 70 of the 1225 second-order ones; same alpha on both sides, so the comparison isolates
+    # the L matrices and the quadratic forms
+    pick = list(range(50)) + sorted(np.random.default_rng(5).choice(np.arange(50, 1275), 70, replace=False).tolist())
+    _, sob_ref = oo.sobol_oak(ref, cfg["Z"], alpha.reshape(-1, 1), only=pick)
+    scale = np.abs(sob).max()
+    assert np.max(np.abs(sob[pick] - np.asarray(sob_ref))) < 1e-8 * scale
+
+
+def test_config_A_gpr_1030_depth8():
+    """N = 1030, D = 8, full depth 8: Gram, K_diag, LML, alpha and the 255 Sobol indices vs the oracle."""
+    from oak_b200.models import GPR
+    from oak_b200.utils import compute_sobol_oak
+    from oak_b200.workloads import build_kernel, config_A
+
+    cfg = config_A()
+    k, ref = build_kernel(cfg), build_oracle(cfg)
+    K = k.K(cfg["X"])
+    assert max_rel_err(K, ref.K(cfg["X"])) < RTOL
+    assert max_rel_err(k.K_diag(cfg["X"]), ref.K_diag(cfg["X"])) < RTOL
+    model = GPR((cfg["X"], cfg["y"]), kernel=k)
+    model.likelihood.variance.assign(cfg["noise"])
+    lml = model.log_marginal_likelihood()
+    lml_ref = oo.gpr_log_marginal_likelihood(ref, cfg["X"], cfg["y"], cfg["noise"])
+    assert abs(lml - lml_ref) < RTOL * abs(lml_ref)
+    alpha = model.sufficient_statistics()
+    alpha = alpha.cpu().numpy() if hasattr(alpha, "cpu") else np.asarray(alpha)
+    _, sob = compute_sobol_oak(model, 1.0, 0.0)
+    sob = np.asarray(sob, dtype=np.float64)
+    assert len(sob) == 255
+    # all 8 first-order, the single order-8 component and 15 random others (the oracle recomputes each L)
+    pick = list(range(8)) + sorted(np.random.default_rng(8).choice(np.arange(8, 254), 15, replace=False).tolist()) + [254]
+    _, sob_ref = oo.sobol_oak(ref, cfg["X"], alpha.reshape(-1, 1), only=pick)
+    assert np.max(np.abs(sob[pick] - np.asarray(sob_ref))) < 1e-8 * np.abs(sob).max()
