@@ -180,6 +180,9 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
 
   const int tid = threadIdx.x;
   const int tx = tid % TXD, ty = tid / TXD;
+  const bool issuer = (tid & 31) == 0 && (tid >> 5) < TM / 16;  // lanes that issue the TMA stores
+  int pend = 0, pend_row0 = 0, pend_col0 = 0;                  // mirrored tile staged, not yet issued
+  unsigned pend_stage = 0;
 
   // replicate the exp table: entry j, replica r at sTab[j*16 + r]
   // (high words pre-compensated by -(j << 12), see exp_tail)
@@ -312,6 +315,13 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
     for (int ch = 0; ch < num_chunks; ++ch) {
       cp_async_wait_all();
       __syncthreads();  // stage landed; everyone is done with the other buffer
+      if (pend) {       // ... and the staged transpose of the previous tile is complete
+        if (issuer) {
+          tma_store_2d(&prm.tm_mir, pend_row0 + 16 * (tid >> 5), pend_col0, pend_stage + (tid >> 5) * (TN * 128));
+          bulk_commit();
+        }
+        pend = 0;
+      }
       // prefetch the next stage into the other buffer
       if (ch + 1 < num_chunks) {
         issue_stage(row0, col0, ch + 1, buf ^ 1);
@@ -407,6 +417,33 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
     const int64_t ldk = prm.ldk;
     const int64_t trow = row0 + ty * RM;  // first row / first column of this thread
     const int64_t tcol = col0 + tx;
+    if (mirror && prm.use_tma) {
+      // The transposed tile would cost every warp 16 partial lines per store instruction.
+      // Instead: registers -> swizzled shared-memory staging (double buffered) -> TM/16 2-D TMA
+      // stores of [TN rows][16 doubles], one per lane 0 of the first TM/16 warps.  The stores are
+      // issued after the NEXT stage barrier (which orders the staging writes), so the epilogue
+      // needs no barrier of its own; the tensor map clips partial tiles.
+      static_assert(RM % 2 == 0, "the transposed tile is staged as 16-byte pairs of consecutive rows");
+      static_assert(kThreads / 32 >= TM / 16, "one issuing warp per 16-column box");
+      const unsigned stage = out_mir + (unsigned)mirror_buf * L::kOutBytes;
+#pragma unroll
+      for (int c = 0; c < RN; ++c)
+#pragma unroll
+        for (int r = 0; r + 1 < RM; r += 2) {
+          const int i = ty * RM + r, j = tx + TXD * c;
+          const unsigned off = (unsigned)((i >> 4) * (TN * 128) + j * 128 + ((((i & 15) >> 1) ^ (j & 7)) << 4));
+          sts128(stage + off, acc[r][c][0], acc[r + 1][c][0]);
+        }
+      fence_async_smem();
+      // the group issued at the top of this tile read the OTHER buffer: it must be drained before
+      // the next stage barrier lets anybody write that buffer again
+      if (issuer) bulk_wait_read<0>();
+      pend = 1;
+      pend_row0 = (int)row0;
+      pend_col0 = (int)col0;
+      pend_stage = stage;
+      mirror_buf ^= 1;
+    }
     double* const kp = prm.K + trow * ldk + tcol;
     const bool interior = row0 + TM <= nrows && col0 + TN <= prm.n2;
     // the tile itself: straight from registers (a warp store covers two 128-byte row segments)
@@ -422,49 +459,28 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
         for (int c = 0; c < RN; ++c)
           if (trow + r < nrows && tcol + TXD * c < prm.n2) __stcs(kp + r * ldk + TXD * c, acc[r][c][0]);
     }
-    if (mirror) {
-      if (prm.use_tma) {
-        // The transposed tile would cost every warp 16 partial lines per store instruction.
-        // Instead: registers -> swizzled shared-memory staging (double buffered) -> TM/16 2-D TMA
-        // stores of [TN rows][16 doubles], one issued by lane 0 of each of the first TM/16 warps.
-        // The tensor map clips partial tiles.  Buffer reuse: the issuing lanes leave only their
-        // newest group pending before they reach the next stage barrier.
-        static_assert(RM % 2 == 0, "the transposed tile is staged as 16-byte pairs of consecutive rows");
-        static_assert(kThreads / 32 >= TM / 16, "one issuing warp per 16-column box");
-        const unsigned stage = out_mir + (unsigned)mirror_buf * L::kOutBytes;
+    if (mirror && !prm.use_tma) {
+      // direct mirrored stores (odd leading dimension / unaligned output)
+      double* const mp = prm.K + tcol * ldk + trow;  // row = column index, column = row index
 #pragma unroll
-        for (int c = 0; c < RN; ++c)
+      for (int c = 0; c < RN; ++c) {
+        if (tcol + TXD * c < nrows) {
 #pragma unroll
-          for (int r = 0; r + 1 < RM; r += 2) {
-            const int i = ty * RM + r, j = tx + TXD * c;
-            const unsigned off = (unsigned)((i >> 4) * (TN * 128) + j * 128 + ((((i & 15) >> 1) ^ (j & 7)) << 4));
-            sts128(stage + off, acc[r][c][0], acc[r + 1][c][0]);
-          }
-        fence_async_smem();
-        __syncthreads();
-        const int q = tid >> 5;
-        if ((tid & 31) == 0 && q < TM / 16) {
-          tma_store_2d(&prm.tm_mir, (int)row0 + 16 * q, (int)col0, stage + q * (TN * 128));
-          bulk_commit();
-          bulk_wait_read<1>();
-        }
-        mirror_buf ^= 1;
-      } else {
-        // direct mirrored stores (odd leading dimension / unaligned output)
-        double* const mp = prm.K + tcol * ldk + trow;  // row = column index, column = row index
-#pragma unroll
-        for (int c = 0; c < RN; ++c) {
-          if (tcol + TXD * c < nrows) {
-#pragma unroll
-            for (int r = 0; r < RM; ++r)
-              if (trow + r < prm.n2) __stcs(mp + (int64_t)(TXD * c) * ldk + r, acc[r][c][0]);
-          }
+          for (int r = 0; r < RM; ++r)
+            if (trow + r < prm.n2) __stcs(mp + (int64_t)(TXD * c) * ldk + r, acc[r][c][0]);
         }
       }
     }
   }
+  if (pend) {  // the last mirrored tile of this CTA
+    __syncthreads();
+    if (issuer) {
+      tma_store_2d(&prm.tm_mir, pend_row0 + 16 * (tid >> 5), pend_col0, pend_stage + (tid >> 5) * (TN * 128));
+      bulk_commit();
+    }
+  }
   cp_async_wait_all();
-  if ((tid & 31) == 0) bulk_wait_all();
+  if (issuer) bulk_wait_all();
 }
 
 // ---- launch plumbing -------------------------------------------------------------------

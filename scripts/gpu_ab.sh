@@ -1,6 +1,7 @@
 #!/bin/bash
 TAG=${1:-ab}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+echo "== pytest"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
 {
-scripts/ubench/dmma_dfma
-for m in 1 0 9 20 21 22; do OAK_SYRK_MODE=$m python scripts/quick_sgpr.py; done
-} 2>&1 | grep -v Warning | tee $OUT/sgpr.txt
+python scripts/ab_gram.py
+AB_N=65536 python scripts/ab_gram.py
+} 2>&1 | grep -v Warning | tee $OUT/ab.txt
