@@ -111,6 +111,10 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
 inline const unsigned long long* points_minmax(const oak_spec* spec, const double2* pts, int64_t n_pad) {
   return reinterpret_cast<const unsigned long long*>(pts + (int64_t)spec->D * n_pad);
 }
+// Phi(lower, column-major) += A A^T on the FP64 tensor cores (oak_syrk.cu)
+size_t syrk_dmma_work_bytes(int m);
+int syrk_lower_dmma(int m, int64_t k, double* A, int64_t lda, double* C, double* work, size_t work_bytes,
+                    int device, cudaStream_t stream);
 int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_t n_pad,
                      double* out, cudaStream_t stream);
 

@@ -180,12 +180,13 @@ constexpr size_t kFinishHeader = 16 + 8 * sizeof(double);
 // C(lower, column-major M x M) += A'^T A' with A' column-major (k x M, lda).  cuBLAS DSYRK runs
 // at full-GEMM cost on this shape (measured on B200), so the triangle is cut recursively into
 // off-diagonal rectangles (plain DGEMM, the efficient path) and small diagonal blocks:
-//   OAK_SYRK_MODE=0 one DSYRK | 1,2,3 recursion depth | 9 one full DGEMM | 20 batched blocks (default)
+//   OAK_SYRK_MODE=0 one DSYRK | 1,2,3 recursion depth | 9 one full DGEMM | 20 batched blocks
+//                 | 30 own stream-K DMMA kernel (oak_syrk.cu, default)
 static int syrk_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("OAK_SYRK_MODE");
-    v = e ? atoi(e) : 20;  // measured on B200 (scripts/quick_sgpr.py, profiles/)
+    v = e ? atoi(e) : 30;  // measured on B200 (scripts/quick_sgpr.py, profiles/): 30 = 56.7, 20 = 58.7, 1 = 76 ms / 10^6
   }
   return v;
 }
@@ -208,7 +209,7 @@ static int syrk_rec(cublasHandle_t cb, int off, int m, int k, const double* A, i
   return syrk_rec(cb, off + h, m - h, k, A, lda, C, ldc, depth - 1);
 }
 
-// Default: the lower triangle in 128 x 128 blocks as ONE batched DGEMM (diagonal blocks computed in
+// cuBLAS alternative (OAK_SYRK_MODE=20): the lower triangle in 128 x 128 blocks as ONE batched DGEMM (diagonal blocks computed in
 // full: 590 k instead of 525 k block entries at M = 1024, against 786 k for DGEMM + 2 DSYRK).
 // Measured on B200 (profiles/): 2.4 ms per 1024 x 65536 chunk against 3.4 ms.  A ragged last
 // block row (M % 128 rows) goes through one DGEMM + one small DSYRK.
@@ -265,9 +266,10 @@ static int syrk_batched(cublasHandle_t cb, int m, int k, const double* A, int ld
   return 0;
 }
 
-static int syrk_lower_accumulate(cublasHandle_t cb, int m, int k, const double* A, int lda, double* C,
-                                 cudaStream_t stream) {
+static int syrk_lower_accumulate(cublasHandle_t cb, int m, int k, double* A, int lda, double* C,
+                                 double* partials, size_t partial_bytes, int device, cudaStream_t stream) {
   const int mode = syrk_mode();
+  if (mode == 30) return syrk_lower_dmma(m, k, A, lda, C, partials, partial_bytes, device, stream);
   if (mode == 20) {
     const int rc = syrk_batched(cb, m, k, A, lda, C, stream);
     if (rc >= 0) return rc;
@@ -295,7 +297,7 @@ extern "C" size_t oak_sgpr_stats_count(int64_t m) { return m < 0 ? 0 : (size_t)(
 
 extern "C" size_t oak_sgpr_stats_work_bytes(int64_t m, int64_t chunk) {
   if (m < 0 || chunk < 0) return 0;
-  return (size_t)(m * chunk + chunk) * sizeof(double);
+  return (size_t)(m * chunk + chunk) * sizeof(double) + syrk_dmma_work_bytes((int)m);
 }
 
 extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
@@ -315,6 +317,8 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
 
   double* kuf = (double*)d_work;           // M x chunk, row-major, ld = chunk
   double* kdiag = kuf + m * chunk;         // chunk
+  double* partials = kdiag + chunk;        // stream-K partial tiles of the contraction
+  const size_t partial_bytes = syrk_dmma_work_bytes((int)m);
   double* phi = d_stats;                   // M x M
   double* kufy = d_stats + m * m;          // M
   double* tail = kufy + m;                 // sum_kdiag, yty
@@ -330,7 +334,7 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
       return rc;
     // Phi += Kuf Kuf^T.  Row-major (M x nc, ld=chunk) == column-major (nc x M, lda=chunk) A';
     // Phi = A'^T A'  ->  DSYRK(trans = T).  Only one triangle is updated.
-    if (int rc = syrk_lower_accumulate(cb, (int)m, (int)nc, kuf, (int)chunk, phi, stream)) return rc;
+    if (int rc = syrk_lower_accumulate(cb, (int)m, (int)nc, kuf, (int)chunk, phi, partials, partial_bytes, spec->device, stream)) return rc;
     // Kuf_y += Kuf y_chunk = A'^T y
     OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, (int)nc, (int)m, &one, kuf, (int)chunk, d_y + c0, 1, &one,
                            kufy, 1));

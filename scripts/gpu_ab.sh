@@ -1,7 +1,7 @@
 #!/bin/bash
 TAG=${1:-ab}; OUT=gpurun_out/$TAG; mkdir -p $OUT
-echo "== pytest"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $OUT/pytest_gpu.txt
+U=$PWD/scripts/ubench
 {
-python scripts/ab_gram.py
-AB_N=65536 python scripts/ab_gram.py
-} 2>&1 | grep -v Warning | tee $OUT/ab.txt
+OAK_SYRK_MODE=30 python scripts/quick_sgpr.py
+for v in s16x3 s16x6 s32x3; do echo $v; OAK_B200_LIB=$U/liboak_$v.so OAK_SYRK_MODE=30 python scripts/quick_sgpr.py; done
+} 2>&1 | grep -v Warning | tee $OUT/sgpr.txt
