@@ -56,7 +56,9 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled from a thread
+    (sub-millisecond period, so even the 20 ms timed region of an 8-GPU run gets samples);
+    falls back to `nvidia-smi -lms` when pynvml is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -64,8 +66,36 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.stop_flag, self.samples = None, None, False, []
+        self.max_mhz, self.reason_bits = None, 0
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(
+            nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    self.reason_bits |= int(get_reasons(self.handle))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -80,6 +110,18 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.samples)
+            if not sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            # NVML clocks-event-reason bits (nvml.h): 0x8 hw_slowdown, 0x40 hw_thermal_slowdown,
+            # 0x20 sw_thermal_slowdown, 0x4 sw_power_cap
+            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            reasons = sorted(v for k, v in names.items() if self.reason_bits & k)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -104,7 +146,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def mem_available_gb():

@@ -593,7 +593,7 @@ static int launch_small_depth(const GramParams& prm, int algo, int sms, cudaStre
   }
 }
 
-int tile_rows_for_depth(int depth) { return depth <= 4 ? 64 : 32; }
+int tile_rows_for_depth(int depth) { return depth <= 8 ? 64 : 32; }
 
 static int sm_count(int device) {
   static int cached[64] = {0};
@@ -645,10 +645,12 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
     case 2: return launch_small_depth<2>(prm, algo, sms, stream);
     case 3: return launch_small_depth<3>(prm, algo, sms, stream);
     case 4: return launch_small_depth<4>(prm, algo, sms, stream);
-    case 5: return launch_algo<5, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
-    case 6: return launch_algo<6, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
-    case 7: return launch_algo<7, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
-    case 8: return launch_algo<8, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
+    // depth 5..8: 2 x 4 micro-tile (32 x 64 tiles): 8 entries x P accumulators, the same register
+    // budget as 4 x 4 at depth 4, twice the work per staged operand of the former 2 x 2 geometry
+    case 5: return launch_algo<5, 16, 16, 2, 4, 1>(prm, algo, sms, stream);
+    case 6: return launch_algo<6, 16, 16, 2, 4, 1>(prm, algo, sms, stream);
+    case 7: return launch_algo<7, 16, 16, 2, 4, 1>(prm, algo, sms, stream);
+    case 8: return launch_algo<8, 16, 16, 2, 4, 1>(prm, algo, sms, stream);
     default:
       if (depth <= 12) return launch_algo<12, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
       return launch_algo<16, 16, 16, 2, 2, 1>(prm, algo, sms, stream);
