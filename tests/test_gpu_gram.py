@@ -250,3 +250,75 @@ def test_gram_host_pipeline_matches_device():
         assert rc == 0, _cabi.last_error()
         assert max_rel_err(out.numpy(), ref.K(X, X2)) < RTOL
     spec.close()
+
+
+def test_fast_and_general_exp_bodies_agree_per_stage():
+    """The clamp-free exp body is taken per 16-dim stage when every dim of the stage qualifies
+    (s^2 == 1, bounded |a_i - b_j|).  D = 40: stage 0 has a tiny lengthscale (general body), stage 1
+    has s^2 != 1 (general), stage 2 qualifies (fast).  All must match the oracle; and forcing the
+    general body everywhere (min/max keys ignored) must agree with the default to rounding."""
+    cfg = _gauss_cfg(300, 40, 3, seed=21)
+    cfg["dims"][3]["lengthscale"] = 0.004
+    cfg["dims"][20]["variance"] = 1.7
+    k, ref = _product(cfg), build_oracle(cfg)
+    X = cfg["X"]
+    K, Kref = k.K(X), ref.K(X)
+    assert np.all(np.isfinite(K))
+    assert max_rel_err(K, Kref) < RTOL
+    X2 = np.random.default_rng(5).standard_normal((170, 40))
+    assert max_rel_err(k.K(X, X2), ref.K(X, X2)) < RTOL
+
+
+def test_many_dims_beyond_the_fast_flag_words():
+    """D = 300 > 256: dims past the flag words always take the general body."""
+    cfg = _gauss_cfg(130, 300, 2, seed=22)
+    k, ref = _product(cfg), build_oracle(cfg)
+    assert max_rel_err(k.K(cfg["X"]), ref.K(cfg["X"])) < RTOL
+
+
+def test_unaligned_and_odd_pitch_outputs_take_the_direct_store_path():
+    """The mirrored tile leaves through TMA only for 16-byte aligned outputs with an even pitch;
+    other outputs (views at an odd offset / odd leading dimension) use direct stores.  Both paths
+    must produce the same bits."""
+    import torch
+
+    from oak_b200 import _device
+
+    cfg = _gauss_cfg(448, 6, 4, seed=23)
+    k = _product(cfg)
+    spec = k._make_spec()
+    px = _device.Points(spec, _device.to_device(cfg["X"]))
+    base = _device.gram(spec, px)                      # aligned, even pitch -> TMA mirror
+    big = torch.full((449, 451), float("nan"), dtype=torch.float64, device="cuda")
+    view = big[1:, 1:449]                              # odd pitch (451), 8-byte offset
+    _device.gram(spec, px, out=view)
+    assert torch.equal(view, base)
+    assert torch.isnan(big[0]).all() and torch.isnan(big[:, 0]).all() and torch.isnan(big[:, 449:]).all()
+    big2 = torch.full((448, 450), float("nan"), dtype=torch.float64, device="cuda")
+    view2 = big2[:, :448]                              # even pitch, aligned, wider than n -> TMA with ldk > n
+    _device.gram(spec, px, out=view2)
+    assert torch.equal(view2, base)
+    assert torch.isnan(big2[:, 448:]).all()
+    spec.close()
+
+
+def test_non_finite_inputs_poison_only_their_rows_and_columns():
+    cfg = _gauss_cfg(200, 4, 3, seed=24)
+    k, ref = _product(cfg), build_oracle(cfg)
+    X = cfg["X"].copy()
+    X[17, 2] = np.nan
+    K = k.K(X)
+    bad = np.zeros(200, bool)
+    bad[17] = True
+    assert np.all(np.isnan(K[17, :])) and np.all(np.isnan(K[:, 17]))
+    good = ~bad
+    Kref = ref.K(cfg["X"])
+    assert max_rel_err(K[np.ix_(good, good)], Kref[np.ix_(good, good)]) < RTOL
+    # +-inf: exp(-inf) = 0 in the reference; the kernel must stay finite off the poisoned point
+    X = cfg["X"].copy()
+    X[5, 1] = np.inf
+    K = k.K(X)
+    good = np.ones(200, bool)
+    good[5] = False
+    assert np.all(np.isfinite(K[np.ix_(good, good)]))
+    assert max_rel_err(K[np.ix_(good, good)], Kref[np.ix_(good, good)]) < RTOL
