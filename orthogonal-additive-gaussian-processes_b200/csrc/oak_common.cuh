@@ -67,7 +67,11 @@ struct DimDev {
 };
 
 constexpr int kPointPad = 128;  // prepared-point rows are padded to a multiple of this
-constexpr int kExpTab = 256;    // 2^(j/256) table entries
+#ifndef OAK_EXP_BITS
+#define OAK_EXP_BITS 9  // 8: 256-entry table + degree-4 Taylor; 9: 512 entries + degree-3 near-minimax
+#endif
+constexpr int kExpBits = OAK_EXP_BITS;
+constexpr int kExpTab = 1 << kExpBits;  // 2^(j/kExpTab) table entries
 
 inline int64_t padded(int64_t n) { return (n + kPointPad - 1) / kPointPad * kPointPad; }
 
@@ -119,32 +123,49 @@ int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_
                      double* out, cudaStream_t stream);
 
 // ---- fast FP64 exp(-z) on pre-scaled distances ---------------------------------------
-// Prepared RBF coordinates carry the factor sqrt(256 / ln 2): with d = a_i - b_j,
-//   d^2 = z * 256 / ln 2,  z = (x - y)^2 / (2 l^2)
+// T = kExpTab table entries of 2^(j/T).  Prepared RBF coordinates carry the factor sqrt(T / ln 2):
+// with d = a_i - b_j,
+//   d^2 = z * T / ln 2,  z = (x - y)^2 / (2 l^2)
 // so that n = -round(d^2) is the table/exponent index and w = d^2 + n (|w| <= 1/2, EXACT: both
-// products are fused) gives the reduced argument r = -w ln2/256:
-//   exp(-z) = 2^(n >> 8) * T[n & 255] * e^r,   e^r - 1 = w (C1 + w (C2 + w (C3 + w C4)))
-// 256-entry table of 2^(j/256), degree-4 polynomial (truncation 3.8e-17 relative).
-// Fast form: 9 FP64-pipe instructions from d (was 10 from z), no clamp; valid for d^2 <= 261120
-// (z <= 707), which the launcher proves per dimension from the min/max of the prepared coordinates.
-// General form (s^2 != 1 or unbounded distance): zs = d^2 - ln(s^2) 256/ln2 clamped at 261120.
+// products are fused) gives the reduced argument r = -w ln2/T:
+//   exp(-z) = 2^(n >> bits) * T[n & (T-1)] * e^r,   e^r - 1 = w * poly(w)
+// Default: T = 512 with a degree-3 near-minimax polynomial (max error 1.5e-15 relative, measured max
+// Gram error vs the oracle 1.7e-15): 8 FP64-pipe instructions from d.  OAK_EXP_BITS=8 selects
+// T = 256 with the degree-4 Taylor polynomial (3.8e-17, measured 6e-16) at one instruction more;
+// measured on config B: 0.991 vs 0.933 of the roofline (profiles/).
+// Fast form: no clamp; valid for |d| <= kFastSpan (z <= 704), which the launcher proves per
+// dimension from the min/max of the prepared coordinates.
+// General form (s^2 != 1 or unbounded distance): zs = d^2 - ln(s^2) T/ln2, clamped at z ~ 707.
 //
-// Measured on B200 (scripts/ubench, profiles/): integer-ALU instructions (LOP3/SHF/LEA/IADD3/
-// VIMNMX) steal issue cycles from the FP64 pipe, IMAD (FMA pipe) does not.  The index math is
-// therefore IMAD only:
-//   off = mulhi(n << 24, 2^15) + lane_bits = (n & 255) * 128 + lane_bits   IMAD.SHL + IMAD.HI
-//   hi  = n * 4096 + T'hi[j]                                               IMAD
-// with the table's high words stored pre-compensated, T'hi[j] = hi(2^(j/256)) - (j << 12), so
-// that adding n << 12 = (k << 20) + (j << 12) inserts the binary exponent k without masking.
-// `tab_bytes` is the table base in shared memory (entry j, replica lane % 16 at j*128 + (lane%16)*8:
-// a half-warp never bank-conflicts), `lane_bits` = (lane % 16) * 8.
+// Measured on B200 (scripts/ubench, profiles/): an FP64 instruction holds the issue port for two
+// cycles and every other instruction for one, without overlap; integer-ALU forms (LOP3/SHF/VIMNMX)
+// are the expensive ones, IMAD (FMA pipe) the cheap one.  The index math is therefore
+//   off = mulhi(n << (32-bits), 2^(bits+7)) + lane_bits = (n & (T-1)) * 128 + lane_bits   IMAD.SHL + LEA.HI
+//   hi  = n * 2^(20-bits) + T'hi[j]                                                      IMAD
+// with the table's high words stored pre-compensated, T'hi[j] = hi(2^(j/T)) - (j << (20-bits)), so
+// that adding n << (20-bits) = (k << 20) + (j << (20-bits)) inserts the binary exponent k without
+// masking.  `tab_bytes` is the table base in shared memory (entry j, replica lane % 16 at
+// j*128 + (lane%16)*8: a half-warp never bank-conflicts), `lane_bits` = (lane % 16) * 8.
+#if OAK_EXP_BITS == 8
 constexpr double kXScale = 19.217958540583197;      // sqrt(256 / ln 2)
 constexpr double kXScale2 = 369.3299304675746271;   // 256 / ln 2
-constexpr double kLn2Over256 = 0.0027076061740622863;
-constexpr double kFastSpan = 510.0;                 // |d| bound of the clamp-free form (d^2 <= 260100)
+constexpr double kInvXScale2 = 0.0027076061740622863;  // ln 2 / 256
+constexpr double kFastSpan = 510.0;                 // |d| bound of the clamp-free form (z <= 704)
+constexpr int kHiClampScaled = 0x410fe000;          // hi word of 261120.0 (z ~ 707)
+#elif OAK_EXP_BITS == 9
+constexpr double kXScale = 27.17829760921661;       // sqrt(512 / ln 2)
+constexpr double kXScale2 = 738.6598609351493;      // 512 / ln 2
+constexpr double kInvXScale2 = 0.0013538030870311431;  // ln 2 / 512
+constexpr double kFastSpan = 721.0;                 // d^2 <= 519841 (z <= 703.8)
+constexpr int kHiClampScaled = 0x411fe000;          // hi word of 522240.0 (z ~ 707)
+#else
+#error "OAK_EXP_BITS must be 8 or 9"
+#endif
 #ifdef __CUDACC__
 __device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char* __restrict__ tab_bytes,
                                            unsigned lane_bits) {
+#if OAK_EXP_BITS == 8
+  // degree-4 Taylor in r = -w ln2/256: truncation 3.8e-17
   constexpr double C1 = -0.0027076061740622863;
   constexpr double C2 = 3.6655655969101062e-06;
   constexpr double C3 = -3.3083026805413713e-09;
@@ -152,30 +173,42 @@ __device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char
   double p = fma(w, C4, C3);
   p = fma(p, w, C2);
   p = fma(p, w, C1);
+#else
+  // degree-3 near-minimax (Chebyshev least squares on |w| <= 1/2) in r = -w ln2/512: max error
+  // 1.5e-15 relative (Taylor would give 8.8e-15); one FP64 instruction fewer per entry
+  constexpr double C1 = -0.0013538030870311425;
+  constexpr double C2 = 9.163914283863184e-07;
+  constexpr double C3 = -4.1353784691025013e-10;
+  double p = fma(w, C3, C2);
+  p = fma(p, w, C1);
+#endif
   const double q = p * w;  // e^r - 1
 #ifndef OAK_IDX_MODE
 #define OAK_IDX_MODE 0  // development switch, see scripts/ubench/fp64_mix3.cu
 #endif
+  constexpr unsigned kShl = 1u << (32 - kExpBits);  // n << (32 - bits): the table index in the top bits
+  constexpr unsigned kMulHi = 1u << (kExpBits + 7); // ... >> (32 - bits - 7): byte offset j * 128
+  constexpr int kExpIns = 1 << (20 - kExpBits);     // n * 2^(20 - bits) = (k << 20) + (j << (20 - bits))
   unsigned off;
 #if OAK_IDX_MODE == 0    // IMAD.SHL + LEA.HI
-  asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(off) : "r"((unsigned)ni * 16777216u), "r"(lane_bits));
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(off) : "r"((unsigned)ni * kShl), "n"(kMulHi), "r"(lane_bits));
 #elif OAK_IDX_MODE == 1  // IMAD.SHL + IMAD.HI.U32 (multiplier kept opaque in a register)
   unsigned m15;
-  asm volatile("mov.u32 %0, 32768;" : "=r"(m15));
-  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(off) : "r"((unsigned)ni * 16777216u), "r"(m15), "r"(lane_bits));
+  asm volatile("mov.u32 %0, %1;" : "=r"(m15) : "n"(kMulHi));
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(off) : "r"((unsigned)ni * kShl), "r"(m15), "r"(lane_bits));
 #elif OAK_IDX_MODE == 2  // IMAD.SHL + IMAD.WIDE.U32, high word
   unsigned m15;
-  asm volatile("mov.u32 %0, 32768;" : "=r"(m15));
+  asm volatile("mov.u32 %0, %1;" : "=r"(m15) : "n"(kMulHi));
   unsigned long long wide;
-  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(wide) : "r"((unsigned)ni * 16777216u), "r"(m15),
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(wide) : "r"((unsigned)ni * kShl), "r"(m15),
       "l"((unsigned long long)lane_bits << 32));
   off = (unsigned)(wide >> 32);
 #else                    // IMAD.SHL + LOP3 (round-1 form)
-  off = (((unsigned)ni * 128u) & 0x7F80u) | lane_bits;
+  off = (((unsigned)ni * 128u) & (unsigned)((kExpTab - 1) << 7)) | lane_bits;
 #endif
   const uint2 tv = *reinterpret_cast<const uint2*>(tab_bytes + off);
   int thi;
-  asm("mad.lo.s32 %0, %1, 4096, %2;" : "=r"(thi) : "r"(ni), "r"((int)tv.y));
+  asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(thi) : "r"(ni), "n"(kExpIns), "r"((int)tv.y));
   const double t = __hiloint2double(thi, (int)tv.x);
   return fma(t, q, t);
 }
@@ -194,7 +227,7 @@ __device__ __forceinline__ double exp_neg_sq_fast(double d, const unsigned char*
 __device__ __forceinline__ double exp_neg_scaled(double zs, const unsigned char* __restrict__ tab_bytes,
                                                  unsigned lane_bits) {
   constexpr double kMagic = 6755399441055744.0;
-  constexpr int kHiClamp = 0x410fe000;  // hi word of 261120.0
+  constexpr int kHiClamp = kHiClampScaled;
   int hi = __double2hiint(zs);
   hi = min(hi, kHiClamp);  // (sign bit set => negative int => untouched)
   zs = __hiloint2double(hi, __double2loint(zs));

@@ -27,7 +27,7 @@ __device__ __forceinline__ double dim_value(bool discrete, double aux, const dou
     return tbl[__double2hiint(a.x) + __double2loint(b.x)];
   }
   const double t = a.x - b.x;  // prepared coordinates carry sqrt(256/ln2)
-  return fma(-a.y, b.y, exp(-fma(t * t, kLn2Over256, aux)));
+  return fma(-a.y, b.y, exp(-fma(t * t, kInvXScale2, aux)));
 }
 
 __global__ void component_gram_kernel(SubsetParams sp, const double* __restrict__ tables,

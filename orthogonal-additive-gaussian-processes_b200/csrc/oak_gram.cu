@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
   for (int i = tid; i < L::kTabDoubles; i += kThreads) {
     const int j = i >> 4;
     const double v = prm.exptab[j];
-    sTab[i] = __hiloint2double(__double2hiint(v) - (j << 12), __double2loint(v));
+    sTab[i] = __hiloint2double(__double2hiint(v) - (j << (20 - kExpBits)), __double2loint(v));
   }
   const unsigned char* tab_bytes = smem_raw;
   const unsigned lane_bits = (unsigned)(tx & 15) * 8u;

@@ -14,7 +14,7 @@ std::atomic<long long> g_launches{0};
 
 void set_error(const std::string& msg) { t_error = msg; }
 
-// 2^(j/256) table, one copy per device.
+// 2^(j/kExpTab) table, one copy per device.
 static std::mutex g_tab_mu;
 static double* g_exptab[64] = {nullptr};
 
