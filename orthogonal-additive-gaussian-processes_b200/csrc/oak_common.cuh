@@ -68,7 +68,7 @@ struct DimDev {
 
 constexpr int kPointPad = 128;  // prepared-point rows are padded to a multiple of this
 #ifndef OAK_EXP_BITS
-#define OAK_EXP_BITS 9  // 8: 256-entry table + degree-4 Taylor; 9: 512 entries + degree-3 near-minimax
+#define OAK_EXP_BITS 10  // 8: 256-entry table + degree-4 Taylor; 9 / 10: 512 / 1024 entries + degree-3 near-minimax
 #endif
 constexpr int kExpBits = OAK_EXP_BITS;
 constexpr int kExpTab = 1 << kExpBits;  // 2^(j/kExpTab) table entries
@@ -129,10 +129,11 @@ int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_
 // so that n = -round(d^2) is the table/exponent index and w = d^2 + n (|w| <= 1/2, EXACT: both
 // products are fused) gives the reduced argument r = -w ln2/T:
 //   exp(-z) = 2^(n >> bits) * T[n & (T-1)] * e^r,   e^r - 1 = w * poly(w)
-// Default: T = 512 with a degree-3 near-minimax polynomial (max error 1.5e-15 relative, measured max
-// Gram error vs the oracle 1.7e-15): 8 FP64-pipe instructions from d.  OAK_EXP_BITS=8 selects
-// T = 256 with the degree-4 Taylor polynomial (3.8e-17, measured 6e-16) at one instruction more;
-// measured on config B: 0.991 vs 0.933 of the roofline (profiles/).
+// Default: T = 1024 with a degree-3 near-minimax polynomial (max error 9.5e-17 relative, measured
+// max Gram error vs the oracle 6e-16): 8 FP64-pipe instructions from d.  The table is replicated
+// 8x in shared memory (64 KB).  Alternatives kept for A/B runs (profiles/): T = 512, 16 replicas
+// (1.5e-15, 0.4 % faster); T = 256 with the degree-4 Taylor polynomial (3.8e-17, one FP64
+// instruction more: 0.933 vs 0.99 of the roofline on config B).
 // Fast form: no clamp; valid for |d| <= kFastSpan (z <= 704), which the launcher proves per
 // dimension from the min/max of the prepared coordinates.
 // General form (s^2 != 1 or unbounded distance): zs = d^2 - ln(s^2) T/ln2, clamped at z ~ 707.
@@ -140,12 +141,13 @@ int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_
 // Measured on B200 (scripts/ubench, profiles/): an FP64 instruction holds the issue port for two
 // cycles and every other instruction for one, without overlap; integer-ALU forms (LOP3/SHF/VIMNMX)
 // are the expensive ones, IMAD (FMA pipe) the cheap one.  The index math is therefore
-//   off = mulhi(n << (32-bits), 2^(bits+7)) + lane_bits = (n & (T-1)) * 128 + lane_bits   IMAD.SHL + LEA.HI
+//   off = mulhi(n << (32-bits), 8R 2^bits) + lane_bits = (n & (T-1)) * 8R + lane_bits   IMAD.SHL + LEA.HI
 //   hi  = n * 2^(20-bits) + T'hi[j]                                                      IMAD
 // with the table's high words stored pre-compensated, T'hi[j] = hi(2^(j/T)) - (j << (20-bits)), so
 // that adding n << (20-bits) = (k << 20) + (j << (20-bits)) inserts the binary exponent k without
-// masking.  `tab_bytes` is the table base in shared memory (entry j, replica lane % 16 at
-// j*128 + (lane%16)*8: a half-warp never bank-conflicts), `lane_bits` = (lane % 16) * 8.
+// masking.  `tab_bytes` is the table base in shared memory (entry j, replica lane % R at
+// j*8R + (lane%R)*8; R = 16: a half-warp never bank-conflicts, R = 8: two-way at worst),
+// `lane_bits` = (lane % R) * 8.
 #if OAK_EXP_BITS == 8
 constexpr double kXScale = 19.217958540583197;      // sqrt(256 / ln 2)
 constexpr double kXScale2 = 369.3299304675746271;   // 256 / ln 2
@@ -158,9 +160,21 @@ constexpr double kXScale2 = 738.6598609351493;      // 512 / ln 2
 constexpr double kInvXScale2 = 0.0013538030870311431;  // ln 2 / 512
 constexpr double kFastSpan = 721.0;                 // d^2 <= 519841 (z <= 703.8)
 constexpr int kHiClampScaled = 0x411fe000;          // hi word of 522240.0 (z ~ 707)
+#elif OAK_EXP_BITS == 10
+constexpr double kXScale = 38.435917081166394;      // sqrt(1024 / ln 2)
+constexpr double kXScale2 = 1477.3197218702985;     // 1024 / ln 2
+constexpr double kInvXScale2 = 0.0006769015435155716;  // ln 2 / 1024
+constexpr double kFastSpan = 1019.0;                // d^2 <= 1038361 (z <= 702.9)
+constexpr int kHiClampScaled = 0x412fe000;          // hi word of 1044480.0 (z ~ 707)
 #else
-#error "OAK_EXP_BITS must be 8 or 9"
+#error "OAK_EXP_BITS must be 8, 9 or 10"
 #endif
+#ifndef OAK_EXP_REPL
+#define OAK_EXP_REPL 8  // shared-memory replicas of the table (entry stride = replicas * 8 bytes)
+#endif
+constexpr int kExpRepl = OAK_EXP_REPL;
+constexpr int kExpReplLog2 = kExpRepl == 16 ? 4 : (kExpRepl == 8 ? 3 : -1);
+static_assert(kExpReplLog2 > 0, "OAK_EXP_REPL must be 8 or 16");
 #ifdef __CUDACC__
 __device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char* __restrict__ tab_bytes,
                                            unsigned lane_bits) {
@@ -173,12 +187,19 @@ __device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char
   double p = fma(w, C4, C3);
   p = fma(p, w, C2);
   p = fma(p, w, C1);
-#else
+#elif OAK_EXP_BITS == 9
   // degree-3 near-minimax (Chebyshev least squares on |w| <= 1/2) in r = -w ln2/512: max error
   // 1.5e-15 relative (Taylor would give 8.8e-15); one FP64 instruction fewer per entry
   constexpr double C1 = -0.0013538030870311425;
   constexpr double C2 = 9.163914283863184e-07;
   constexpr double C3 = -4.1353784691025013e-10;
+  double p = fma(w, C3, C2);
+  p = fma(p, w, C1);
+#else
+  // degree-3 near-minimax in r = -w ln2/1024: max error 9.5e-17 relative
+  constexpr double C1 = -0.0006769015435155716;
+  constexpr double C2 = 2.290978516293061e-07;
+  constexpr double C3 = -5.1692229753539507e-11;
   double p = fma(w, C3, C2);
   p = fma(p, w, C1);
 #endif
@@ -187,7 +208,7 @@ __device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char
 #define OAK_IDX_MODE 0  // development switch, see scripts/ubench/fp64_mix3.cu
 #endif
   constexpr unsigned kShl = 1u << (32 - kExpBits);  // n << (32 - bits): the table index in the top bits
-  constexpr unsigned kMulHi = 1u << (kExpBits + 7); // ... >> (32 - bits - 7): byte offset j * 128
+  constexpr unsigned kMulHi = 1u << (kExpBits + 3 + kExpReplLog2);  // ... byte offset j * (replicas * 8)
   constexpr int kExpIns = 1 << (20 - kExpBits);     // n * 2^(20 - bits) = (k << 20) + (j << (20 - bits))
   unsigned off;
 #if OAK_IDX_MODE == 0    // IMAD.SHL + LEA.HI
@@ -204,7 +225,7 @@ __device__ __forceinline__ double exp_tail(double w, int ni, const unsigned char
       "l"((unsigned long long)lane_bits << 32));
   off = (unsigned)(wide >> 32);
 #else                    // IMAD.SHL + LOP3 (round-1 form)
-  off = (((unsigned)ni * 128u) & (unsigned)((kExpTab - 1) << 7)) | lane_bits;
+  off = (((unsigned)ni * (8u * kExpRepl)) & (unsigned)((kExpTab - 1) << (3 + kExpReplLog2))) | lane_bits;
 #endif
   const uint2 tv = *reinterpret_cast<const uint2*>(tab_bytes + off);
   int thi;

@@ -54,7 +54,7 @@ constexpr int kFastWords = 8;  // clamp-free exp flags for the first 256 continu
 template <int TXD, int TYD, int RM, int RN>
 struct SmemLayout {
   static constexpr int TM = TYD * RM, TN = TXD * RN;
-  static constexpr int kTabDoubles = kExpTab * 16;
+  static constexpr int kTabDoubles = kExpTab * kExpRepl;
   static constexpr int kStageDouble2 = kDimChunk * (TM + TN);
   // Staging of the transposed tile (symmetric mode) for the TMA stores: TM/16 sub-tiles of
   // [TN rows][16 doubles] in the 128-byte swizzle the tensor map declares; two buffers,
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
   constexpr int TM = L::TM, TN = L::TN;
   constexpr int RS = TN / TM;  // row sub-tiles per TN-sized triangle block (symmetric modes)
   constexpr int kThreads = TXD * TYD;
-  static_assert(TXD % 16 == 0, "the exp-table replicas are indexed by lane % 16");
+  static_assert(TXD % kExpRepl == 0, "the exp-table replicas are indexed by lane % kExpRepl");
   static_assert(TN % TM == 0, "triangle blocks are TN x TN");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sTab = reinterpret_cast<double*>(smem_raw);
@@ -184,15 +184,15 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
   int pend = 0, pend_row0 = 0, pend_col0 = 0;                  // mirrored tile staged, not yet issued
   unsigned pend_stage = 0;
 
-  // replicate the exp table: entry j, replica r at sTab[j*16 + r]
+  // replicate the exp table: entry j, replica r at sTab[j*kExpRepl + r]
   // (high words pre-compensated by -(j << 12), see exp_tail)
   for (int i = tid; i < L::kTabDoubles; i += kThreads) {
-    const int j = i >> 4;
+    const int j = i / kExpRepl;
     const double v = prm.exptab[j];
     sTab[i] = __hiloint2double(__double2hiint(v) - (j << (20 - kExpBits)), __double2loint(v));
   }
   const unsigned char* tab_bytes = smem_raw;
-  const unsigned lane_bits = (unsigned)(tx & 15) * 8u;
+  const unsigned lane_bits = (unsigned)(tx & (kExpRepl - 1)) * 8u;
 
   const int D = prm.D, Dc = prm.Dc;
   const int num_chunks = (D + kDimChunk - 1) / kDimChunk;

@@ -1,7 +1,7 @@
 // Per-point prologue and K_diag.
 //
 // Prepared-point block ("points"): double2 pts[D][n_pad], feature-major, kernel order (RBF dims
-// first).  RBF dim:   .x = x sqrt(256/ln2) / (sqrt(2) l)   .y = cov_X_s(x) / sqrt(var_s())
+// first).  RBF dim:   .x = x sqrt(T/ln2) / (sqrt(2) l), T = kExpTab   .y = cov_X_s(x) / sqrt(var_s())
 //          discrete:  .x = bits{lo: idx, hi: idx*C}         .y = B_diag[idx]
 // Padding rows (n <= i < n_pad) hold zeros so that tiles can be loaded without bounds checks.
 // The block ends with 2 D uint64 keys: per-dimension min and max of .x over the n real points
