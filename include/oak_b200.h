@@ -168,7 +168,8 @@ size_t oak_sgpr_stats_work_bytes(int64_t m, int64_t chunk);
 /* Replaces the Kuf build + A A^T contraction of SGPR.elbo / get_model_sufficient_statistics
  * (oak/utils.py:180-191; gpflow Kuf at utils.py:184).  Streams the local n points in chunks:
  * Kuf chunk (M x chunk, L2 resident) -> Phi += Kuf Kuf^T (cuBLAS DSYRK), Kuf_y += Kuf y,
- * sum_kdiag += sum K_diag(X), yty += y^T y.  Accumulates INTO d_stats (caller zeroes it). */
+ * sum_kdiag += sum K_diag(X), yty += y^T y.  Accumulates INTO d_stats (caller zeroes it).
+ * The contraction runs on the FP64 tensor cores (csrc/oak_syrk.cu). */
 int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
                        const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
                        double* d_stats, void* d_work, void* stream);
@@ -203,6 +204,25 @@ int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
                             const int32_t* d_subsets, const double* d_scale,
                             int32_t num_components, int32_t max_order, const double* d_alpha,
                             double* d_out, void* stream);
+
+/* ---- backward tiles (training) ------------------------------------------------------ */
+/* Replaces TensorFlow's autodiff through OAKKernel.K / K_diag inside the gpflow objectives
+ * (oak/oak_kernel.py:223-278 differentiated; optimiser loop at oak/model_utils.py:168-175).
+ * For a cotangent W = d objective / d K (rows [row_begin,row_end) of points x all of points2,
+ * pitch ldw; d_points2 == NULL => the same point set):
+ *   d_grad[i]             += sum W * dK/d lengthscale_i   (i = sub-kernel in the caller's order;
+ *                            RBF sub-kernels with a Gaussian measure or none -- entries of other
+ *                            sub-kernels are left untouched)
+ *   d_grad[num_dims + n]  += sum W * e_n = dK/d sigma2_n  (n = 0..max_interaction_depth)
+ * max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points). */
+size_t oak_gram_backward_work_bytes(const oak_spec* spec, int64_t n);
+int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                          int64_t row_end, const void* d_points2, int64_t n2, const double* d_W,
+                          int64_t ldw, double* d_grad, void* d_work, void* stream);
+/* Same for wscale * sum_i w_i K_diag(x_i) (d_w == NULL => all ones). */
+int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, int64_t n,
+                               const double* d_w, double wscale, double* d_grad, void* d_work,
+                               void* stream);
 
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Dependent-chain DFMA microbenchmark: writes achieved FP64 issue slots / second to

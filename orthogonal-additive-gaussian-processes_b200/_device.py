@@ -199,6 +199,49 @@ def component_predict(spec: Spec, subsets: Sequence[Sequence[int]], px: Points, 
     return out
 
 
+# ---- backward tiles ---------------------------------------------------------------------
+def gram_backward(spec: Spec, px: Points, W, px2: Optional[Points] = None, row_begin: int = 0,
+                  row_end: Optional[int] = None, grad=None):
+    """grad[:D] += sum W dK/d lengthscale_i, grad[D:] += sum W e_n for K(px[row_begin:row_end], px2)."""
+    torch = _torch()
+    lib = _cabi.load()
+    n = px.n
+    n2 = n if px2 is None else px2.n
+    row_end = n if row_end is None else row_end
+    nout = spec.num_dims + max(spec.depth, 1) + 1
+    if grad is None:
+        grad = torch.zeros(nout, dtype=torch.float64, device=px.buf.device)
+    if row_end > row_begin and n2 > 0:
+        assert W.shape == (row_end - row_begin, n2) and W.stride(1) == 1
+        work = torch.empty(max(int(lib.oak_gram_backward_work_bytes(spec.handle, max(n, n2))) // 8, 1),
+                           dtype=torch.float64, device=px.buf.device)
+        check(
+            lib.oak_gram_backward_f64(spec.handle, _p(px.buf), n, row_begin, row_end,
+                                      _p(None if px2 is None else px2.buf), n2, _p(W), int(W.stride(0)), _p(grad),
+                                      _p(work), C.c_void_p(stream_ptr())),
+            "oak_gram_backward_f64",
+        )
+    return grad
+
+
+def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad=None):
+    """grad += d/d theta of wscale * sum_i w_i K_diag(x_i)."""
+    torch = _torch()
+    lib = _cabi.load()
+    nout = spec.num_dims + max(spec.depth, 1) + 1
+    if grad is None:
+        grad = torch.zeros(nout, dtype=torch.float64, device=px.buf.device)
+    if px.n > 0:
+        work = torch.empty(max(int(lib.oak_gram_backward_work_bytes(spec.handle, px.n)) // 8, 1),
+                           dtype=torch.float64, device=px.buf.device)
+        check(
+            lib.oak_gram_diag_backward_f64(spec.handle, _p(px.buf), px.n, _p(w), float(wscale), _p(grad), _p(work),
+                                           C.c_void_p(stream_ptr())),
+            "oak_gram_diag_backward_f64",
+        )
+    return grad
+
+
 # ---- SGPR / GPR -------------------------------------------------------------------------
 def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 65536, stats=None):
     """Accumulates Phi | Kuf y | sum K_diag | y^T y for the local points into ``stats``."""

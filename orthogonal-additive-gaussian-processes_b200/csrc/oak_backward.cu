@@ -1,0 +1,484 @@
+// Backward pass of the fused OAK tiles: the reference trains by
+// TensorFlow autodiff through OAKKernel.K (oak/oak_kernel.py:223-265) inside gpflow's objectives
+// (oak/model_utils.py:168-175).  Here the same contraction is done tile by tile:
+//
+//   grad[l_d]       += sum_ij W_ij * dK_ij/dk~_d * dk~_d/dl_d        (RBF dims, Gaussian measure or none)
+//   grad[sigma2_n]  += sum_ij W_ij * e_n(k~_1..k~_D)_ij              (n = 0..P)
+//
+// for a caller-supplied cotangent W (d objective / d K).  Per entry, sweep 1 over the dimensions
+// builds e_1..e_P with the direct recurrence (registers), sweep 2 recomputes each k~_d and forms
+//   dK/dk~_d = sum_n sigma2_n e_{n-1}^{(-d)},  e_m^{(-d)} = e_m - k~_d e_{m-1}^{(-d)}   (removal recurrence)
+//   dk~/dl   = ex * z * 2/l - c^i c^j (kappa + u_i + u_j)
+// with ex = s^2 exp(-z), z = (x-y)^2/(2 l^2), c^ = cov_X_s / sqrt(var_s), and for the Gaussian measure
+// N(mu, delta^2): kappa = 1/l + l/(l^2+2 delta^2) - 2l/(l^2+delta^2), u(x) = (x-mu)^2 l/(l^2+delta^2)^2
+// (ortho_rbf_kernel.py:82-97 differentiated by hand; checked against torch autograd in tests/).
+// No per-dimension N x N2 derivative matrix is ever formed; W is read once per entry.
+// Reductions are deterministic: warp shuffles -> per-warp shared slots -> per-CTA partials ->
+// one fixed-order pass over the CTAs.
+#include "oak_common.cuh"
+
+namespace oak {
+
+namespace bw {
+constexpr int kDimChunk = 16;
+constexpr int kThreads = 256;
+constexpr int kTXD = 16, kTYD = 16;
+constexpr int kMaxDims = 512;  // per-warp shared slots for the lengthscale partials
+}  // namespace bw
+
+struct BwDim {      // per sub-kernel (kernel order)
+  double kappa;     // d log(prefactor of c^ c^) / dl
+  double uc;        // l / (l^2 + delta^2)^2
+  double mu;
+  double inv_xscale;  // prepared coordinate -> x
+  double c2;        // (2 / l) * ln2 / kExpTab : ex * d'^2 * c2 = ex * z * 2 / l
+  double supported; // 1: lengthscale gradient available; 0: not (discrete dim / other measure)
+};
+
+struct BwParams {
+  double sigma2[OAK_MAX_DEPTH + 1];
+  const double2* pts_row;
+  const double2* pts_col;
+  const double* dim_aux;
+  const double* tables;
+  const double* exptab;
+  const BwDim* bwdims;
+  const double* W;
+  double* partial;  // [grid][D + P + 1]
+  int64_t n_row_pad, n_col_pad, ldw;
+  int64_t row_begin, row_end, n2;
+  int64_t tiles_n, num_tiles;
+  int D, Dc;
+};
+
+template <int P, int RM, int RN>
+__global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const BwParams prm) {
+  using namespace bw;
+  constexpr int TM = kTYD * RM, TN = kTXD * RN;
+  constexpr int kTabDoubles = kExpTab * kExpRepl;
+  constexpr int kStageDouble2 = kDimChunk * (TM + TN);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sTab = reinterpret_cast<double*>(smem_raw);
+  double2* sStage = reinterpret_cast<double2*>(sTab + kTabDoubles);
+  double* sAux = reinterpret_cast<double*>(sStage + 2 * kStageDouble2);
+  double* sG = sAux + 2 * kDimChunk;  // [8 warps][D + P + 1]
+
+  const int tid = threadIdx.x;
+  const int tx = tid % kTXD, ty = tid / kTXD;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int D = prm.D, Dc = prm.Dc;
+  const int nout = D + P + 1;
+  for (int i = tid; i < kTabDoubles; i += kThreads) {
+    const int j = i / kExpRepl;
+    const double v = prm.exptab[j];
+    sTab[i] = __hiloint2double(__double2hiint(v) - (j << (20 - kExpBits)), __double2loint(v));
+  }
+  for (int i = tid; i < 8 * nout; i += kThreads) sG[i] = 0.0;
+  const unsigned char* tab_bytes = smem_raw;
+  const unsigned lane_bits = (unsigned)(tx & (kExpRepl - 1)) * 8u;
+  const int num_chunks = (D + kDimChunk - 1) / kDimChunk;
+  double* myG = sG + warp * nout;
+  __syncthreads();
+
+  auto issue_stage = [&](int64_t row0, int64_t col0, int ch, int buf) {
+    const int d0 = ch * kDimChunk;
+    const int nd = min(kDimChunk, D - d0);
+    double2* dst = sStage + buf * kStageDouble2;
+    for (int o = tid; o < TM + TN; o += kThreads) {
+      const double2* src = (o < TM) ? prm.pts_row + (int64_t)d0 * prm.n_row_pad + prm.row_begin + row0 + o
+                                    : prm.pts_col + (int64_t)d0 * prm.n_col_pad + col0 + (o - TM);
+      const int64_t stride = (o < TM) ? prm.n_row_pad : prm.n_col_pad;
+      for (int dl = 0; dl < nd; ++dl) cp_async16(dst + dl * (TM + TN) + o, src + dl * stride);
+    }
+    if (tid < nd) cp_async8(sAux + buf * kDimChunk + tid, prm.dim_aux + d0 + tid);
+    cp_async_commit();
+  };
+
+  const int64_t nrows = prm.row_end - prm.row_begin;
+  for (int64_t t = blockIdx.x; t < prm.num_tiles; t += gridDim.x) {
+    const int64_t bi = t / prm.tiles_n;
+    const int64_t row0 = bi * TM, col0 = (t - bi * prm.tiles_n) * TN;
+
+    double E[RM][RN][P];  // e_1..e_P (direct recurrence)
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+      for (int c = 0; c < RN; ++c)
+#pragma unroll
+        for (int p = 0; p < P; ++p) E[r][c][p] = 0.0;
+
+    // ---- sweep 1: elementary symmetric polynomials ------------------------------------------
+    int buf = 0;
+    issue_stage(row0, col0, 0, 0);
+    for (int ch = 0; ch < num_chunks; ++ch) {
+      cp_async_wait_all();
+      __syncthreads();
+      if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
+      const double2* sRow = sStage + buf * kStageDouble2;
+      const double* aux = sAux + buf * kDimChunk;
+      const int d0 = ch * kDimChunk;
+      const int nd = min(kDimChunk, D - d0);
+#pragma unroll 1
+      for (int dl = 0; dl < nd; ++dl) {
+        const double2* rowp = sRow + dl * (TM + TN);
+        const double2* colp = rowp + TM;
+        double2 rv[RM], cv[RN];
+#pragma unroll
+        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
+#pragma unroll
+        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
+        const bool cont = d0 + dl < Dc;
+        const double ax = aux[dl];
+        const double* tbl = cont ? nullptr : prm.tables + (int)__double_as_longlong(ax);
+#pragma unroll
+        for (int r = 0; r < RM; ++r)
+#pragma unroll
+          for (int c = 0; c < RN; ++c) {
+            double k;
+            if (cont) {
+              const double d = rv[r].x - cv[c].x;
+              k = fma(-rv[r].y, cv[c].y, exp_neg_scaled(fma(d, d, ax), tab_bytes, lane_bits));
+            } else {
+              k = __ldg(tbl + __double2hiint(rv[r].x) + __double2loint(cv[c].x));
+            }
+#pragma unroll
+            for (int p = P - 1; p >= 1; --p) E[r][c][p] = fma(k, E[r][c][p - 1], E[r][c][p]);
+            E[r][c][0] += k;
+          }
+      }
+      buf ^= 1;
+    }
+
+    // ---- cotangent tile + order-variance gradients --------------------------------------------
+    double wv[RM][RN];
+    double gs[P + 1];
+#pragma unroll
+    for (int p = 0; p <= P; ++p) gs[p] = 0.0;
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+      for (int c = 0; c < RN; ++c) {
+        const int64_t row = row0 + ty * RM + r, col = col0 + tx + kTXD * c;
+        wv[r][c] = (row < nrows && col < prm.n2) ? __ldcs(prm.W + row * prm.ldw + col) : 0.0;
+        gs[0] += wv[r][c];
+#pragma unroll
+        for (int p = 1; p <= P; ++p) gs[p] = fma(wv[r][c], E[r][c][p - 1], gs[p]);
+      }
+#pragma unroll
+    for (int p = 0; p <= P; ++p) {
+      double v = gs[p];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) myG[D + p] += v;
+    }
+
+    // ---- sweep 2: lengthscale gradients ---------------------------------------------------------
+    __syncthreads();  // everybody has left sweep 1's last buffer before it is overwritten
+    buf = 0;
+    issue_stage(row0, col0, 0, 0);
+    for (int ch = 0; ch < num_chunks; ++ch) {
+      cp_async_wait_all();
+      __syncthreads();
+      if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
+      const double2* sRow = sStage + buf * kStageDouble2;
+      const double* aux = sAux + buf * kDimChunk;
+      const int d0 = ch * kDimChunk;
+      const int nc = max(0, min(min(kDimChunk, D - d0), Dc - d0));  // continuous dims of this chunk
+#pragma unroll 1
+      for (int dl = 0; dl < nc; ++dl) {
+        const BwDim bd = prm.bwdims[d0 + dl];
+        if (bd.supported == 0.0) continue;
+        const double2* rowp = sRow + dl * (TM + TN);
+        const double2* colp = rowp + TM;
+        double2 rv[RM], cv[RN];
+        double ur[RM], uc[RN];
+#pragma unroll
+        for (int r = 0; r < RM; ++r) {
+          rv[r] = rowp[ty * RM + r];
+          const double xm = fma(rv[r].x, bd.inv_xscale, -bd.mu);
+          ur[r] = fma(xm * xm, bd.uc, bd.kappa);  // kappa + u_i
+        }
+#pragma unroll
+        for (int c = 0; c < RN; ++c) {
+          cv[c] = colp[tx + kTXD * c];
+          const double xm = fma(cv[c].x, bd.inv_xscale, -bd.mu);
+          uc[c] = xm * xm * bd.uc;
+        }
+        const double ax = aux[dl];
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < RM; ++r)
+#pragma unroll
+          for (int c = 0; c < RN; ++c) {
+            const double d = rv[r].x - cv[c].x;
+            const double d2 = d * d;
+            const double ex = exp_neg_scaled(d2 + ax, tab_bytes, lane_bits);
+            const double cc = rv[r].y * cv[c].y;
+            const double k = ex - cc;
+            // removal recurrence: g_m = e_m - k g_{m-1}; dK/dk = sum_n sigma2_n g_{n-1}
+            double g = 1.0;
+            double dKdk = prm.sigma2[1];
+#pragma unroll
+            for (int m = 1; m < P; ++m) {
+              g = fma(-k, g, E[r][c][m - 1]);
+              dKdk = fma(prm.sigma2[m + 1], g, dKdk);
+            }
+            const double dkdl = fma(ex * d2, bd.c2, -cc * (ur[r] + uc[c]));
+            acc = fma(wv[r][c] * dKdk, dkdl, acc);
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) myG[d0 + dl] += acc;
+      }
+      buf ^= 1;
+    }
+    __syncthreads();  // stage buffers are re-issued by the next tile
+  }
+
+  // ---- per-CTA partials (fixed order over the warps) ---------------------------------------------
+  __syncthreads();
+  for (int i = tid; i < nout; i += kThreads) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += sG[w * nout + i];
+    prm.partial[(int64_t)blockIdx.x * nout + i] = v;
+  }
+}
+
+// grad[i] += sum over CTAs (fixed order); the lengthscale part is scattered to the caller's
+// dimension order
+__global__ void backward_reduce_kernel(const double* __restrict__ partial, int grid, int nout, int D,
+                                       const int* __restrict__ orig_of_pos, double* __restrict__ grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nout) return;
+  double v = 0.0;
+  for (int b = 0; b < grid; ++b) v += partial[(int64_t)b * nout + i];
+  const int dst = i < D ? orig_of_pos[i] : i;
+  grad[dst] += v;
+}
+
+// K_diag backward: one thread per point; grad += sum_i w_i dK_diag(x_i)/d theta
+struct DiagBwParams {
+  double sigma2[OAK_MAX_DEPTH + 1];
+  int D, Dc, depth;
+};
+
+__global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, const DimDev* __restrict__ dims,
+                                                            const BwDim* __restrict__ bwdims,
+                                                            const double2* __restrict__ pts, int64_t n,
+                                                            int64_t n_pad, const double* __restrict__ w,
+                                                            double wscale, double* __restrict__ partial) {
+  extern __shared__ double sh[];  // [8 warps][nout]
+  const int P = prm.depth;
+  const int nout = prm.D + P + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 8 * nout; i += 256) sh[i] = 0.0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * 256 + tid;
+  const bool live = i < n;
+  double e[OAK_MAX_DEPTH + 1];
+#pragma unroll
+  for (int p = 0; p <= OAK_MAX_DEPTH; ++p) e[p] = 0.0;
+  e[0] = 1.0;
+  const double wi = live ? (w ? w[i] : 1.0) * wscale : 0.0;
+  for (int k = 0; k < prm.D; ++k) {
+    const double2 v = pts[(int64_t)k * n_pad + (live ? i : 0)];
+    const double kd = (k < prm.Dc) ? dims[k].s2 - v.y * v.y : v.y;
+#pragma unroll
+    for (int p = OAK_MAX_DEPTH; p >= 1; --p)
+      if (p <= P) e[p] = fma(kd, e[p - 1], e[p]);
+  }
+  for (int p = 0; p <= P; ++p) {
+    double v = wi * e[p];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp * nout + prm.D + p] += v;
+  }
+  for (int k = 0; k < prm.Dc; ++k) {
+    const BwDim bd = bwdims[k];
+    if (bd.supported == 0.0) continue;
+    const double2 v = pts[(int64_t)k * n_pad + (live ? i : 0)];
+    const double cc = v.y * v.y;
+    const double kd = dims[k].s2 - cc;
+    double g = 1.0, dKdk = prm.sigma2[1];
+    for (int m = 1; m < P; ++m) {
+      g = fma(-kd, g, e[m]);
+      dKdk = fma(prm.sigma2[m + 1], g, dKdk);
+    }
+    const double xm = fma(v.x, bd.inv_xscale, -bd.mu);
+    double c = wi * dKdk * (-cc * (bd.kappa + 2.0 * xm * xm * bd.uc));
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) sh[warp * nout + k] += c;
+  }
+  __syncthreads();
+  for (int j = tid; j < nout; j += 256) {
+    double v = 0.0;
+    for (int wq = 0; wq < 8; ++wq) v += sh[wq * nout + j];
+    partial[(int64_t)blockIdx.x * nout + j] = v;
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vector<int>& orig_of_pos) {
+  out.assign(spec->D, BwDim{0, 0, 0, 0, 0, 0});
+  orig_of_pos.assign(spec->D, 0);
+  for (int k = 0; k < spec->D; ++k) {
+    const DimDev& dd = spec->h_dims[k];
+    orig_of_pos[k] = dd.orig;
+    if (dd.type != OAK_DIM_RBF) continue;
+    const double l = dd.lengthscale;
+    BwDim b;
+    b.inv_xscale = 1.0 / dd.xscale;
+    b.c2 = (2.0 / l) * kInvXScale2;
+    b.mu = 0.0;
+    b.kappa = 0.0;
+    b.uc = 0.0;
+    b.supported = 0.0;
+    if (dd.measure == OAK_MEASURE_NONE) {
+      b.supported = 1.0;  // c^ = 0: only the ex z 2/l term survives
+    } else if (dd.measure == OAK_MEASURE_GAUSSIAN) {
+      const double l2d = 0.5 / dd.c2;      // l^2 + delta^2
+      const double delta2 = l2d - l * l;
+      b.mu = dd.c1;
+      b.kappa = 1.0 / l + l / (l * l + 2.0 * delta2) - 2.0 * l / l2d;
+      b.uc = l / (l2d * l2d);
+      b.supported = 1.0;
+    }
+    out[k] = b;
+  }
+  return 0;
+}
+
+template <int P, int RM, int RN>
+static int launch_backward(BwParams prm, int grid_max, cudaStream_t stream, int* grid_out) {
+  using namespace bw;
+  constexpr int TM = kTYD * RM, TN = kTXD * RN;
+  const int64_t rows = prm.row_end - prm.row_begin;
+  prm.tiles_n = (prm.n2 + TN - 1) / TN;
+  prm.num_tiles = ((rows + TM - 1) / TM) * prm.tiles_n;
+  const size_t smem = sizeof(double) * kExpTab * kExpRepl + 2 * sizeof(double2) * kDimChunk * (TM + TN) +
+                      2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (prm.D + P + 1);
+  auto kern = gram_backward_kernel<P, RM, RN>;
+  OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)(prm.num_tiles < grid_max ? prm.num_tiles : grid_max);
+  *grid_out = grid;
+  kern<<<grid, kThreads, smem, stream>>>(prm);
+  OAK_LAUNCHED();
+  return 0;
+}
+
+}  // namespace oak
+
+using namespace oak;
+
+// workspace: per-dimension constants + dimension map + per-CTA partials
+extern "C" size_t oak_gram_backward_work_bytes(const oak_spec* spec, int64_t n) {
+  if (!spec || n < 0) return 0;
+  const size_t nout = (size_t)spec->D + spec->depth + 2;
+  const size_t blocks = (size_t)((n + 255) / 256);
+  const size_t ctas = blocks > 1024 ? blocks : 1024;
+  return 256 + (size_t)spec->D * (sizeof(BwDim) + sizeof(int)) + 64 + ctas * nout * sizeof(double);
+}
+
+static int stage_bwdims(const oak_spec* spec, void* d_work, cudaStream_t stream, const BwDim** d_bw,
+                        const int** d_map, double** d_partial) {
+  std::vector<BwDim> h;
+  std::vector<int> map;
+  build_bwdims(spec, h, map);
+  char* w = (char*)d_work;
+  BwDim* dbw = (BwDim*)w;
+  w += (size_t)spec->D * sizeof(BwDim);
+  int* dmap = (int*)w;
+  w += ((size_t)spec->D * sizeof(int) + 63) / 64 * 64;
+  // pageable sources: the copies are staged before the calls return
+  OAK_CUDA(cudaMemcpyAsync(dbw, h.data(), h.size() * sizeof(BwDim), cudaMemcpyHostToDevice, stream));
+  OAK_CUDA(cudaMemcpyAsync(dmap, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+  *d_bw = dbw;
+  *d_map = dmap;
+  *d_partial = (double*)w;
+  return 0;
+}
+
+// grad[0..D) += d/d lengthscale of sub-kernel i (caller's order; unsupported ones untouched),
+// grad[D..D+depth] += d/d sigma2_n, for rows [row_begin,row_end) of points x all points2
+// (points2 == NULL: the same point set), cotangent W (rows x n2, pitch ldw).
+extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                                     int64_t row_end, const void* d_points2, int64_t n2, const double* d_W,
+                                     int64_t ldw, double* d_grad, void* d_work, void* stream_) {
+  OAK_REQUIRE(spec && d_points && d_grad && d_work, "oak_gram_backward_f64: null argument");
+  const bool same = d_points2 == nullptr;
+  if (same) n2 = n;
+  OAK_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n, "oak_gram_backward_f64: bad row range");
+  if (row_end == row_begin || n2 <= 0) return 0;
+  OAK_REQUIRE(d_W && ldw >= n2, "oak_gram_backward_f64: bad cotangent");
+  OAK_REQUIRE(row_begin % 64 == 0, "oak_gram_backward_f64: row_begin must be a multiple of 64");
+  OAK_REQUIRE(spec->D <= bw::kMaxDims, "oak_gram_backward_f64: too many dimensions");
+  const int depth = spec->depth < 1 ? 1 : spec->depth;
+  OAK_REQUIRE(depth <= 8, "oak_gram_backward_f64: max_interaction_depth > 8 is not supported by the backward tiles");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const BwDim* d_bw;
+  const int* d_map;
+  double* d_partial;
+  if (int rc = stage_bwdims(spec, d_work, stream, &d_bw, &d_map, &d_partial)) return rc;
+  BwParams prm;
+  for (int p = 0; p <= OAK_MAX_DEPTH; ++p) prm.sigma2[p] = spec->sigma2[p];
+  prm.pts_row = (const double2*)d_points;
+  prm.pts_col = same ? (const double2*)d_points : (const double2*)d_points2;
+  prm.n_row_pad = padded(n);
+  prm.n_col_pad = padded(n2);
+  prm.dim_aux = spec->d_gram_aux;
+  prm.tables = spec->d_tables;
+  prm.exptab = spec->d_exptab;
+  prm.bwdims = d_bw;
+  prm.W = d_W;
+  prm.ldw = ldw;
+  prm.partial = d_partial;
+  prm.row_begin = row_begin;
+  prm.row_end = row_end;
+  prm.n2 = n2;
+  prm.D = spec->D;
+  prm.Dc = spec->Dc;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, spec->device);
+  int grid = 0, rc = 0;
+  switch (depth) {
+    case 1: rc = launch_backward<1, 2, 4>(prm, sms, stream, &grid); break;
+    case 2: rc = launch_backward<2, 2, 4>(prm, sms, stream, &grid); break;
+    case 3: rc = launch_backward<3, 2, 4>(prm, sms, stream, &grid); break;
+    case 4: rc = launch_backward<4, 2, 4>(prm, sms, stream, &grid); break;
+    case 5: rc = launch_backward<5, 2, 2>(prm, sms, stream, &grid); break;
+    case 6: rc = launch_backward<6, 2, 2>(prm, sms, stream, &grid); break;
+    case 7: rc = launch_backward<7, 2, 2>(prm, sms, stream, &grid); break;
+    default: rc = launch_backward<8, 2, 2>(prm, sms, stream, &grid); break;
+  }
+  if (rc) return rc;
+  const int nout = spec->D + depth + 1;
+  backward_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(d_partial, grid, nout, spec->D, d_map, d_grad);
+  OAK_LAUNCHED();
+  return 0;
+}
+
+// grad += d/d theta of  wscale * sum_i w_i K_diag(x_i)   (w == NULL: all ones)
+extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, const double* d_w,
+                                          double wscale, double* d_grad, void* d_work, void* stream_) {
+  OAK_REQUIRE(spec && d_points && d_grad && d_work, "oak_gram_diag_backward_f64: null argument");
+  if (n <= 0) return 0;
+  const int depth = spec->depth < 1 ? 1 : spec->depth;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const BwDim* d_bw;
+  const int* d_map;
+  double* d_partial;
+  if (int rc = stage_bwdims(spec, d_work, stream, &d_bw, &d_map, &d_partial)) return rc;
+  DiagBwParams prm;
+  for (int p = 0; p <= OAK_MAX_DEPTH; ++p) prm.sigma2[p] = spec->sigma2[p];
+  prm.D = spec->D;
+  prm.Dc = spec->Dc;
+  prm.depth = depth;
+  const int nout = spec->D + depth + 1;
+  const int blocks = (int)((n + 255) / 256);
+  diag_backward_kernel<<<blocks, 256, 8 * nout * sizeof(double), stream>>>(
+      prm, spec->d_dims, d_bw, (const double2*)d_points, n, padded(n), d_w, wscale, d_partial);
+  OAK_LAUNCHED();
+  backward_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(d_partial, blocks, nout, spec->D, d_map, d_grad);
+  OAK_LAUNCHED();
+  return 0;
+}

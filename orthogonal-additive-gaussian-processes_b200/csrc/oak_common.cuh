@@ -258,6 +258,18 @@ __device__ __forceinline__ double exp_neg_scaled(double zs, const unsigned char*
   return exp_tail(w, __double2loint(nd), tab_bytes, lane_bits);
 }
 
+// ---- cp.async (LDGSTS) staging helpers ------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n"); }
+
 // monotone uint64 keys for atomicMin / atomicMax on doubles
 __device__ __forceinline__ unsigned long long order_key(double x) {
   const long long b = __double_as_longlong(x);

@@ -75,9 +75,11 @@ def create_model_oak(
     # small initial noise to avoid the all-noise optimum (:167)
     model.likelihood.variance.assign(0.01)
     if optimise:
-        raise NotImplementedError(
-            "hyper-parameter optimisation needs kernel gradients (SURVEY.md section 8(f), next row 1)"
-        )
+        # gpflow.optimizers.Scipy().minimize(training_loss_closure, trainable_variables, method="BFGS")
+        # (model_utils.py:168-173): same optimiser, gradients from the backward tiles
+        from .training import optimise as _optimise
+
+        _optimise(model, method="BFGS")
     return model
 
 
@@ -260,6 +262,13 @@ class oak_model:
         if not self.use_normalising_flow:
             X[:, self.continuous_index] = self.scaler_X_continuous.transform(X[:, self.continuous_index])
         return X
+
+    def optimise(self, compile: bool = True):
+        """BFGS on the training loss (:410-427); ``compile`` is accepted for signature parity."""
+        from .training import optimise as _optimise
+
+        self.alpha = None
+        return _optimise(self.m, method="BFGS")
 
     def predict(self, X, clip=False):
         X = np.asarray(X, dtype=np.float64)

@@ -61,6 +61,13 @@ class GPModel(Module):
     def training_loss_closure(self):
         return self.training_loss
 
+    def training_loss_and_grad(self):
+        """(training_loss, d/d unconstrained trainables): what TensorFlow autodiff hands to the scipy
+        optimiser in the reference (model_utils.py:168-175); see training.py."""
+        from .training import training_loss_and_grad
+
+        return training_loss_and_grad(self)
+
 
 class GPR(GPModel):
     """Exact GP regression: ``log N(y; 0, K + noise I)`` (gpflow ``GPR``; model_utils.py:159)."""

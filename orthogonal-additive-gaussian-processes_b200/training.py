@@ -1,0 +1,253 @@
+"""Objective gradients and the hyper-parameter optimisation step.
+
+The reference trains with ``gpflow.optimizers.Scipy().minimize(model.training_loss_closure(),
+model.trainable_variables, method="BFGS")`` (oak/model_utils.py:168-175, 410-427) on the unconstrained
+variables, gradients by TensorFlow autodiff through ``OAKKernel.K``.  Here the gradient of the
+objective with respect to the kernel matrices is formed on the device (dense M x M / N x N algebra
+through the cuSOLVER / cuBLAS bindings of torch -- plumbing), and contracted with dK/d theta by the
+backward tiles of ``liboak_b200.so`` (``oak_gram_backward_f64``): no per-dimension derivative
+matrix is ever formed.
+
+Supported trainable parameters: RBF lengthscales of sub-kernels with a Gaussian measure (the OAK
+default after the normalising flow) or no measure, the order variances sigma^2_0..P
+(``share_var_across_orders=True``) and the likelihood variance.  Any other *trainable* parameter
+raises ``NotImplementedError`` (set it non-trainable to keep it fixed).
+
+SGPR (gpflow 2.2.1 ``SGPR.elbo``), with Phi = Kuf Kuf^T, b = Kuf y, s = sum K_diag,
+Q = Kuu + jitter I, S = Q + Phi / noise:
+
+    elbo = -N/2 log 2pi - 1/2 (log|S| - log|Q|) - N/2 log noise - y^T y / (2 noise)
+           + b^T S^-1 b / (2 noise^2) - s / (2 noise) + tr(Q^-1 Phi) / (2 noise)
+
+    d/dPhi = -S^-1/(2 noise) - S^-1 b b^T S^-1/(2 noise^3) + Q^-1/(2 noise)
+    d/db   = S^-1 b / noise^2            d/ds = -1/(2 noise)
+    d/dQ   = -S^-1/2 + Q^-1/2 - S^-1 b b^T S^-1/(2 noise^2) - Q^-1 Phi Q^-1/(2 noise)
+
+(checked against torch autograd of the gpflow operation order in tests/test_gpu_training.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import _cabi, _device, parallel
+from ._gpflow_shim import DEFAULT_JITTER, Identity, Parameter, Sigmoid, Softplus, collect_parameters, scalar_of, value_of
+
+
+# ---- d constrained / d unconstrained of the gpflow transforms -------------------------------
+def _transform_grad(p: Parameter) -> np.ndarray:
+    u = np.asarray(p.unconstrained_variable, dtype=np.float64)
+    t = p.transform
+    if isinstance(t, Identity):
+        return np.ones_like(u)
+    if isinstance(t, Softplus):
+        return 1.0 / (1.0 + np.exp(-u))
+    if isinstance(t, Sigmoid):
+        s = 1.0 / (1.0 + np.exp(-u))
+        return (t.high - t.low) * s * (1.0 - s)
+    raise NotImplementedError(f"transform {type(t).__name__}")
+
+
+def _prior_grad(p: Parameter) -> np.ndarray:
+    """d log prior / d constrained value (only the Gamma prior of the order variances exists)."""
+    x = p.numpy()
+    pr = p.prior
+    return (pr.concentration - 1.0) / x - pr.rate
+
+
+def _lengthscale_parameter(sub):
+    base = getattr(sub, "base_kernel", sub)
+    return getattr(base, "lengthscales", None)
+
+
+def _supported_parameters(model) -> Tuple[List[Parameter], List[Parameter], Parameter]:
+    """(per-dimension lengthscale Parameters or None, order variances, noise)."""
+    kern = model.kernel
+    ls = [_lengthscale_parameter(k) for k in kern.kernels]
+    return ls, list(kern.variances), model.likelihood.variance
+
+
+def freeze_unsupported(model) -> List[Parameter]:
+    """Sets ``trainable=False`` on every parameter the backward tiles cannot differentiate
+    (inducing points, base-kernel variances, categorical W / kappa, ...); returns them."""
+    ls, var, noise = _supported_parameters(model)
+    ok = {id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
+    frozen = []
+    for p in collect_parameters(model):
+        if p.trainable and id(p) not in ok:
+            p.trainable = False
+            frozen.append(p)
+    return frozen
+
+
+def _check_trainables(model, spec_dims):
+    ls, var, noise = _supported_parameters(model)
+    ok = {id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
+    for p in collect_parameters(model):
+        if p.trainable and id(p) not in ok:
+            raise NotImplementedError(
+                "gradient of a trainable parameter outside {RBF lengthscales, order variances, likelihood variance} "
+                f"is not implemented ({p!r}); set it non-trainable")
+    if not getattr(model.kernel, "share_var_across_orders", True):
+        raise NotImplementedError("backward tiles need share_var_across_orders=True")
+    for p, d in zip(ls, spec_dims):
+        if p is not None and p.trainable:
+            if d.type != _cabi.DIM_RBF or d.measure not in (_cabi.MEASURE_NONE, _cabi.MEASURE_GAUSSIAN):
+                raise NotImplementedError("lengthscale gradients exist for Gaussian-measure / unconstrained RBF "
+                                          "sub-kernels only; set the other lengthscales non-trainable")
+
+
+# ---- objectives with gradients (constrained space) --------------------------------------------
+def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
+    """(elbo, d/d lengthscales [num sub-kernels], d/d order variances [P+1], d/d noise)."""
+    torch = _device._torch()
+    Xd, Yd = model._device_data()
+    Xs = model._slice_for_kernel(Xd)
+    Zs = model._Z_device()
+    noise = scalar_of(model.likelihood.variance)
+    kern = model.kernel
+    spec = kern._make_spec()
+    try:
+        _check_trainables(model, spec._keep)
+        kern._check_discrete(Xs, spec._keep)
+        kern._check_discrete(Zs, spec._keep)
+        pz, px = _device.Points(spec, Zs), _device.Points(spec, Xs)
+        m, n_local = pz.n, px.n
+        stats = _device.sgpr_stats(spec, pz, px, Yd, chunk=model.chunk)
+        n_total = n_local
+        if model.distributed:
+            parallel.allreduce_sum_(stats)
+            n_total = parallel.allreduce_int(n_total)
+        Kuu = _device.gram(spec, pz)
+        # statistics: Phi arrives as column-major lower == upper triangle of the row-major view
+        U = torch.triu(stats[: m * m].view(m, m))
+        Phi = U + torch.triu(U, 1).T
+        b = stats[m * m: m * m + m].reshape(m, 1)
+        s, yty = float(stats[m * m + m]), float(stats[m * m + m + 1])
+        eye = torch.eye(m, dtype=torch.float64, device=Kuu.device)
+        Q = Kuu + DEFAULT_JITTER * eye
+        S = Q + Phi / noise
+        LQ, LS = torch.linalg.cholesky(Q), torch.linalg.cholesky(S)
+        Qi, Si = torch.cholesky_inverse(LQ), torch.cholesky_inverse(LS)
+        Sib = Si @ b
+        QiPhi = Qi @ Phi
+        logdet = 2.0 * float(torch.log(torch.diagonal(LS)).sum() - torch.log(torch.diagonal(LQ)).sum())
+        bSb = float((b * Sib).sum())
+        trQiPhi = float(torch.diagonal(QiPhi).sum())
+        elbo = (-0.5 * n_total * math.log(2.0 * math.pi) - 0.5 * logdet - 0.5 * n_total * math.log(noise)
+                - 0.5 * yty / noise + 0.5 * bSb / noise ** 2 - 0.5 * s / noise + 0.5 * trQiPhi / noise)
+        SbbS = Sib @ Sib.T
+        G_phi = -0.5 * Si / noise - SbbS / (2.0 * noise ** 3) + Qi / (2.0 * noise)
+        g_b = Sib / noise ** 2
+        G_Q = -0.5 * Si + 0.5 * Qi - SbbS / (2.0 * noise ** 2) - (QiPhi @ Qi) / (2.0 * noise)
+        g_s = -0.5 / noise
+        g_noise = (-0.5 * n_total / noise + 0.5 * yty / noise ** 2 - bSb / noise ** 3 + 0.5 * s / noise ** 2
+                   - 0.5 * trQiPhi / noise ** 2 + 0.5 * float((Si * Phi).sum()) / noise ** 2
+                   + 0.5 * float((Sib * (Phi @ Sib)).sum()) / noise ** 4)
+        # second pass over the local points: W^T = 2 Kuf^T G_phi + y g_b^T, contracted by the backward tiles
+        nout = spec.num_dims + max(spec.depth, 1) + 1
+        grad = torch.zeros(nout, dtype=torch.float64, device=Kuu.device)
+        chunk = max(64, (int(model.chunk) + 63) // 64 * 64)
+        G2 = (2.0 * G_phi).contiguous()
+        for c0 in range(0, n_local, chunk):
+            c1 = min(c0 + chunk, n_local)
+            Kt = _device.gram(spec, px, pz, row_begin=c0, row_end=c1)  # (nc, M) = Kuf[:, c0:c1]^T
+            Wt = torch.addmm(Yd[c0:c1].reshape(-1, 1) @ g_b.T, Kt, G2)
+            _device.gram_backward(spec, px, Wt, px2=pz, row_begin=c0, row_end=c1, grad=grad)
+            del Kt, Wt
+        _device.gram_diag_backward(spec, px, wscale=g_s, grad=grad)
+        if model.distributed:
+            parallel.allreduce_sum_(grad)
+        _device.gram_backward(spec, pz, G_Q.contiguous(), grad=grad)  # Kuu term (replicated, added once)
+        g = grad.cpu().numpy()
+    finally:
+        spec.close()
+    D = spec.num_dims
+    return elbo, g[:D].copy(), g[D:].copy(), float(g_noise)
+
+
+def gpr_lml_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
+    """(log marginal likelihood, d/d lengthscales, d/d order variances, d/d noise)."""
+    torch = _device._torch()
+    Xd, Yd = model._device_data()
+    Xs = model._slice_for_kernel(Xd)
+    noise = scalar_of(model.likelihood.variance)
+    kern = model.kernel
+    spec = kern._make_spec()
+    try:
+        _check_trainables(model, spec._keep)
+        kern._check_discrete(Xs, spec._keep)
+        px = _device.Points(spec, Xs)
+        n = px.n
+        K = _device.gram(spec, px)
+        K.diagonal().add_(noise)
+        L = torch.linalg.cholesky(K)
+        alpha = torch.cholesky_solve(Yd.reshape(-1, 1), L)
+        lml = float(-0.5 * (Yd.reshape(-1, 1) * alpha).sum() - torch.log(torch.diagonal(L)).sum()
+                    - 0.5 * n * math.log(2.0 * math.pi))
+        Kinv = torch.cholesky_inverse(L)
+        W = (0.5 * (alpha @ alpha.T - Kinv)).contiguous()
+        g_noise = float(torch.diagonal(W).sum())
+        g = _device.gram_backward(spec, px, W).cpu().numpy()
+    finally:
+        spec.close()
+    D = spec.num_dims
+    return lml, g[:D].copy(), g[D:].copy(), g_noise
+
+
+# ---- training loss on the unconstrained variables (gpflow's trainable_variables) -----------------
+def trainable_parameters(model) -> List[Parameter]:
+    return [p for p in collect_parameters(model) if p.trainable]
+
+
+def training_loss_and_grad(model) -> Tuple[float, np.ndarray]:
+    """-(objective + log prior) and its gradient w.r.t. the concatenated unconstrained trainables."""
+    from .models import SGPR
+
+    if isinstance(model, SGPR):
+        val, g_ls, g_var, g_noise = sgpr_elbo_and_grad(model)
+    else:
+        val, g_ls, g_var, g_noise = gpr_lml_and_grad(model)
+    ls, var, noise = _supported_parameters(model)
+    cgrad: Dict[int, np.ndarray] = {}
+    for p, g in zip(ls, g_ls):
+        if p is not None:
+            cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
+    for p, g in zip(var, g_var):
+        cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
+    cgrad[id(noise)] = np.full(noise.numpy().shape, g_noise, dtype=np.float64)
+    loss = -(val + model.log_prior_density())
+    parts = []
+    for p in trainable_parameters(model):
+        gc = cgrad[id(p)].copy()
+        if p.prior is not None:
+            gc = gc + _prior_grad(p)
+        parts.append((-(gc) * _transform_grad(p)).reshape(-1))
+    return float(loss), (np.concatenate(parts) if parts else np.zeros(0))
+
+
+def _assign_unconstrained(params: List[Parameter], u: np.ndarray):
+    off = 0
+    for p in params:
+        k = int(np.prod(p.unconstrained_variable.shape)) if np.ndim(p.unconstrained_variable) else 1
+        p.unconstrained_variable = np.asarray(u[off: off + k], dtype=np.float64).reshape(np.shape(p.unconstrained_variable))
+        off += k
+
+
+def optimise(model, method: str = "BFGS", maxiter: int = 1000, **options):
+    """``gpflow.optimizers.Scipy().minimize(model.training_loss_closure(), model.trainable_variables,
+    method="BFGS")`` (oak/model_utils.py:168-175, 410-427) on the unconstrained variables."""
+    from scipy.optimize import minimize
+
+    params = trainable_parameters(model)
+    u0 = np.concatenate([np.asarray(p.unconstrained_variable, dtype=np.float64).reshape(-1) for p in params])
+
+    def fun(u):
+        _assign_unconstrained(params, u)
+        return training_loss_and_grad(model)
+
+    res = minimize(fun, u0, jac=True, method=method, options=dict(maxiter=maxiter, **options))
+    _assign_unconstrained(params, res.x)
+    return res

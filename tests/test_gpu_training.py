@@ -1,0 +1,139 @@
+"""Backward tiles and objective gradients against torch autograd of the
+gpflow operation order (oracle/oak_grad_oracle.py, CPU float64).  The reference differentiates by
+TensorFlow autodiff and holds no gradient fixtures, so the oracle here is autograd of the restated
+forward pass, whose VALUES are pinned against oracle/oak_oracle.py in the same tests."""
+import numpy as np
+import pytest
+
+from helpers import build_oracle, max_rel_err
+from oracle import oak_grad_oracle as go
+from oracle import oak_oracle as oo
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(n, D, P, m, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, D))
+    y = (np.sin(X[:, 0]) + X[:, 1] * X[:, min(2, D - 1)] + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
+    ls = rng.uniform(0.5, 2.5, D)
+    var = list(rng.uniform(0.2, 1.2, P + 1))
+    dims = [{"type": "rbf", "lengthscale": float(l), "variance": 1.0, "measure": ("gaussian", 0.0, 1.0)} for l in ls]
+    return dict(X=X, y=y, Z=X[:m].copy(), dims=dims, depth=P, variances=var, share_var=True, noise=0.05), ls, np.array(var)
+
+
+@pytest.mark.parametrize("D,P", [(3, 1), (5, 2), (6, 3), (5, 4), (20, 3), (7, 6), (8, 8)])
+def test_backward_tiles_match_autograd(D, P):
+    """sum W * K(X, X2) differentiated by the tiles vs autograd, ragged sizes, cross and self."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var = _cfg(210, D, P, 70, seed=10 * D + P)
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    rng = np.random.default_rng(3)
+    Xd, Zd = _device.to_device(cfg["X"]), _device.to_device(cfg["Z"])
+    px, pz = _device.Points(spec, Xd), _device.Points(spec, Zd)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    for (pa, A), (pb, B) in (((px, cfg["X"]), (pz, cfg["Z"])), ((pz, cfg["Z"]), (pz, cfg["Z"]))):
+        W = rng.standard_normal((A.shape[0], B.shape[0]))
+        g = _device.gram_backward(spec, pa, _device.to_device(W), px2=pb).cpu().numpy()
+        lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
+        (t(W) * go.oak_K(t(A), t(B), lsT, vT)).sum().backward()
+        assert max_rel_err(g[:D], lsT.grad.numpy()) < 1e-10
+        assert max_rel_err(g[D:], vT.grad.numpy()) < 1e-10
+    # K_diag
+    w = rng.standard_normal(210)
+    g = _device.gram_diag_backward(spec, px, wscale=0.7, w=_device.to_device(w, ndim=1)).cpu().numpy()
+    lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
+    (0.7 * t(w) * go.oak_K_diag(t(cfg["X"]), lsT, vT)).sum().backward()
+    assert max_rel_err(g[:D], lsT.grad.numpy()) < 1e-10
+    assert max_rel_err(g[D:], vT.grad.numpy()) < 1e-10
+    spec.close()
+
+
+def test_backward_row_ranges_add_up():
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var = _cfg(500, 6, 3, 90, seed=5)
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    Xd, Zd = _device.to_device(cfg["X"]), _device.to_device(cfg["Z"])
+    px, pz = _device.Points(spec, Xd), _device.Points(spec, Zd)
+    W = torch.randn(500, 90, dtype=torch.float64, device="cuda")
+    full = _device.gram_backward(spec, px, W, px2=pz)
+    acc = torch.zeros_like(full)
+    for b, e in ((0, 128), (128, 320), (320, 500)):
+        _device.gram_backward(spec, px, W[b:e].contiguous(), px2=pz, row_begin=b, row_end=e, grad=acc)
+    assert max_rel_err(acc.cpu().numpy(), full.cpu().numpy()) < 1e-12
+    spec.close()
+
+
+@pytest.mark.parametrize("chunk", [128, 8192])
+def test_sgpr_elbo_gradient_matches_autograd(chunk):
+    from oak_b200.models import SGPR
+    from oak_b200.training import freeze_unsupported, sgpr_elbo_and_grad
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var = _cfg(600, 5, 3, 48, seed=2)
+    m = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=chunk)
+    m.likelihood.variance.assign(cfg["noise"])
+    freeze_unsupported(m)  # inducing points (zfixed=True in the reference) and the unit base variances
+    elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
+    v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], cfg["Z"], ls, var, cfg["noise"])
+    ref = oo.sgpr_elbo(build_oracle(cfg), cfg["X"], cfg["y"], cfg["Z"], cfg["noise"])
+    assert abs(v - ref) < 1e-9 * abs(ref)          # the autograd oracle's value is the NumPy oracle's
+    assert abs(elbo - ref) < 1e-9 * abs(ref)
+    assert abs(elbo - m.elbo()) < 1e-9 * abs(ref)  # and the gpflow-order value of the product path
+    assert max_rel_err(g_ls, a_ls) < 1e-7
+    assert max_rel_err(g_var, a_var) < 1e-7
+    assert abs(g_noise - a_noise) < 1e-7 * abs(a_noise)
+
+
+def test_gpr_lml_gradient_matches_autograd():
+    from oak_b200.models import GPR
+    from oak_b200.training import freeze_unsupported, gpr_lml_and_grad
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var = _cfg(300, 4, 4, 10, seed=4)
+    m = GPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg))
+    m.likelihood.variance.assign(cfg["noise"])
+    freeze_unsupported(m)
+    lml, g_ls, g_var, g_noise = gpr_lml_and_grad(m)
+    v, a_ls, a_var, a_noise = go.value_and_grad(go.gpr_lml, cfg["X"], cfg["y"], None, ls, var, cfg["noise"])
+    assert abs(lml - v) < 1e-9 * abs(v)
+    assert max_rel_err(g_ls, a_ls) < 1e-7
+    assert max_rel_err(g_var, a_var) < 1e-7
+    assert abs(g_noise - a_noise) < 1e-7 * abs(a_noise)
+
+
+def test_training_loss_gradient_and_bfgs_improve_the_bound():
+    """d training_loss / d unconstrained variables (softplus transforms, Gamma(1, 0.2) prior on the order
+    variances, model_utils.py:163-167) against autograd + the same chain, then a few BFGS steps (the
+    reference's own training test only asserts that the objective improves: test_optimisation.py:45,70)."""
+    from oak_b200.model_utils import create_model_oak
+    from oak_b200.training import optimise, trainable_parameters, training_loss_and_grad
+
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((400, 3))
+    y = (X[:, 0] ** 2 + 2 * X[:, 1] + X[:, 0] * X[:, 1] + 0.1 * rng.standard_normal(400)).reshape(-1, 1)
+    y = (y - y.mean()) / y.std()
+    Z = X[:40].copy()
+    model = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=Z, optimise=False)
+    params = trainable_parameters(model)
+    assert len(params) == 3 + 3 + 1  # lengthscales, order variances, likelihood variance (Z is fixed)
+    loss0, g = training_loss_and_grad(model)
+    assert abs(loss0 - model.training_loss()) < 1e-9 * abs(loss0)
+    # expected: autograd of the ELBO, prior gradient, softplus chain (initial values: l = 1, sigma2 = 1, noise = 0.01)
+    v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, X, y, Z, np.ones(3), np.ones(3), 0.01)
+    sp = lambda x, lower=0.0: 1.0 - np.exp(-(x - lower))  # d softplus / du at softplus(u) + lower = x
+    want = np.concatenate([-a_ls * sp(1.0), -(a_var - 0.2) * sp(1.0), [-a_noise * sp(0.01, 1e-6)]])
+    assert max_rel_err(g, want) < 1e-7
+    res = optimise(model, method="BFGS", maxiter=15)
+    assert model.training_loss() < loss0 - 1.0
+    assert np.isfinite(res.fun)
