@@ -426,6 +426,25 @@ def main():
                 "work_model": f"{SLOTS_C} slots per Kuf entry (tile 352 + DSYRK 512.5 + Kuf y 1)"},
         }
 
+        # one training step of the same model: ELBO + gradient w.r.t. lengthscales, order variances and
+        # noise (backward tiles) -- what each BFGS iteration of oak_model.fit costs
+        try:
+            from oak_b200.training import freeze_unsupported, sgpr_elbo_and_grad
+
+            freeze_unsupported(model)
+            sgpr_elbo_and_grad(model)
+            barrier()
+            a.record()
+            for _ in range(2):
+                g_out = sgpr_elbo_and_grad(model)
+            b2.record()
+            torch.cuda.synchronize()
+            ms_grad = max_over_ranks(a.elapsed_time(b2) / 2)
+            elbo["training_step"] = {"metric": "SGPR ELBO + gradient evals/sec", "value": 1e3 / ms_grad,
+                                     "ms_per_eval": ms_grad, "grad_norm_lengthscales": float(np.abs(g_out[1]).max())}
+        except Exception as exc:  # the headline must not depend on the widening row
+            elbo["training_step"] = {"error": repr(exc)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
