@@ -24,6 +24,8 @@ Q = Kuu + jitter I, S = Q + Phi / noise:
     d/dQ   = -S^-1/2 + Q^-1/2 - S^-1 b b^T S^-1/(2 noise^2) - Q^-1 Phi Q^-1/(2 noise)
 
 (checked against torch autograd of the gpflow operation order in tests/test_gpu_training.py).
+S^-1 and Q^-1 are never formed from S itself: with L = chol(Q), B = I + L^-1 Phi L^-T / noise (gpflow's
+whitened matrix, always well conditioned), S^-1 = L^-T B^-1 L^-1 and log|S| - log|Q| = log|B|.
 """
 from __future__ import annotations
 
@@ -128,12 +130,19 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         s, yty = float(stats[m * m + m]), float(stats[m * m + m + 1])
         eye = torch.eye(m, dtype=torch.float64, device=Kuu.device)
         Q = Kuu + DEFAULT_JITTER * eye
-        S = Q + Phi / noise
-        LQ, LS = torch.linalg.cholesky(Q), torch.linalg.cholesky(S)
-        Qi, Si = torch.cholesky_inverse(LQ), torch.cholesky_inverse(LS)
+        # whitened algebra (gpflow's operation order): B = I + L^-1 Phi L^-T / noise is always well
+        # conditioned, S^-1 = L^-T B^-1 L^-1, Q^-1 = L^-T L^-1, log|S| - log|Q| = log|B|
+        L = torch.linalg.cholesky(Q)
+        Linv = torch.linalg.solve_triangular(L, eye, upper=False)
+        Phiw = Linv @ Phi @ Linv.T
+        B = eye + Phiw / noise
+        LB = torch.linalg.cholesky(0.5 * (B + B.T))
+        Binv = torch.cholesky_inverse(LB)
+        Qi = Linv.T @ Linv
+        Si = Linv.T @ Binv @ Linv
         Sib = Si @ b
         QiPhi = Qi @ Phi
-        logdet = 2.0 * float(torch.log(torch.diagonal(LS)).sum() - torch.log(torch.diagonal(LQ)).sum())
+        logdet = 2.0 * float(torch.log(torch.diagonal(LB)).sum())
         bSb = float((b * Sib).sum())
         trQiPhi = float(torch.diagonal(QiPhi).sum())
         elbo = (-0.5 * n_total * math.log(2.0 * math.pi) - 0.5 * logdet - 0.5 * n_total * math.log(noise)
@@ -246,7 +255,14 @@ def optimise(model, method: str = "BFGS", maxiter: int = 1000, **options):
 
     def fun(u):
         _assign_unconstrained(params, u)
-        return training_loss_and_grad(model)
+        try:
+            return training_loss_and_grad(model)
+        except (RuntimeError, _cabi.OakNativeError) as exc:
+            # a line-search trial point whose Kuu / K + noise I is not numerically positive definite:
+            # report a huge loss so that the step is shortened (gpflow's Scipy wrapper would abort here)
+            if "positive" not in str(exc) and "Cholesky" not in str(exc):
+                raise
+            return 1e25, np.zeros_like(u)
 
     res = minimize(fun, u0, jac=True, method=method, options=dict(maxiter=maxiter, **options))
     _assign_unconstrained(params, res.x)

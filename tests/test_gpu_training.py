@@ -137,3 +137,30 @@ def test_training_loss_gradient_and_bfgs_improve_the_bound():
     res = optimise(model, method="BFGS", maxiter=15)
     assert model.training_loss() < loss0 - 1.0
     assert np.isfinite(res.fun)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_oak_model_fit_with_optimisation_end_to_end(sparse):
+    """oak_model.fit(optimise=True) (model_utils.py:194-427 flow without the TFP normalising flow):
+    BFGS training on y = x0^2 + 2 x1 + x0 x1 (the reference's Sobol toy, test_sobol_oak_kernel.py:41-75):
+    the fit must explain the data and attribute it to {x0}, {x1}, {x0, x1} and not to x2."""
+    from oak_b200.model_utils import oak_model
+
+    rng = np.random.default_rng(3)
+    N = 300
+    X = rng.standard_normal((N, 3))
+    y = (X[:, 0] ** 2 + 2 * X[:, 1] + X[:, 0] * X[:, 1] + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
+    oak = oak_model(max_interaction_depth=2, use_normalising_flow=False, sparse=sparse, num_inducing=60)
+    oak.fit(X, y, optimise=False, initialise_inducing_points=False)
+    loss0 = oak.m.training_loss()
+    rmse0 = float(np.sqrt(np.mean((oak.predict(X) - y[:, 0]) ** 2)))
+    oak.optimise()
+    assert oak.m.training_loss() < loss0 - 10.0
+    Xt = rng.standard_normal((200, 3))
+    yt = Xt[:, 0] ** 2 + 2 * Xt[:, 1] + Xt[:, 0] * Xt[:, 1]
+    rmse = float(np.sqrt(np.mean((oak.predict(Xt) - yt) ** 2)))
+    assert rmse < 0.5 * max(rmse0, 0.5) and rmse < 0.6
+    sob = oak.get_sobol()
+    # components: [0], [1], [2], [0,1], [0,2], [1,2]
+    assert sob[0] > 0.1 and sob[1] > 0.3 and sob[3] > 0.03
+    assert sob[2] < 0.02 and sob[4] < 0.02 and sob[5] < 0.02
