@@ -43,6 +43,8 @@ struct BwParams {
   const double* tables;
   const double* exptab;
   const BwDim* bwdims;
+  const unsigned long long* mm_row;  // [2 D] min / max keys of the prepared coordinates (see oak_prepare.cu)
+  const unsigned long long* mm_col;
   const double* W;
   double* partial;  // [grid][D + P + 1]
   int64_t n_row_pad, n_col_pad, ldw;
@@ -50,6 +52,14 @@ struct BwParams {
   int64_t tiles_n, num_tiles;
   int D, Dc;
 };
+
+// s^2 exp(-z) of one entry: FAST = clamp-free body (s^2 == 1 and bounded distances, proven per launch
+// from the min/max keys exactly as in the forward kernel), else the general clamped body
+template <bool FAST>
+__device__ __forceinline__ double entry_exp(double d, double ax, const unsigned char* tab_bytes, unsigned lane_bits) {
+  if constexpr (FAST) return exp_neg_sq_fast(d, tab_bytes, lane_bits);
+  return exp_neg_scaled(fma(d, d, ax), tab_bytes, lane_bits);
+}
 
 template <int P, int RM, int RN>
 __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const BwParams prm) {
@@ -78,7 +88,17 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
   const unsigned lane_bits = (unsigned)(tx & (kExpRepl - 1)) * 8u;
   const int num_chunks = (D + kDimChunk - 1) / kDimChunk;
   double* myG = sG + warp * nout;
+  __shared__ int sSlow;
+  if (tid == 0) sSlow = 0;
   __syncthreads();
+  for (int d = tid; d < Dc; d += kThreads) {
+    const double rmin = order_key_decode(prm.mm_row[d]), rmax = order_key_decode(prm.mm_row[D + d]);
+    const double cmin = order_key_decode(prm.mm_col[d]), cmax = order_key_decode(prm.mm_col[D + d]);
+    const double span = fmax(rmax - cmin, cmax - rmin);
+    if (!(prm.dim_aux[d] == 0.0 && span <= kFastSpan)) atomicOr(&sSlow, 1);
+  }
+  __syncthreads();
+  const bool fast = sSlow == 0;
 
   auto issue_stage = [&](int64_t row0, int64_t col0, int ch, int buf) {
     const int d0 = ch * kDimChunk;
@@ -129,22 +149,31 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
         for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
         const bool cont = d0 + dl < Dc;
         const double ax = aux[dl];
-        const double* tbl = cont ? nullptr : prm.tables + (int)__double_as_longlong(ax);
+        auto fold = [&](int r, int c, double k) {
 #pragma unroll
-        for (int r = 0; r < RM; ++r)
+          for (int p = P - 1; p >= 1; --p) E[r][c][p] = fma(k, E[r][c][p - 1], E[r][c][p]);
+          E[r][c][0] += k;
+        };
+        if (cont && fast) {
 #pragma unroll
-          for (int c = 0; c < RN; ++c) {
-            double k;
-            if (cont) {
-              const double d = rv[r].x - cv[c].x;
-              k = fma(-rv[r].y, cv[c].y, exp_neg_scaled(fma(d, d, ax), tab_bytes, lane_bits));
-            } else {
-              k = __ldg(tbl + __double2hiint(rv[r].x) + __double2loint(cv[c].x));
-            }
+          for (int r = 0; r < RM; ++r)
 #pragma unroll
-            for (int p = P - 1; p >= 1; --p) E[r][c][p] = fma(k, E[r][c][p - 1], E[r][c][p]);
-            E[r][c][0] += k;
-          }
+            for (int c = 0; c < RN; ++c)
+              fold(r, c, fma(-rv[r].y, cv[c].y, entry_exp<true>(rv[r].x - cv[c].x, ax, tab_bytes, lane_bits)));
+        } else if (cont) {
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c)
+              fold(r, c, fma(-rv[r].y, cv[c].y, entry_exp<false>(rv[r].x - cv[c].x, ax, tab_bytes, lane_bits)));
+        } else {
+          const double* tbl = prm.tables + (int)__double_as_longlong(ax);
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c)
+              fold(r, c, __ldg(tbl + __double2hiint(rv[r].x) + __double2loint(cv[c].x)));
+        }
       }
       buf ^= 1;
     }
@@ -206,26 +235,37 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
         }
         const double ax = aux[dl];
         double acc = 0.0;
+        auto entry = [&](int r, int c, double d, double ex) {
+          const double cc = rv[r].y * cv[c].y;
+          const double k = ex - cc;
+          // removal recurrence: g_m = e_m - k g_{m-1}; dK/dk = sum_n sigma2_n g_{n-1}
+          double g = 1.0;
+          double dKdk = prm.sigma2[1];
 #pragma unroll
-        for (int r = 0; r < RM; ++r)
-#pragma unroll
-          for (int c = 0; c < RN; ++c) {
-            const double d = rv[r].x - cv[c].x;
-            const double d2 = d * d;
-            const double ex = exp_neg_scaled(d2 + ax, tab_bytes, lane_bits);
-            const double cc = rv[r].y * cv[c].y;
-            const double k = ex - cc;
-            // removal recurrence: g_m = e_m - k g_{m-1}; dK/dk = sum_n sigma2_n g_{n-1}
-            double g = 1.0;
-            double dKdk = prm.sigma2[1];
-#pragma unroll
-            for (int m = 1; m < P; ++m) {
-              g = fma(-k, g, E[r][c][m - 1]);
-              dKdk = fma(prm.sigma2[m + 1], g, dKdk);
-            }
-            const double dkdl = fma(ex * d2, bd.c2, -cc * (ur[r] + uc[c]));
-            acc = fma(wv[r][c] * dKdk, dkdl, acc);
+          for (int m = 1; m < P; ++m) {
+            g = fma(-k, g, E[r][c][m - 1]);
+            dKdk = fma(prm.sigma2[m + 1], g, dKdk);
           }
+          const double dkdl = fma(ex * (d * d), bd.c2, -cc * (ur[r] + uc[c]));
+          acc = fma(wv[r][c] * dKdk, dkdl, acc);
+        };
+        if (fast) {
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c) {
+              const double d = rv[r].x - cv[c].x;
+              entry(r, c, d, entry_exp<true>(d, ax, tab_bytes, lane_bits));
+            }
+        } else {
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c) {
+              const double d = rv[r].x - cv[c].x;
+              entry(r, c, d, entry_exp<false>(d, ax, tab_bytes, lane_bits));
+            }
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) myG[d0 + dl] += acc;
@@ -429,6 +469,8 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   prm.tables = spec->d_tables;
   prm.exptab = spec->d_exptab;
   prm.bwdims = d_bw;
+  prm.mm_row = points_minmax(spec, prm.pts_row, prm.n_row_pad);
+  prm.mm_col = points_minmax(spec, prm.pts_col, prm.n_col_pad);
   prm.W = d_W;
   prm.ldw = ldw;
   prm.partial = d_partial;
@@ -441,9 +483,9 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, spec->device);
   int grid = 0, rc = 0;
   switch (depth) {
-    case 1: rc = launch_backward<1, 2, 4>(prm, sms, stream, &grid); break;
-    case 2: rc = launch_backward<2, 2, 4>(prm, sms, stream, &grid); break;
-    case 3: rc = launch_backward<3, 2, 4>(prm, sms, stream, &grid); break;
+    case 1: rc = launch_backward<1, 4, 4>(prm, sms, stream, &grid); break;
+    case 2: rc = launch_backward<2, 4, 4>(prm, sms, stream, &grid); break;
+    case 3: rc = launch_backward<3, 4, 4>(prm, sms, stream, &grid); break;
     case 4: rc = launch_backward<4, 2, 4>(prm, sms, stream, &grid); break;
     case 5: rc = launch_backward<5, 2, 2>(prm, sms, stream, &grid); break;
     case 6: rc = launch_backward<6, 2, 2>(prm, sms, stream, &grid); break;
