@@ -445,6 +445,51 @@ def main():
         except Exception as exc:  # the headline must not depend on the widening row
             elbo["training_step"] = {"error": repr(exc)}
 
+    # ---- the other BASELINE.json configurations (A, D, E): one timed evaluation each, N=1 only --------
+    others = None
+    if world == 1 and not args.no_elbo:
+        try:
+            from oak_b200.models import GPR
+            from oak_b200.utils import compute_sobol_oak
+            from oak_b200.workloads import config_A, config_D, config_E
+
+            def timed(fn, reps=3):
+                fn()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    r = fn()
+                torch.cuda.synchronize()
+                return (time.perf_counter() - t0) / reps * 1e3, r
+
+            others = {}
+            ca = config_A()
+            ga = GPR((ca["X"], ca["y"]), kernel=build_kernel(ca))
+            ga.likelihood.variance.assign(ca["noise"])
+            ms, lml = timed(ga.log_marginal_likelihood)
+            others["A_gpr_lml_n1030_d8_depth8"] = {"ms": ms, "lml": lml}
+            ms, _ = timed(lambda: compute_sobol_oak(ga, 1.0, 0.0), reps=1)
+            others["A_sobol_255_components"] = {"ms": ms}
+            cd = config_D()
+            kd_ = build_kernel(cd)
+            sd = kd_._make_spec()
+            pxd = _device.Points(sd, _device.to_device(cd["X"]))
+            nd_ = cd["X"].shape[0]
+            outd = torch.empty((nd_, nd_), dtype=torch.float64, device="cuda")
+            ms, _ = timed(lambda: _device.gram(sd, pxd, out=outd))
+            others["D_gram_mixed_n50000_d12_depth2"] = {
+                "ms": ms, "unique_entries_per_s": nd_ * (nd_ + 1) / 2 / (ms * 1e-3),
+                "roofline_frac_135_slots": nd_ * (nd_ + 1) / 2 * 135 / (ms * 1e-3) / peak_slots}
+            sd.close()
+            del outd
+            ce = config_E()
+            me = SGPR((ce["X"], ce["y"]), kernel=build_kernel(ce), inducing_variable=ce["Z"], chunk=65536)
+            me.likelihood.variance.assign(ce["noise"])
+            ms, _ = timed(lambda: compute_sobol_oak(me, 1.0, 0.0), reps=1)
+            others["E_sobol_d50_n200000_m512_1275_components"] = {"ms": ms}
+        except Exception as exc:
+            others = {"error": repr(exc)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -467,7 +512,8 @@ def main():
                 "esp": "newton_girard" if args.algo == 0 else "direct_recurrence",
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "extra": {"sgpr_elbo": elbo, "fp64_peak_slots_per_s": peak_slots},
+            "cpu_baseline": cpu,
+            "extra": {"sgpr_elbo": elbo, "other_configs": others, "fp64_peak_slots_per_s": peak_slots},
         }
         print(json.dumps(line))
     spec.close()

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(syrk::kThreads, 2) syrk_lower_dmma_kernel(cons
     const int k0 = (int)((int64_t)s * prm.k_steps / prm.slices);
     const int k1 = (int)((int64_t)(s + 1) * prm.k_steps / prm.slices);
     const int steps = k1 - k0;
+    const bool skip_mma = (bi == bj) && wm == 0 && wn == 1;
 
     // stage loader: 128 rows x kChunks chunks of 16 bytes; rows >= m are zero-filled
     auto load_stage = [&](int step, int buf) {
@@ -115,6 +116,9 @@ __global__ void __launch_bounds__(syrk::kThreads, 2) syrk_lower_dmma_kernel(cons
       }
       const double* As = smem + (step % kStages) * kStageDoubles + (wm * 32 + g) * kRowStride + q * 4;
       const double* Bs = smem + (step % kStages) * kStageDoubles + (kTile + wn * 32 + g) * kRowStride + q * 4;
+      // the upper-right 32 x 32 quadrant of a diagonal tile lies strictly above the diagonal: its
+      // warp only takes part in the staging, and leaves its DMMA slots to the co-resident CTAs
+      if (skip_mma) continue;
       // this lane's k values: groups of four consecutive ones, 16 apart (kk -> (kk/4)*16 + 4q + kk%4)
 #pragma unroll
       for (int h = 0; h < kKT / 16; ++h) {
