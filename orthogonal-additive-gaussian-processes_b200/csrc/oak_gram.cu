@@ -566,20 +566,14 @@ static int launch_algo(const GramParams& prm, int algo, int sms, cudaStream_t st
 //      latency-bound epilogue (Newton-Girard + stores) of one overlaps the FP64 loop of the other
 //   3: 256 threads (16x16), 2x4 micro-tile, 32x64 tile, 2 CTAs / SM
 //   4: 256 threads (32x8), 4x2 micro-tile, 32x64 tile, 2 CTAs / SM
-static int gram_variant() {
-  static int v = -1;
-  if (v < 0) v = env_int("OAK_GRAM_VARIANT", 0);
-  return v;
-}
-
 template <int P>
 static int launch_small_depth(const GramParams& prm, int algo, int sms, cudaStream_t stream) {
-  switch (gram_variant()) {
-    case 0: return launch_algo<P, 16, 16, 4, 4, 1>(prm, algo, sms, stream);
-    case 1: return launch_algo<P, 32, 16, 4, 2, 1>(prm, algo, sms, stream);
-    case 2: return launch_algo<P, 16, 8, 4, 4, 2>(prm, algo, sms, stream);
-    default: return launch_algo<P, 16, 16, 4, 4, 1>(prm, algo, sms, stream);
-  }
+#ifdef OAK_GRAM_EXPERIMENTS  // the losing geometries of profiles/r01_ab_gram_variants_*.txt; not built by default
+  static const int variant = env_int("OAK_GRAM_VARIANT", 0);
+  if (variant == 1) return launch_algo<P, 32, 16, 4, 2, 1>(prm, algo, sms, stream);
+  if (variant == 2) return launch_algo<P, 16, 8, 4, 4, 2>(prm, algo, sms, stream);
+#endif
+  return launch_algo<P, 16, 16, 4, 4, 1>(prm, algo, sms, stream);
 }
 
 int tile_rows_for_depth(int depth) { return depth <= 8 ? 64 : 32; }
