@@ -211,18 +211,25 @@ int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
  * For a cotangent W = d objective / d K (rows [row_begin,row_end) of points x all of points2,
  * pitch ldw; d_points2 == NULL => the same point set):
  *   d_grad[i]             += sum W * dK/d lengthscale_i   (i = sub-kernel in the caller's order;
- *                            RBF sub-kernels with a Gaussian measure or none -- entries of other
- *                            sub-kernels are left untouched)
+ *                            RBF sub-kernels with a Gaussian or empirical measure, or none --
+ *                            entries of other sub-kernels are left untouched)
  *   d_grad[num_dims + n]  += sum W * e_n = dK/d sigma2_n  (n = 0..max_interaction_depth)
- * max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points). */
+ * max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points).
+ * Empirical-measure dims need the per-point derivative block d c^/dl of both point sets, written
+ * by oak_prepare_backward_f64 from the prepared points (oak_backward_points_bytes bytes each);
+ * pass NULL when the kernel has none. */
+size_t oak_backward_points_bytes(const oak_spec* spec, int64_t n);
+int oak_prepare_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, void* d_dpoints,
+                             void* stream);
 size_t oak_gram_backward_work_bytes(const oak_spec* spec, int64_t n);
-int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
-                          int64_t row_end, const void* d_points2, int64_t n2, const double* d_W,
-                          int64_t ldw, double* d_grad, void* d_work, void* stream);
+int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints, int64_t n,
+                          int64_t row_begin, int64_t row_end, const void* d_points2,
+                          const void* d_dpoints2, int64_t n2, const double* d_W, int64_t ldw,
+                          double* d_grad, void* d_work, void* stream);
 /* Same for wscale * sum_i w_i K_diag(x_i) (d_w == NULL => all ones). */
-int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, int64_t n,
-                               const double* d_w, double wscale, double* d_grad, void* d_work,
-                               void* stream);
+int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints,
+                               int64_t n, const double* d_w, double wscale, double* d_grad,
+                               void* d_work, void* stream);
 
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Dependent-chain DFMA microbenchmark: writes achieved FP64 issue slots / second to

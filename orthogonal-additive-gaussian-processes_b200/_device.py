@@ -61,6 +61,22 @@ def _p(t) -> C.c_void_p:
 class Points:
     """Prepared-point block of ``n`` points for one spec (see csrc/oak_prepare.cu)."""
 
+    _dbuf = None
+
+    def backward_block(self):
+        """Per-point d c^/dl block for the backward tiles (empirical-measure dims), built on first use."""
+        if not any(d.type == _cabi.DIM_RBF and d.measure == _cabi.MEASURE_EMPIRICAL for d in self.spec._keep):
+            return None  # closed forms only: the library takes NULL
+        if self._dbuf is None:
+            torch = _torch()
+            lib = _cabi.load()
+            nbytes = int(lib.oak_backward_points_bytes(self.spec.handle, self.n))
+            self._dbuf = torch.zeros(max(nbytes // 8, 1), dtype=torch.float64, device=self.buf.device)
+            if self.n > 0:
+                check(lib.oak_prepare_backward_f64(self.spec.handle, _p(self.buf), self.n, _p(self._dbuf),
+                                                   C.c_void_p(stream_ptr())), "oak_prepare_backward_f64")
+        return self._dbuf
+
     def __init__(self, spec: Spec, Xd):
         torch = _torch()
         self.n = int(Xd.shape[0])
@@ -216,9 +232,10 @@ def gram_backward(spec: Spec, px: Points, W, px2: Optional[Points] = None, row_b
         work = torch.empty(max(int(lib.oak_gram_backward_work_bytes(spec.handle, max(n, n2))) // 8, 1),
                            dtype=torch.float64, device=px.buf.device)
         check(
-            lib.oak_gram_backward_f64(spec.handle, _p(px.buf), n, row_begin, row_end,
-                                      _p(None if px2 is None else px2.buf), n2, _p(W), int(W.stride(0)), _p(grad),
-                                      _p(work), C.c_void_p(stream_ptr())),
+            lib.oak_gram_backward_f64(spec.handle, _p(px.buf), _p(px.backward_block()), n, row_begin, row_end,
+                                      _p(None if px2 is None else px2.buf),
+                                      _p(None if px2 is None else px2.backward_block()), n2, _p(W),
+                                      int(W.stride(0)), _p(grad), _p(work), C.c_void_p(stream_ptr())),
             "oak_gram_backward_f64",
         )
     return grad
@@ -235,8 +252,8 @@ def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad
         work = torch.empty(max(int(lib.oak_gram_backward_work_bytes(spec.handle, px.n)) // 8, 1),
                            dtype=torch.float64, device=px.buf.device)
         check(
-            lib.oak_gram_diag_backward_f64(spec.handle, _p(px.buf), px.n, _p(w), float(wscale), _p(grad), _p(work),
-                                           C.c_void_p(stream_ptr())),
+            lib.oak_gram_diag_backward_f64(spec.handle, _p(px.buf), _p(px.backward_block()), px.n, _p(w),
+                                           float(wscale), _p(grad), _p(work), C.c_void_p(stream_ptr())),
             "oak_gram_diag_backward_f64",
         )
     return grad

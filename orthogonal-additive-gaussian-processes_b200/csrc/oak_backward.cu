@@ -27,12 +27,15 @@ constexpr int kMaxDims = 512;  // per-warp shared slots for the lengthscale part
 }  // namespace bw
 
 struct BwDim {      // per sub-kernel (kernel order)
-  double kappa;     // d log(prefactor of c^ c^) / dl
+  double half_kappa;  // Gaussian measure: d c^/dl = c^ (kappa/2 + u(x))
   double uc;        // l / (l^2 + delta^2)^2
   double mu;
   double inv_xscale;  // prepared coordinate -> x
   double c2;        // (2 / l) * ln2 / kExpTab : ex * d'^2 * c2 = ex * z * 2 / l
-  double supported; // 1: lengthscale gradient available; 0: not (discrete dim / other measure)
+  double kind;      // 0: no lengthscale gradient (discrete dim / uniform / MOG measure)
+                    // 1: closed form above (Gaussian measure, or no measure: c^ = 0)
+                    // 2: d c^/dl read from the per-point array written by oak_prepare_backward_f64
+                    //    (empirical measure)
 };
 
 struct BwParams {
@@ -43,6 +46,8 @@ struct BwParams {
   const double* tables;
   const double* exptab;
   const BwDim* bwdims;
+  const double* dch_row;  // [D][n_row_pad] d c^/dl per point (kind 2 dims), may be null
+  const double* dch_col;
   const unsigned long long* mm_row;  // [2 D] min / max keys of the prepared coordinates (see oak_prepare.cu)
   const unsigned long long* mm_col;
   const double* W;
@@ -216,22 +221,33 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
 #pragma unroll 1
       for (int dl = 0; dl < nc; ++dl) {
         const BwDim bd = prm.bwdims[d0 + dl];
-        if (bd.supported == 0.0) continue;
+        if (bd.kind == 0.0) continue;
         const double2* rowp = sRow + dl * (TM + TN);
         const double2* colp = rowp + TM;
         double2 rv[RM], cv[RN];
-        double ur[RM], uc[RN];
+        double dr[RM], dc[RN];  // d c^/dl of the row / column points
 #pragma unroll
-        for (int r = 0; r < RM; ++r) {
-          rv[r] = rowp[ty * RM + r];
-          const double xm = fma(rv[r].x, bd.inv_xscale, -bd.mu);
-          ur[r] = fma(xm * xm, bd.uc, bd.kappa);  // kappa + u_i
-        }
+        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
 #pragma unroll
-        for (int c = 0; c < RN; ++c) {
-          cv[c] = colp[tx + kTXD * c];
-          const double xm = fma(cv[c].x, bd.inv_xscale, -bd.mu);
-          uc[c] = xm * xm * bd.uc;
+        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
+        if (bd.kind == 1.0) {
+#pragma unroll
+          for (int r = 0; r < RM; ++r) {
+            const double xm = fma(rv[r].x, bd.inv_xscale, -bd.mu);
+            dr[r] = rv[r].y * fma(xm * xm, bd.uc, bd.half_kappa);
+          }
+#pragma unroll
+          for (int c = 0; c < RN; ++c) {
+            const double xm = fma(cv[c].x, bd.inv_xscale, -bd.mu);
+            dc[c] = cv[c].y * fma(xm * xm, bd.uc, bd.half_kappa);
+          }
+        } else {
+          const double* gr = prm.dch_row + (int64_t)(d0 + dl) * prm.n_row_pad + prm.row_begin + row0 + ty * RM;
+          const double* gc = prm.dch_col + (int64_t)(d0 + dl) * prm.n_col_pad + col0 + tx;
+#pragma unroll
+          for (int r = 0; r < RM; ++r) dr[r] = __ldg(gr + r);
+#pragma unroll
+          for (int c = 0; c < RN; ++c) dc[c] = __ldg(gc + kTXD * c);
         }
         const double ax = aux[dl];
         double acc = 0.0;
@@ -246,7 +262,7 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
             g = fma(-k, g, E[r][c][m - 1]);
             dKdk = fma(prm.sigma2[m + 1], g, dKdk);
           }
-          const double dkdl = fma(ex * (d * d), bd.c2, -cc * (ur[r] + uc[c]));
+          const double dkdl = fma(ex * (d * d), bd.c2, -fma(dr[r], cv[c].y, rv[r].y * dc[c]));
           acc = fma(wv[r][c] * dKdk, dkdl, acc);
         };
         if (fast) {
@@ -305,7 +321,8 @@ struct DiagBwParams {
 
 __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, const DimDev* __restrict__ dims,
                                                             const BwDim* __restrict__ bwdims,
-                                                            const double2* __restrict__ pts, int64_t n,
+                                                            const double2* __restrict__ pts,
+                                                            const double* __restrict__ dch, int64_t n,
                                                             int64_t n_pad, const double* __restrict__ w,
                                                             double wscale, double* __restrict__ partial) {
   extern __shared__ double sh[];  // [8 warps][nout]
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
   }
   for (int k = 0; k < prm.Dc; ++k) {
     const BwDim bd = bwdims[k];
-    if (bd.supported == 0.0) continue;
+    if (bd.kind == 0.0) continue;
     const double2 v = pts[(int64_t)k * n_pad + (live ? i : 0)];
     const double cc = v.y * v.y;
     const double kd = dims[k].s2 - cc;
@@ -344,8 +361,14 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
       g = fma(-kd, g, e[m]);
       dKdk = fma(prm.sigma2[m + 1], g, dKdk);
     }
-    const double xm = fma(v.x, bd.inv_xscale, -bd.mu);
-    double c = wi * dKdk * (-cc * (bd.kappa + 2.0 * xm * xm * bd.uc));
+    double dchat;
+    if (bd.kind == 1.0) {
+      const double xm = fma(v.x, bd.inv_xscale, -bd.mu);
+      dchat = v.y * fma(xm * xm, bd.uc, bd.half_kappa);
+    } else {
+      dchat = dch[(int64_t)k * n_pad + (live ? i : 0)];
+    }
+    double c = wi * dKdk * (-2.0 * v.y * dchat);
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) sh[warp * nout + k] += c;
   }
@@ -355,6 +378,73 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
     for (int wq = 0; wq < 8; ++wq) v += sh[wq * nout + j];
     partial[(int64_t)blockIdx.x * nout + j] = v;
   }
+}
+
+// ---- d c^/dl for empirical-measure dims (ortho_rbf_kernel.py:101-120 differentiated) -------------
+//   c(x) = s^2 sum_q w_q exp(-t_q^2),  t_q = (x - s_q)/(sqrt(2) l):   c'(x) = s^2 sum_q w_q exp(-t_q^2) 2 t_q^2 / l
+//   v    = s^2 sum_pq w_p w_q exp(-t_pq^2):                            v'    = s^2 sum_pq w_p w_q exp(-t_pq^2) 2 t_pq^2 / l
+//   c^ = c / sqrt(v):   d c^/dl = c'/sqrt(v) - c^ v'/(2 v)
+// v' uses the same deterministic two-pass reduction as var_s in oak_spec.cu.
+__global__ void empirical_dvar_partial(const double* __restrict__ loc, const double* __restrict__ w, int m,
+                                       double inv_sqrt2_l, double scale, double* __restrict__ partial) {
+  extern __shared__ double sh[];
+  const int tile = blockDim.x;
+  double* sl = sh;
+  double* sw = sh + tile;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double zi = (i < m) ? loc[i] * inv_sqrt2_l : 0.0;
+  const double wi = (i < m) ? w[i] : 0.0;
+  double acc = 0.0;
+  for (int base = 0; base < m; base += tile) {
+    const int j = base + threadIdx.x;
+    sl[threadIdx.x] = (j < m) ? loc[j] * inv_sqrt2_l : 0.0;
+    sw[threadIdx.x] = (j < m) ? w[j] : 0.0;
+    __syncthreads();
+    const int lim = min(tile, m - base);
+    for (int k = 0; k < lim; ++k) {
+      const double t = zi - sl[k];
+      acc = fma(sw[k] * (t * t), exp(-t * t), acc);
+    }
+    __syncthreads();
+  }
+  acc *= wi * scale;  // scale = s^2 * 2 / l
+  sl[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = tile / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sl[threadIdx.x] += sl[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sl[0];
+}
+
+__global__ void __launch_bounds__(256) empirical_dch_kernel(const double* __restrict__ loc, const double* __restrict__ w,
+                                                            int m, double inv_sqrt2_l, double s2, double two_over_l,
+                                                            const double* __restrict__ inv_sqrt_v_slot,
+                                                            const double* __restrict__ dvar_partial, int nblocks,
+                                                            const double2* __restrict__ pts_k, int64_t n,
+                                                            double* __restrict__ out_k) {
+  __shared__ double sl[256], sw[256];
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const double isv = *inv_sqrt_v_slot;
+  double dv = 0.0;
+  for (int b = 0; b < nblocks; ++b) dv += dvar_partial[b];
+  const double half_dlogv = 0.5 * dv * isv * isv;
+  const double2 p = (i < n) ? pts_k[i] : make_double2(0.0, 0.0);
+  const double a = p.x * (1.0 / kXScale);  // x / (sqrt(2) l)
+  double acc = 0.0;
+  for (int base = 0; base < m; base += 256) {
+    const int j = base + threadIdx.x;
+    sl[threadIdx.x] = (j < m) ? loc[j] * inv_sqrt2_l : 0.0;
+    sw[threadIdx.x] = (j < m) ? w[j] : 0.0;
+    __syncthreads();
+    const int lim = min(256, m - base);
+    for (int q = 0; q < lim; ++q) {
+      const double t = a - sl[q];
+      acc = fma(sw[q] * (t * t), exp(-t * t), acc);
+    }
+    __syncthreads();
+  }
+  if (i < n) out_k[i] = s2 * two_over_l * acc * isv - p.y * half_dlogv;
 }
 
 // ---- host side ------------------------------------------------------------------------------
@@ -370,18 +460,20 @@ static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vect
     b.inv_xscale = 1.0 / dd.xscale;
     b.c2 = (2.0 / l) * kInvXScale2;
     b.mu = 0.0;
-    b.kappa = 0.0;
+    b.half_kappa = 0.0;
     b.uc = 0.0;
-    b.supported = 0.0;
+    b.kind = 0.0;
     if (dd.measure == OAK_MEASURE_NONE) {
-      b.supported = 1.0;  // c^ = 0: only the ex z 2/l term survives
+      b.kind = 1.0;  // c^ = 0: only the ex z 2/l term survives
     } else if (dd.measure == OAK_MEASURE_GAUSSIAN) {
       const double l2d = 0.5 / dd.c2;      // l^2 + delta^2
       const double delta2 = l2d - l * l;
       b.mu = dd.c1;
-      b.kappa = 1.0 / l + l / (l * l + 2.0 * delta2) - 2.0 * l / l2d;
+      b.half_kappa = 0.5 * (1.0 / l + l / (l * l + 2.0 * delta2) - 2.0 * l / l2d);
       b.uc = l / (l2d * l2d);
-      b.supported = 1.0;
+      b.kind = 1.0;
+    } else if (dd.measure == OAK_MEASURE_EMPIRICAL) {
+      b.kind = 2.0;
     }
     out[k] = b;
   }
@@ -438,12 +530,47 @@ static int stage_bwdims(const oak_spec* spec, void* d_work, cudaStream_t stream,
   return 0;
 }
 
+// per-point derivative block: double dch[D][n_pad] (d c^/dl; written for empirical-measure dims only)
+extern "C" size_t oak_backward_points_bytes(const oak_spec* spec, int64_t n) {
+  if (!spec || n < 0) return 0;
+  return (size_t)spec->D * (size_t)padded(n) * sizeof(double);
+}
+
+extern "C" int oak_prepare_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, void* d_dpoints,
+                                        void* stream_) {
+  OAK_REQUIRE(spec && d_points && d_dpoints, "oak_prepare_backward_f64: null argument");
+  if (n <= 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t n_pad = padded(n);
+  for (int k = 0; k < spec->Dc; ++k) {
+    const DimDev& dd = spec->h_dims[k];
+    if (dd.measure != OAK_MEASURE_EMPIRICAL) continue;
+    const int threads = 256;
+    const int blocks = (dd.count + threads - 1) / threads;
+    double* partial = nullptr;
+    OAK_CUDA(cudaMallocAsync(&partial, blocks * sizeof(double), stream));
+    const double two_over_l = 2.0 / dd.lengthscale;
+    empirical_dvar_partial<<<blocks, threads, 2 * threads * sizeof(double), stream>>>(
+        dd.v0, dd.v1, dd.count, dd.inv_sqrt2_l, dd.s2 * two_over_l, partial);
+    OAK_LAUNCHED();
+    empirical_dch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        dd.v0, dd.v1, dd.count, dd.inv_sqrt2_l, dd.s2, two_over_l, spec->d_inv_sqrt_v + k, partial, blocks,
+        (const double2*)d_points + (int64_t)k * n_pad, n, (double*)d_dpoints + (int64_t)k * n_pad);
+    OAK_LAUNCHED();
+    OAK_CUDA(cudaFreeAsync(partial, stream));
+  }
+  return 0;
+}
+
 // grad[0..D) += d/d lengthscale of sub-kernel i (caller's order; unsupported ones untouched),
 // grad[D..D+depth] += d/d sigma2_n, for rows [row_begin,row_end) of points x all points2
-// (points2 == NULL: the same point set), cotangent W (rows x n2, pitch ldw).
-extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
-                                     int64_t row_end, const void* d_points2, int64_t n2, const double* d_W,
-                                     int64_t ldw, double* d_grad, void* d_work, void* stream_) {
+// (points2 == NULL: the same point set), cotangent W (rows x n2, pitch ldw).  d_dpoints /
+// d_dpoints2: the blocks written by oak_prepare_backward_f64 (needed when the kernel has
+// empirical-measure dims; may be NULL otherwise).
+extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints, int64_t n,
+                                     int64_t row_begin, int64_t row_end, const void* d_points2,
+                                     const void* d_dpoints2, int64_t n2, const double* d_W, int64_t ldw,
+                                     double* d_grad, void* d_work, void* stream_) {
   OAK_REQUIRE(spec && d_points && d_grad && d_work, "oak_gram_backward_f64: null argument");
   const bool same = d_points2 == nullptr;
   if (same) n2 = n;
@@ -469,6 +596,12 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   prm.tables = spec->d_tables;
   prm.exptab = spec->d_exptab;
   prm.bwdims = d_bw;
+  prm.dch_row = (const double*)d_dpoints;
+  prm.dch_col = same ? (const double*)d_dpoints : (const double*)d_dpoints2;
+  bool need_dch = false;
+  for (int k = 0; k < spec->Dc; ++k) need_dch |= spec->h_dims[k].measure == OAK_MEASURE_EMPIRICAL;
+  OAK_REQUIRE(!need_dch || (prm.dch_row && prm.dch_col),
+              "oak_gram_backward_f64: empirical-measure dims need the oak_prepare_backward_f64 blocks");
   prm.mm_row = points_minmax(spec, prm.pts_row, prm.n_row_pad);
   prm.mm_col = points_minmax(spec, prm.pts_col, prm.n_col_pad);
   prm.W = d_W;
@@ -500,10 +633,14 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
 }
 
 // grad += d/d theta of  wscale * sum_i w_i K_diag(x_i)   (w == NULL: all ones)
-extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, const double* d_w,
-                                          double wscale, double* d_grad, void* d_work, void* stream_) {
+extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints,
+                                          int64_t n, const double* d_w, double wscale, double* d_grad,
+                                          void* d_work, void* stream_) {
   OAK_REQUIRE(spec && d_points && d_grad && d_work, "oak_gram_diag_backward_f64: null argument");
   if (n <= 0) return 0;
+  for (int k = 0; k < spec->Dc; ++k)
+    OAK_REQUIRE(spec->h_dims[k].measure != OAK_MEASURE_EMPIRICAL || d_dpoints,
+                "oak_gram_diag_backward_f64: empirical-measure dims need the oak_prepare_backward_f64 block");
   const int depth = spec->depth < 1 ? 1 : spec->depth;
   cudaStream_t stream = (cudaStream_t)stream_;
   const BwDim* d_bw;
@@ -518,7 +655,8 @@ extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_po
   const int nout = spec->D + depth + 1;
   const int blocks = (int)((n + 255) / 256);
   diag_backward_kernel<<<blocks, 256, 8 * nout * sizeof(double), stream>>>(
-      prm, spec->d_dims, d_bw, (const double2*)d_points, n, padded(n), d_w, wscale, d_partial);
+      prm, spec->d_dims, d_bw, (const double2*)d_points, (const double*)d_dpoints, n, padded(n), d_w, wscale,
+      d_partial);
   OAK_LAUNCHED();
   backward_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(d_partial, blocks, nout, spec->D, d_map, d_grad);
   OAK_LAUNCHED();

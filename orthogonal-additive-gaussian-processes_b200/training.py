@@ -9,7 +9,7 @@ backward tiles of ``liboak_b200.so`` (``oak_gram_backward_f64``): no per-dimensi
 matrix is ever formed.
 
 Supported trainable parameters: RBF lengthscales of sub-kernels with a Gaussian measure (the OAK
-default after the normalising flow) or no measure, the order variances sigma^2_0..P
+default after the normalising flow), an empirical measure or no measure, the order variances sigma^2_0..P
 (``share_var_across_orders=True``) and the likelihood variance.  Any other *trainable* parameter
 raises ``NotImplementedError`` (set it non-trainable to keep it fixed).
 
@@ -96,9 +96,10 @@ def _check_trainables(model, spec_dims):
         raise NotImplementedError("backward tiles need share_var_across_orders=True")
     for p, d in zip(ls, spec_dims):
         if p is not None and p.trainable:
-            if d.type != _cabi.DIM_RBF or d.measure not in (_cabi.MEASURE_NONE, _cabi.MEASURE_GAUSSIAN):
-                raise NotImplementedError("lengthscale gradients exist for Gaussian-measure / unconstrained RBF "
-                                          "sub-kernels only; set the other lengthscales non-trainable")
+            if d.type != _cabi.DIM_RBF or d.measure not in (_cabi.MEASURE_NONE, _cabi.MEASURE_GAUSSIAN,
+                                                            _cabi.MEASURE_EMPIRICAL):
+                raise NotImplementedError("lengthscale gradients exist for RBF sub-kernels with a Gaussian or "
+                                          "empirical measure (or none); set the other lengthscales non-trainable")
 
 
 # ---- objectives with gradients (constrained space) --------------------------------------------

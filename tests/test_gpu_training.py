@@ -164,3 +164,86 @@ def test_oak_model_fit_with_optimisation_end_to_end(sparse):
     # components: [0], [1], [2], [0,1], [0,2], [1,2]
     assert sob[0] > 0.1 and sob[1] > 0.3 and sob[3] > 0.03
     assert sob[2] < 0.02 and sob[4] < 0.02 and sob[5] < 0.02
+
+
+def _mixed_cfg(n, m, seed, depth=2):
+    """Gaussian-measure, empirical-measure and unconstrained RBF dims + a binary and a categorical dim."""
+    rng = np.random.default_rng(seed)
+    X = np.zeros((n, 6))
+    X[:, 0] = rng.standard_normal(n)
+    X[:, 1] = np.round(4 * rng.standard_normal(n)) / 4
+    X[:, 2] = rng.standard_normal(n)
+    X[:, 3] = np.round(3 * rng.standard_normal(n)) / 3
+    X[:, 4] = (rng.random(n) < 0.3).astype(float)
+    X[:, 5] = rng.integers(0, 4, n).astype(float)
+    loc1, cnt1 = np.unique(X[:, 1], return_counts=True)
+    loc3, cnt3 = np.unique(X[:, 3], return_counts=True)
+    ls = rng.uniform(0.6, 2.0, 6)
+    dims = [
+        {"type": "rbf", "lengthscale": float(ls[0]), "variance": 1.0, "measure": ("gaussian", 0.3, 1.7)},
+        {"type": "rbf", "lengthscale": float(ls[1]), "variance": 1.0, "measure": ("empirical", loc1, cnt1 / cnt1.sum())},
+        {"type": "rbf", "lengthscale": float(ls[2]), "variance": 1.0, "measure": None},
+        {"type": "rbf", "lengthscale": float(ls[3]), "variance": 1.0, "measure": ("empirical", loc3, cnt3 / cnt3.sum())},
+        {"type": "binary", "p0": 0.7, "variance": 1.0},
+        {"type": "categorical", "p": np.array([0.2, 0.3, 0.1, 0.4]), "W": rng.uniform(0, 1, (4, 2)),
+         "kappa": rng.uniform(0.5, 1.5, 4), "variance": 1.0},
+    ]
+    var = list(rng.uniform(0.3, 1.2, depth + 1))
+    y = (np.sin(X[:, 0]) + X[:, 1] * X[:, 4] + 0.3 * X[:, 5] + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
+    cfg = dict(X=X, y=y, Z=X[:m].copy(), dims=dims, depth=depth, variances=var, share_var=True, noise=0.05)
+    ref = build_oracle(cfg)
+    # oracle-side description: tables of the discrete dims come from the NumPy oracle (constants)
+    measures = [("gaussian", 0.3, 1.7), ("empirical", loc1, cnt1 / cnt1.sum()), ("none",),
+                ("empirical", loc3, cnt3 / cnt3.sum()), ("table", ref.dims[4].table()), ("table", ref.dims[5].table())]
+    return cfg, ls, np.array(var), measures, ref
+
+
+def test_backward_tiles_mixed_measures_match_autograd():
+    """Lengthscale gradients under the empirical measure (per-point d c^/dl block), a non-standard
+    Gaussian measure and no measure, with discrete dims in the product; order variances as well."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var, measures, ref = _mixed_cfg(230, 60, seed=11)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    # the autograd oracle's forward value is the NumPy oracle's
+    assert max_rel_err(go.oak_K(t(cfg["Z"]), t(cfg["X"]), t(ls), t(var), measures).numpy(), ref.K(cfg["Z"], cfg["X"])) < 1e-12
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    px, pz = _device.Points(spec, _device.to_device(cfg["X"])), _device.Points(spec, _device.to_device(cfg["Z"]))
+    rng = np.random.default_rng(1)
+    W = rng.standard_normal((230, 60))
+    g = _device.gram_backward(spec, px, _device.to_device(W), px2=pz).cpu().numpy()
+    lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
+    (t(W) * go.oak_K(t(cfg["X"]), t(cfg["Z"]), lsT, vT, measures)).sum().backward()
+    assert max_rel_err(g[:4], lsT.grad.numpy()[:4]) < 1e-10
+    assert np.all(g[4:6] == 0.0)  # discrete sub-kernels: no lengthscale, entries untouched
+    assert max_rel_err(g[6:], vT.grad.numpy()) < 1e-10
+    w = rng.standard_normal(230)
+    g = _device.gram_diag_backward(spec, px, wscale=-0.3, w=_device.to_device(w, ndim=1)).cpu().numpy()
+    lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
+    (-0.3 * t(w) * go.oak_K_diag(t(cfg["X"]), lsT, vT, measures)).sum().backward()
+    assert max_rel_err(g[:4], lsT.grad.numpy()[:4]) < 1e-10
+    assert max_rel_err(g[6:], vT.grad.numpy()) < 1e-10
+    spec.close()
+
+
+def test_sgpr_gradient_mixed_model_with_frozen_discrete_parameters():
+    from oak_b200.models import SGPR
+    from oak_b200.training import freeze_unsupported, sgpr_elbo_and_grad
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var, measures, ref = _mixed_cfg(500, 40, seed=12)
+    m = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=128)
+    m.likelihood.variance.assign(cfg["noise"])
+    frozen = freeze_unsupported(m)  # Z, base variances, categorical W / kappa
+    assert len(frozen) >= 3
+    elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
+    v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], cfg["Z"], ls, var, cfg["noise"], measures)
+    assert abs(v - oo.sgpr_elbo(ref, cfg["X"], cfg["y"], cfg["Z"], cfg["noise"])) < 1e-9 * abs(v)
+    assert abs(elbo - v) < 1e-9 * abs(v)
+    assert max_rel_err(g_ls[:4], a_ls[:4]) < 1e-7
+    assert max_rel_err(g_var, a_var) < 1e-7
+    assert abs(g_noise - a_noise) < 1e-7 * abs(a_noise)
