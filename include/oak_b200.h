@@ -214,10 +214,15 @@ int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
  *                            RBF sub-kernels with a Gaussian or empirical measure, or none --
  *                            entries of other sub-kernels are left untouched)
  *   d_grad[num_dims + n]  += sum W * e_n = dK/d sigma2_n  (n = 0..max_interaction_depth)
- * max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points).
+ *   d_grad[num_dims + depth + 1 + t] += cotangent of entry t of the discrete kernels' table blob
+ *                            (binary / categorical B tables and their diagonals; the caller chains
+ *                            it to W, kappa, variance -- oak_spec_table_layout gives the offsets)
+ * d_grad has oak_backward_grad_count(spec) entries.  max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points).
  * Empirical-measure dims need the per-point derivative block d c^/dl of both point sets, written
  * by oak_prepare_backward_f64 from the prepared points (oak_backward_points_bytes bytes each);
  * pass NULL when the kernel has none. */
+size_t oak_backward_grad_count(const oak_spec* spec);
+int oak_spec_table_layout(const oak_spec* spec, int32_t dim, int32_t* offset, int32_t* count);
 size_t oak_backward_points_bytes(const oak_spec* spec, int64_t n);
 int oak_prepare_backward_f64(const oak_spec* spec, const void* d_points, int64_t n, void* d_dpoints,
                              void* stream);

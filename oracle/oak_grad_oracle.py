@@ -52,7 +52,7 @@ def _dim_values(X, X2, ls, measures):
         elif m[0] == "none":
             out.append(torch.exp(-0.5 * (X[:, d][:, None] - X2[:, d][None, :]) ** 2 / ls[d] ** 2))
         elif m[0] == "table":
-            B = torch.as_tensor(m[1], dtype=X.dtype)
+            B = m[1] if isinstance(m[1], torch.Tensor) else torch.as_tensor(m[1], dtype=X.dtype)
             out.append(B[X[:, d].long()][:, X2[:, d].long()])
         else:
             raise ValueError(m[0])

@@ -76,6 +76,8 @@ SIGNATURES = {
     "oak_gram_host_work_bytes": (_sz, [_vp, _i64, _i64, _i64, _i64]),
     "oak_gram_host_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
     "oak_gram_backward_work_bytes": (_sz, [_vp, _i64]),
+    "oak_backward_grad_count": (_sz, [_vp]),
+    "oak_spec_table_layout": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "oak_backward_points_bytes": (_sz, [_vp, _i64]),
     "oak_prepare_backward_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "oak_gram_backward_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _vp, _vp]),

@@ -224,9 +224,11 @@ def gram_backward(spec: Spec, px: Points, W, px2: Optional[Points] = None, row_b
     n = px.n
     n2 = n if px2 is None else px2.n
     row_end = n if row_end is None else row_end
-    nout = spec.num_dims + max(spec.depth, 1) + 1
+    nout = int(lib.oak_backward_grad_count(spec.handle))
     if grad is None:
         grad = torch.zeros(nout, dtype=torch.float64, device=px.buf.device)
+    if grad.numel() != nout or not grad.is_contiguous():
+        raise ValueError(f"gradient buffer must hold oak_backward_grad_count = {nout} contiguous doubles")
     if row_end > row_begin and n2 > 0:
         assert W.shape == (row_end - row_begin, n2) and W.stride(1) == 1
         work = torch.empty(max(int(lib.oak_gram_backward_work_bytes(spec.handle, max(n, n2))) // 8, 1),
@@ -241,13 +243,22 @@ def gram_backward(spec: Spec, px: Points, W, px2: Optional[Points] = None, row_b
     return grad
 
 
+def table_layout(spec: Spec, dim: int):
+    """(offset, C) of sub-kernel ``dim``'s table inside the table-blob part of the gradient vector."""
+    off, cnt = C.c_int32(0), C.c_int32(0)
+    check(_cabi.load().oak_spec_table_layout(spec.handle, int(dim), C.byref(off), C.byref(cnt)), "oak_spec_table_layout")
+    return int(off.value), int(cnt.value)
+
+
 def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad=None):
     """grad += d/d theta of wscale * sum_i w_i K_diag(x_i)."""
     torch = _torch()
     lib = _cabi.load()
-    nout = spec.num_dims + max(spec.depth, 1) + 1
+    nout = int(lib.oak_backward_grad_count(spec.handle))
     if grad is None:
         grad = torch.zeros(nout, dtype=torch.float64, device=px.buf.device)
+    if grad.numel() != nout or not grad.is_contiguous():
+        raise ValueError(f"gradient buffer must hold oak_backward_grad_count = {nout} contiguous doubles")
     if px.n > 0:
         work = torch.empty(max(int(lib.oak_gram_backward_work_bytes(spec.handle, px.n)) // 8, 1),
                            dtype=torch.float64, device=px.buf.device)

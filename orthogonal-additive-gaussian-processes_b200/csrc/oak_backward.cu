@@ -51,11 +51,11 @@ struct BwParams {
   const unsigned long long* mm_row;  // [2 D] min / max keys of the prepared coordinates (see oak_prepare.cu)
   const unsigned long long* mm_col;
   const double* W;
-  double* partial;  // [grid][D + P + 1]
+  double* partial;  // [grid][D + P + 1 + tables_len]
   int64_t n_row_pad, n_col_pad, ldw;
   int64_t row_begin, row_end, n2;
   int64_t tiles_n, num_tiles;
-  int D, Dc;
+  int D, Dc, tables_len;  // gradient layout: [D lengthscales | P + 1 order variances | tables_len table entries]
 };
 
 // s^2 exp(-z) of one entry: FAST = clamp-free body (s^2 == 1 and bounded distances, proven per launch
@@ -76,13 +76,13 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
   double* sTab = reinterpret_cast<double*>(smem_raw);
   double2* sStage = reinterpret_cast<double2*>(sTab + kTabDoubles);
   double* sAux = reinterpret_cast<double*>(sStage + 2 * kStageDouble2);
-  double* sG = sAux + 2 * kDimChunk;  // [8 warps][D + P + 1]
+  double* sG = sAux + 2 * kDimChunk;  // [8 warps][D + P + 1 + tables_len]
 
   const int tid = threadIdx.x;
   const int tx = tid % kTXD, ty = tid / kTXD;
   const int lane = tid & 31, warp = tid >> 5;
   const int D = prm.D, Dc = prm.Dc;
-  const int nout = D + P + 1;
+  const int nout = D + P + 1 + prm.tables_len;
   for (int i = tid; i < kTabDoubles; i += kThreads) {
     const int j = i / kExpRepl;
     const double v = prm.exptab[j];
@@ -286,6 +286,36 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) myG[d0 + dl] += acc;
       }
+      // discrete dims: cotangent of the table blob (the host chains it to W / kappa / variance)
+      const int nd2 = min(kDimChunk, D - d0);
+#pragma unroll 1
+      for (int dl = nc; dl < nd2; ++dl) {
+        const double2* rowp = sRow + dl * (TM + TN);
+        const double2* colp = rowp + TM;
+        const int toff = (int)__double_as_longlong(aux[dl]);
+        const double* tbl = prm.tables + toff;
+        double* gt = myG + D + P + 1 + toff;
+        int ro[RM], co[RN];
+#pragma unroll
+        for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty * RM + r].x);
+#pragma unroll
+        for (int c = 0; c < RN; ++c) co[c] = __double2loint(colp[tx + kTXD * c].x);
+#pragma unroll
+        for (int r = 0; r < RM; ++r)
+#pragma unroll
+          for (int c = 0; c < RN; ++c) {
+            if (wv[r][c] == 0.0) continue;  // out-of-range entries carry zero cotangent
+            const double k = __ldg(tbl + ro[r] + co[c]);
+            double g = 1.0;
+            double dKdk = prm.sigma2[1];
+#pragma unroll
+            for (int m = 1; m < P; ++m) {
+              g = fma(-k, g, E[r][c][m - 1]);
+              dKdk = fma(prm.sigma2[m + 1], g, dKdk);
+            }
+            atomicAdd(gt + ro[r] + co[c], wv[r][c] * dKdk);  // per-warp slots: intra-warp order only
+          }
+      }
       buf ^= 1;
     }
     __syncthreads();  // stage buffers are re-issued by the next tile
@@ -316,7 +346,7 @@ __global__ void backward_reduce_kernel(const double* __restrict__ partial, int g
 // K_diag backward: one thread per point; grad += sum_i w_i dK_diag(x_i)/d theta
 struct DiagBwParams {
   double sigma2[OAK_MAX_DEPTH + 1];
-  int D, Dc, depth;
+  int D, Dc, depth, tables_len;
 };
 
 __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, const DimDev* __restrict__ dims,
@@ -327,7 +357,7 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
                                                             double wscale, double* __restrict__ partial) {
   extern __shared__ double sh[];  // [8 warps][nout]
   const int P = prm.depth;
-  const int nout = prm.D + P + 1;
+  const int nout = prm.D + P + 1 + prm.tables_len;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 8 * nout; i += 256) sh[i] = 0.0;
   __syncthreads();
@@ -371,6 +401,19 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
     double c = wi * dKdk * (-2.0 * v.y * dchat);
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) sh[warp * nout + k] += c;
+  }
+  // discrete dims: K_diag reads tables[table_off + C*C + idx]
+  for (int k = prm.Dc; k < prm.D; ++k) {
+    if (!live || wi == 0.0) continue;
+    const DimDev dd = dims[k];
+    const double2 v = pts[(int64_t)k * n_pad + i];
+    double g = 1.0, dKdk = prm.sigma2[1];
+    for (int m = 1; m < P; ++m) {
+      g = fma(-v.y, g, e[m]);
+      dKdk = fma(prm.sigma2[m + 1], g, dKdk);
+    }
+    atomicAdd(sh + warp * nout + prm.D + P + 1 + dd.table_off + dd.count * dd.count + __double2loint(v.x),
+              wi * dKdk);
   }
   __syncthreads();
   for (int j = tid; j < nout; j += 256) {
@@ -488,7 +531,7 @@ static int launch_backward(BwParams prm, int grid_max, cudaStream_t stream, int*
   prm.tiles_n = (prm.n2 + TN - 1) / TN;
   prm.num_tiles = ((rows + TM - 1) / TM) * prm.tiles_n;
   const size_t smem = sizeof(double) * kExpTab * kExpRepl + 2 * sizeof(double2) * kDimChunk * (TM + TN) +
-                      2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (prm.D + P + 1);
+                      2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (prm.D + P + 1 + prm.tables_len);
   auto kern = gram_backward_kernel<P, RM, RN>;
   OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(prm.num_tiles < grid_max ? prm.num_tiles : grid_max);
@@ -505,7 +548,7 @@ using namespace oak;
 // workspace: per-dimension constants + dimension map + per-CTA partials
 extern "C" size_t oak_gram_backward_work_bytes(const oak_spec* spec, int64_t n) {
   if (!spec || n < 0) return 0;
-  const size_t nout = (size_t)spec->D + spec->depth + 2;
+  const size_t nout = (size_t)spec->D + spec->depth + 2 + spec->tables_len;
   const size_t blocks = (size_t)((n + 255) / 256);
   const size_t ctas = blocks > 1024 ? blocks : 1024;
   return 256 + (size_t)spec->D * (sizeof(BwDim) + sizeof(int)) + 64 + ctas * nout * sizeof(double);
@@ -527,6 +570,29 @@ static int stage_bwdims(const oak_spec* spec, void* d_work, cudaStream_t stream,
   *d_bw = dbw;
   *d_map = dmap;
   *d_partial = (double*)w;
+  return 0;
+}
+
+// Layout of the gradient vector: [num_dims lengthscales (caller's order) | depth + 1 order
+// variances | cotangent of the discrete-kernel table blob].
+extern "C" size_t oak_backward_grad_count(const oak_spec* spec) {
+  if (!spec) return 0;
+  return (size_t)spec->D + (size_t)(spec->depth < 1 ? 1 : spec->depth) + 1 + (size_t)spec->tables_len;
+}
+
+// Where sub-kernel `dim` (caller's order) keeps its table inside that blob: C x C entries B[a, b]
+// (row-major) followed by the C diagonal entries read by K_diag.  count = 0 for RBF sub-kernels.
+extern "C" int oak_spec_table_layout(const oak_spec* spec, int32_t dim, int32_t* offset, int32_t* count) {
+  OAK_REQUIRE(spec && offset && count, "oak_spec_table_layout: null argument");
+  OAK_REQUIRE(dim >= 0 && dim < spec->D, "oak_spec_table_layout: dim out of range");
+  const DimDev& dd = spec->h_dims[spec->pos_of_orig[dim]];
+  if (dd.type == OAK_DIM_RBF) {
+    *offset = 0;
+    *count = 0;
+  } else {
+    *offset = dd.table_off;
+    *count = dd.count;
+  }
   return 0;
 }
 
@@ -612,6 +678,7 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   prm.n2 = n2;
   prm.D = spec->D;
   prm.Dc = spec->Dc;
+  prm.tables_len = spec->tables_len;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, spec->device);
   int grid = 0, rc = 0;
@@ -626,7 +693,7 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
     default: rc = launch_backward<8, 2, 2>(prm, sms, stream, &grid); break;
   }
   if (rc) return rc;
-  const int nout = spec->D + depth + 1;
+  const int nout = spec->D + depth + 1 + spec->tables_len;
   backward_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(d_partial, grid, nout, spec->D, d_map, d_grad);
   OAK_LAUNCHED();
   return 0;
@@ -652,7 +719,8 @@ extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_po
   prm.D = spec->D;
   prm.Dc = spec->Dc;
   prm.depth = depth;
-  const int nout = spec->D + depth + 1;
+  prm.tables_len = spec->tables_len;
+  const int nout = spec->D + depth + 1 + spec->tables_len;
   const int blocks = (int)((n + 255) / 256);
   diag_backward_kernel<<<blocks, 256, 8 * nout * sizeof(double), stream>>>(
       prm, spec->d_dims, d_bw, (const double2*)d_points, (const double*)d_dpoints, n, padded(n), d_w, wscale,

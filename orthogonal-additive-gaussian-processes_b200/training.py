@@ -10,7 +10,8 @@ matrix is ever formed.
 
 Supported trainable parameters: RBF lengthscales of sub-kernels with a Gaussian measure (the OAK
 default after the normalising flow), an empirical measure or no measure, the order variances sigma^2_0..P
-(``share_var_across_orders=True``) and the likelihood variance.  Any other *trainable* parameter
+(``share_var_across_orders=True``), the likelihood variance, and W / kappa of the categorical sub-kernels
+(through the cotangent of their B tables).  Any other *trainable* parameter
 raises ``NotImplementedError`` (set it non-trainable to keep it fixed).
 
 SGPR (gpflow 2.2.1 ``SGPR.elbo``), with Phi = Kuf Kuf^T, b = Kuf y, s = sum K_diag,
@@ -71,11 +72,29 @@ def _supported_parameters(model) -> Tuple[List[Parameter], List[Parameter], Para
     return ls, list(kern.variances), model.likelihood.variance
 
 
+def _discrete_parameters(model) -> List[Parameter]:
+    """W, kappa and (when it is a Parameter) variance of the categorical sub-kernels, variance of the
+    binary ones: differentiated through the cotangent of their B tables."""
+    out = []
+    for k in model.kernel.kernels:
+        if hasattr(k, "kappa") or hasattr(k, "p0"):
+            for name in ("W", "kappa", "variance"):
+                p = getattr(k, name, None)
+                if isinstance(p, Parameter):
+                    out.append(p)
+    return out
+
+
+def _all_supported_ids(model):
+    ls, var, noise = _supported_parameters(model)
+    return ({id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
+            | {id(p) for p in _discrete_parameters(model)})
+
+
 def freeze_unsupported(model) -> List[Parameter]:
     """Sets ``trainable=False`` on every parameter the backward tiles cannot differentiate
     (inducing points, base-kernel variances, categorical W / kappa, ...); returns them."""
-    ls, var, noise = _supported_parameters(model)
-    ok = {id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
+    ok = _all_supported_ids(model)
     frozen = []
     for p in collect_parameters(model):
         if p.trainable and id(p) not in ok:
@@ -86,12 +105,12 @@ def freeze_unsupported(model) -> List[Parameter]:
 
 def _check_trainables(model, spec_dims):
     ls, var, noise = _supported_parameters(model)
-    ok = {id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
+    ok = _all_supported_ids(model)
     for p in collect_parameters(model):
         if p.trainable and id(p) not in ok:
             raise NotImplementedError(
-                "gradient of a trainable parameter outside {RBF lengthscales, order variances, likelihood variance} "
-                f"is not implemented ({p!r}); set it non-trainable")
+                "gradient of a trainable parameter outside (RBF lengthscales, order variances, likelihood variance, "
+                f"categorical W / kappa) is not implemented ({p!r}); set it non-trainable (freeze_unsupported)")
     if not getattr(model.kernel, "share_var_across_orders", True):
         raise NotImplementedError("backward tiles need share_var_across_orders=True")
     for p, d in zip(ls, spec_dims):
@@ -157,7 +176,7 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
                    - 0.5 * trQiPhi / noise ** 2 + 0.5 * float((Si * Phi).sum()) / noise ** 2
                    + 0.5 * float((Sib * (Phi @ Sib)).sum()) / noise ** 4)
         # second pass over the local points: W^T = 2 Kuf^T G_phi + y g_b^T, contracted by the backward tiles
-        nout = spec.num_dims + max(spec.depth, 1) + 1
+        nout = int(_cabi.load().oak_backward_grad_count(spec.handle))  # lengthscales | variances | table blob
         grad = torch.zeros(nout, dtype=torch.float64, device=Kuu.device)
         chunk = max(64, (int(model.chunk) + 63) // 64 * 64)
         G2 = (2.0 * G_phi).contiguous()
@@ -172,10 +191,12 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
             parallel.allreduce_sum_(grad)
         _device.gram_backward(spec, pz, G_Q.contiguous(), grad=grad)  # Kuu term (replicated, added once)
         g = grad.cpu().numpy()
+        layout = [_device.table_layout(spec, i) for i in range(spec.num_dims)]
     finally:
         spec.close()
-    D = spec.num_dims
-    return elbo, g[:D].copy(), g[D:].copy(), float(g_noise)
+    D, P1 = spec.num_dims, max(spec.depth, 1) + 1
+    model._table_cotangent = (g[D + P1:].copy(), layout)
+    return elbo, g[:D].copy(), g[D: D + P1].copy(), float(g_noise)
 
 
 def gpr_lml_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
@@ -201,10 +222,53 @@ def gpr_lml_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         W = (0.5 * (alpha @ alpha.T - Kinv)).contiguous()
         g_noise = float(torch.diagonal(W).sum())
         g = _device.gram_backward(spec, px, W).cpu().numpy()
+        layout = [_device.table_layout(spec, i) for i in range(spec.num_dims)]
     finally:
         spec.close()
-    D = spec.num_dims
-    return lml, g[:D].copy(), g[D:].copy(), g_noise
+    D, P1 = spec.num_dims, max(spec.depth, 1) + 1
+    model._table_cotangent = (g[D + P1:].copy(), layout)
+    return lml, g[:D].copy(), g[D: D + P1].copy(), g_noise
+
+
+def discrete_parameter_gradients(model) -> Dict[int, np.ndarray]:
+    """Chains the table-blob cotangent of the last ``*_and_grad`` call to the categorical W / kappa /
+    variance and binary variance Parameters (ortho_categorical_kernel.py:34-53, ortho_binary_kernel.py:29-38):
+    a few C x C operations, differentiated with torch autograd on the host.  {id(Parameter): gradient}."""
+    import torch
+
+    g_tab, layout = model._table_cotangent
+    out: Dict[int, np.ndarray] = {}
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    for i, k in enumerate(model.kernel.kernels):
+        off, C_ = layout[i]
+        if C_ == 0:
+            continue
+        GB = t(g_tab[off: off + C_ * C_].reshape(C_, C_))
+        Gd = t(g_tab[off + C_ * C_: off + C_ * C_ + C_])
+        var_p = getattr(k, "variance", None)
+        var_t = t(scalar_of(var_p) if var_p is not None else 1.0).clone().requires_grad_(True)
+        if hasattr(k, "kappa"):  # categorical
+            W_t = t(value_of(k.W)).clone().requires_grad_(True)
+            kap_t = t(value_of(k.kappa)).reshape(-1).clone().requires_grad_(True)
+            p = t(k._p_vector()).reshape(-1, 1)
+            A = W_t @ W_t.T + torch.diag(kap_t)
+            Ap = A @ p
+            pAp = (p.T @ Ap)[0, 0]
+            B = (A - (Ap @ Ap.T) / pAp) * var_t
+            Bd = ((W_t ** 2).sum(1) + kap_t - Ap[:, 0] ** 2 / pAp) * var_t
+            ((GB * B).sum() + (Gd * Bd).sum()).backward()
+            if isinstance(k.W, Parameter):
+                out[id(k.W)] = W_t.grad.numpy().reshape(k.W.numpy().shape)
+            if isinstance(k.kappa, Parameter):
+                out[id(k.kappa)] = kap_t.grad.numpy().reshape(k.kappa.numpy().shape)
+        else:  # binary
+            p0 = float(k.p0)
+            p1 = 1.0 - p0
+            B1 = t([[p1 * p1, -p0 * p1], [-p0 * p1, p0 * p0]])
+            ((GB * B1 * var_t).sum() + (Gd * torch.diagonal(B1) * var_t).sum()).backward()
+        if isinstance(var_p, Parameter):
+            out[id(var_p)] = np.full(var_p.numpy().shape, float(var_t.grad))
+    return out
 
 
 # ---- training loss on the unconstrained variables (gpflow's trainable_variables) -----------------
@@ -228,6 +292,8 @@ def training_loss_and_grad(model) -> Tuple[float, np.ndarray]:
     for p, g in zip(var, g_var):
         cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
     cgrad[id(noise)] = np.full(noise.numpy().shape, g_noise, dtype=np.float64)
+    if any(p.trainable for p in _discrete_parameters(model)):
+        cgrad.update(discrete_parameter_gradients(model))
     loss = -(val + model.log_prior_density())
     parts = []
     for p in trainable_parameters(model):

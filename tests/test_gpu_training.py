@@ -220,13 +220,14 @@ def test_backward_tiles_mixed_measures_match_autograd():
     (t(W) * go.oak_K(t(cfg["X"]), t(cfg["Z"]), lsT, vT, measures)).sum().backward()
     assert max_rel_err(g[:4], lsT.grad.numpy()[:4]) < 1e-10
     assert np.all(g[4:6] == 0.0)  # discrete sub-kernels: no lengthscale, entries untouched
-    assert max_rel_err(g[6:], vT.grad.numpy()) < 1e-10
+    assert max_rel_err(g[6:9], vT.grad.numpy()) < 1e-10
+    assert g.shape[0] == 6 + 3 + (4 + 2) + (16 + 4) and np.any(g[9:] != 0.0)  # + cotangent of the B tables
     w = rng.standard_normal(230)
     g = _device.gram_diag_backward(spec, px, wscale=-0.3, w=_device.to_device(w, ndim=1)).cpu().numpy()
     lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
     (-0.3 * t(w) * go.oak_K_diag(t(cfg["X"]), lsT, vT, measures)).sum().backward()
     assert max_rel_err(g[:4], lsT.grad.numpy()[:4]) < 1e-10
-    assert max_rel_err(g[6:], vT.grad.numpy()) < 1e-10
+    assert max_rel_err(g[6:9], vT.grad.numpy()) < 1e-10
     spec.close()
 
 
@@ -247,3 +248,37 @@ def test_sgpr_gradient_mixed_model_with_frozen_discrete_parameters():
     assert max_rel_err(g_ls[:4], a_ls[:4]) < 1e-7
     assert max_rel_err(g_var, a_var) < 1e-7
     assert abs(g_noise - a_noise) < 1e-7 * abs(a_noise)
+
+
+def test_categorical_W_kappa_gradients_through_the_table_cotangent():
+    """d ELBO / d (W, kappa) of a categorical sub-kernel: the backward tiles return the cotangent of the
+    B table, training.py chains it (ortho_categorical_kernel.py:34-53); oracle = autograd with B(W, kappa)
+    rebuilt in torch."""
+    import torch
+
+    from oak_b200.models import SGPR
+    from oak_b200.training import discrete_parameter_gradients, freeze_unsupported, sgpr_elbo_and_grad
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var, measures, ref = _mixed_cfg(400, 36, seed=13)
+    kern = build_kernel(cfg)
+    m = SGPR((cfg["X"], cfg["y"]), kernel=kern, inducing_variable=cfg["Z"], chunk=128)
+    m.likelihood.variance.assign(cfg["noise"])
+    freeze_unsupported(m)
+    elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
+    grads = discrete_parameter_gradients(m)
+    cat = kern.kernels[5]
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64))
+    W = t(cfg["dims"][5]["W"]).clone().requires_grad_(True)
+    kap = t(cfg["dims"][5]["kappa"]).clone().requires_grad_(True)
+    p = t(cfg["dims"][5]["p"]).reshape(-1, 1)
+    A = W @ W.T + torch.diag(kap)
+    Ap = A @ p
+    B = A - (Ap @ Ap.T) / (p.T @ Ap)[0, 0]
+    meas = list(measures)
+    meas[5] = ("table", B)
+    val = go.sgpr_elbo(t(cfg["X"]), t(cfg["y"]), t(cfg["Z"]), t(ls), t(var), t(cfg["noise"]), meas)
+    val.backward()
+    assert abs(float(val.detach()) - elbo) < 1e-9 * abs(elbo)
+    assert max_rel_err(grads[id(cat.W)], W.grad.numpy()) < 1e-7
+    assert max_rel_err(grads[id(cat.kappa)].reshape(-1), kap.grad.numpy()) < 1e-7
