@@ -217,7 +217,8 @@ int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
  *   d_grad[num_dims + depth + 1 + t] += cotangent of entry t of the discrete kernels' table blob
  *                            (binary / categorical B tables and their diagonals; the caller chains
  *                            it to W, kappa, variance -- oak_spec_table_layout gives the offsets)
- * d_grad has oak_backward_grad_count(spec) entries.  max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points).
+ *   d_grad[count - num_dims + i] += sum W * dK/d s2_i   (base variance of RBF sub-kernel i)
+ * d_grad has count = oak_backward_grad_count(spec) entries.  max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points).
  * Empirical-measure dims need the per-point derivative block d c^/dl of both point sets, written
  * by oak_prepare_backward_f64 from the prepared points (oak_backward_points_bytes bytes each);
  * pass NULL when the kernel has none. */

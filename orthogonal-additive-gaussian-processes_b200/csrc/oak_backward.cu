@@ -32,6 +32,7 @@ struct BwDim {      // per sub-kernel (kernel order)
   double mu;
   double inv_xscale;  // prepared coordinate -> x
   double c2;        // (2 / l) * ln2 / kExpTab : ex * d'^2 * c2 = ex * z * 2 / l
+  double inv_s2;    // 1 / s^2 (base variance)
   double kind;      // 0: no lengthscale gradient (discrete dim / uniform / MOG measure)
                     // 1: closed form above (Gaussian measure, or no measure: c^ = 0)
                     // 2: d c^/dl read from the per-point array written by oak_prepare_backward_f64
@@ -55,7 +56,8 @@ struct BwParams {
   int64_t n_row_pad, n_col_pad, ldw;
   int64_t row_begin, row_end, n2;
   int64_t tiles_n, num_tiles;
-  int D, Dc, tables_len;  // gradient layout: [D lengthscales | P + 1 order variances | tables_len table entries]
+  int D, Dc, tables_len;  // gradient layout: [D lengthscales | P + 1 order variances | tables_len table
+                          // entries | D base variances s^2 of the RBF sub-kernels]
 };
 
 // s^2 exp(-z) of one entry: FAST = clamp-free body (s^2 == 1 and bounded distances, proven per launch
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
   const int tx = tid % kTXD, ty = tid / kTXD;
   const int lane = tid & 31, warp = tid >> 5;
   const int D = prm.D, Dc = prm.Dc;
-  const int nout = D + P + 1 + prm.tables_len;
+  const int nout = 2 * D + P + 1 + prm.tables_len;
+  const int vbase = D + P + 1 + prm.tables_len;  // first base-variance slot
   for (int i = tid; i < kTabDoubles; i += kThreads) {
     const int j = i / kExpRepl;
     const double v = prm.exptab[j];
@@ -221,7 +224,6 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
 #pragma unroll 1
       for (int dl = 0; dl < nc; ++dl) {
         const BwDim bd = prm.bwdims[d0 + dl];
-        if (bd.kind == 0.0) continue;
         const double2* rowp = sRow + dl * (TM + TN);
         const double2* colp = rowp + TM;
         double2 rv[RM], cv[RN];
@@ -230,7 +232,12 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
         for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
 #pragma unroll
         for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
-        if (bd.kind == 1.0) {
+        if (bd.kind == 0.0) {  // no lengthscale gradient (uniform / MOG measure): base variance only
+#pragma unroll
+          for (int r = 0; r < RM; ++r) dr[r] = 0.0;
+#pragma unroll
+          for (int c = 0; c < RN; ++c) dc[c] = 0.0;
+        } else if (bd.kind == 1.0) {
 #pragma unroll
           for (int r = 0; r < RM; ++r) {
             const double xm = fma(rv[r].x, bd.inv_xscale, -bd.mu);
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
           for (int c = 0; c < RN; ++c) dc[c] = __ldg(gc + kTXD * c);
         }
         const double ax = aux[dl];
-        double acc = 0.0;
+        double acc = 0.0, accv = 0.0;
         auto entry = [&](int r, int c, double d, double ex) {
           const double cc = rv[r].y * cv[c].y;
           const double k = ex - cc;
@@ -263,7 +270,9 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
             dKdk = fma(prm.sigma2[m + 1], g, dKdk);
           }
           const double dkdl = fma(ex * (d * d), bd.c2, -fma(dr[r], cv[c].y, rv[r].y * dc[c]));
-          acc = fma(wv[r][c] * dKdk, dkdl, acc);
+          const double wk = wv[r][c] * dKdk;
+          acc = fma(wk, dkdl, acc);
+          accv = fma(wk, k, accv);  // k~ is homogeneous of degree one in s^2: d k~ / d s^2 = k~ / s^2
         };
         if (fast) {
 #pragma unroll
@@ -283,8 +292,14 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
             }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) myG[d0 + dl] += acc;
+        for (int o = 16; o > 0; o >>= 1) {
+          acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          accv += __shfl_xor_sync(0xffffffffu, accv, o);
+        }
+        if (lane == 0) {
+          if (bd.kind != 0.0) myG[d0 + dl] += acc;
+          myG[vbase + d0 + dl] += accv * bd.inv_s2;
+        }
       }
       // discrete dims: cotangent of the table blob (the host chains it to W / kappa / variance)
       const int nd2 = min(kDimChunk, D - d0);
@@ -339,7 +354,9 @@ __global__ void backward_reduce_kernel(const double* __restrict__ partial, int g
   if (i >= nout) return;
   double v = 0.0;
   for (int b = 0; b < grid; ++b) v += partial[(int64_t)b * nout + i];
-  const int dst = i < D ? orig_of_pos[i] : i;
+  int dst = i;
+  if (i < D) dst = orig_of_pos[i];                                   // lengthscales
+  else if (i >= nout - D) dst = nout - D + orig_of_pos[i - (nout - D)];  // base variances
   grad[dst] += v;
 }
 
@@ -357,7 +374,8 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
                                                             double wscale, double* __restrict__ partial) {
   extern __shared__ double sh[];  // [8 warps][nout]
   const int P = prm.depth;
-  const int nout = prm.D + P + 1 + prm.tables_len;
+  const int nout = 2 * prm.D + P + 1 + prm.tables_len;
+  const int vbase = prm.D + P + 1 + prm.tables_len;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 8 * nout; i += 256) sh[i] = 0.0;
   __syncthreads();
@@ -382,7 +400,6 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
   }
   for (int k = 0; k < prm.Dc; ++k) {
     const BwDim bd = bwdims[k];
-    if (bd.kind == 0.0) continue;
     const double2 v = pts[(int64_t)k * n_pad + (live ? i : 0)];
     const double cc = v.y * v.y;
     const double kd = dims[k].s2 - cc;
@@ -391,16 +408,23 @@ __global__ void __launch_bounds__(256) diag_backward_kernel(DiagBwParams prm, co
       g = fma(-kd, g, e[m]);
       dKdk = fma(prm.sigma2[m + 1], g, dKdk);
     }
-    double dchat;
+    double dchat = 0.0;
     if (bd.kind == 1.0) {
       const double xm = fma(v.x, bd.inv_xscale, -bd.mu);
       dchat = v.y * fma(xm * xm, bd.uc, bd.half_kappa);
-    } else {
+    } else if (bd.kind == 2.0) {
       dchat = dch[(int64_t)k * n_pad + (live ? i : 0)];
     }
     double c = wi * dKdk * (-2.0 * v.y * dchat);
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) sh[warp * nout + k] += c;
+    double cv = wi * dKdk * kd * bd.inv_s2;
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      cv += __shfl_xor_sync(0xffffffffu, cv, o);
+    }
+    if (lane == 0) {
+      if (bd.kind != 0.0) sh[warp * nout + k] += c;
+      sh[warp * nout + vbase + k] += cv;
+    }
   }
   // discrete dims: K_diag reads tables[table_off + C*C + idx]
   for (int k = prm.Dc; k < prm.D; ++k) {
@@ -492,7 +516,7 @@ __global__ void __launch_bounds__(256) empirical_dch_kernel(const double* __rest
 
 // ---- host side ------------------------------------------------------------------------------
 static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vector<int>& orig_of_pos) {
-  out.assign(spec->D, BwDim{0, 0, 0, 0, 0, 0});
+  out.assign(spec->D, BwDim{0, 0, 0, 0, 0, 0, 0});
   orig_of_pos.assign(spec->D, 0);
   for (int k = 0; k < spec->D; ++k) {
     const DimDev& dd = spec->h_dims[k];
@@ -502,6 +526,7 @@ static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vect
     BwDim b;
     b.inv_xscale = 1.0 / dd.xscale;
     b.c2 = (2.0 / l) * kInvXScale2;
+    b.inv_s2 = 1.0 / dd.s2;
     b.mu = 0.0;
     b.half_kappa = 0.0;
     b.uc = 0.0;
@@ -531,7 +556,7 @@ static int launch_backward(BwParams prm, int grid_max, cudaStream_t stream, int*
   prm.tiles_n = (prm.n2 + TN - 1) / TN;
   prm.num_tiles = ((rows + TM - 1) / TM) * prm.tiles_n;
   const size_t smem = sizeof(double) * kExpTab * kExpRepl + 2 * sizeof(double2) * kDimChunk * (TM + TN) +
-                      2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (prm.D + P + 1 + prm.tables_len);
+                      2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (2 * prm.D + P + 1 + prm.tables_len);
   auto kern = gram_backward_kernel<P, RM, RN>;
   OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)(prm.num_tiles < grid_max ? prm.num_tiles : grid_max);
@@ -548,7 +573,7 @@ using namespace oak;
 // workspace: per-dimension constants + dimension map + per-CTA partials
 extern "C" size_t oak_gram_backward_work_bytes(const oak_spec* spec, int64_t n) {
   if (!spec || n < 0) return 0;
-  const size_t nout = (size_t)spec->D + spec->depth + 2 + spec->tables_len;
+  const size_t nout = 2 * (size_t)spec->D + spec->depth + 2 + spec->tables_len;
   const size_t blocks = (size_t)((n + 255) / 256);
   const size_t ctas = blocks > 1024 ? blocks : 1024;
   return 256 + (size_t)spec->D * (sizeof(BwDim) + sizeof(int)) + 64 + ctas * nout * sizeof(double);
@@ -574,10 +599,11 @@ static int stage_bwdims(const oak_spec* spec, void* d_work, cudaStream_t stream,
 }
 
 // Layout of the gradient vector: [num_dims lengthscales (caller's order) | depth + 1 order
-// variances | cotangent of the discrete-kernel table blob].
+// variances | cotangent of the discrete-kernel table blob | num_dims base variances s^2 of the RBF
+// sub-kernels (caller's order; zero for discrete sub-kernels)].
 extern "C" size_t oak_backward_grad_count(const oak_spec* spec) {
   if (!spec) return 0;
-  return (size_t)spec->D + (size_t)(spec->depth < 1 ? 1 : spec->depth) + 1 + (size_t)spec->tables_len;
+  return 2 * (size_t)spec->D + (size_t)(spec->depth < 1 ? 1 : spec->depth) + 1 + (size_t)spec->tables_len;
 }
 
 // Where sub-kernel `dim` (caller's order) keeps its table inside that blob: C x C entries B[a, b]
@@ -693,7 +719,7 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
     default: rc = launch_backward<8, 2, 2>(prm, sms, stream, &grid); break;
   }
   if (rc) return rc;
-  const int nout = spec->D + depth + 1 + spec->tables_len;
+  const int nout = 2 * spec->D + depth + 1 + spec->tables_len;
   backward_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(d_partial, grid, nout, spec->D, d_map, d_grad);
   OAK_LAUNCHED();
   return 0;
@@ -720,7 +746,7 @@ extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_po
   prm.Dc = spec->Dc;
   prm.depth = depth;
   prm.tables_len = spec->tables_len;
-  const int nout = spec->D + depth + 1 + spec->tables_len;
+  const int nout = 2 * spec->D + depth + 1 + spec->tables_len;
   const int blocks = (int)((n + 255) / 256);
   diag_backward_kernel<<<blocks, 256, 8 * nout * sizeof(double), stream>>>(
       prm, spec->d_dims, d_bw, (const double2*)d_points, (const double*)d_dpoints, n, padded(n), d_w, wscale,

@@ -10,8 +10,9 @@ matrix is ever formed.
 
 Supported trainable parameters: RBF lengthscales of sub-kernels with a Gaussian measure (the OAK
 default after the normalising flow), an empirical measure or no measure, the order variances sigma^2_0..P
-(``share_var_across_orders=True``), the likelihood variance, and W / kappa of the categorical sub-kernels
-(through the cotangent of their B tables).  Any other *trainable* parameter
+(``share_var_across_orders=True``), the likelihood variance, the base variances s^2 of the RBF sub-kernels
+where the reference keeps them trainable, and W / kappa of the categorical sub-kernels (through the
+cotangent of their B tables).  Any other *trainable* parameter
 raises ``NotImplementedError`` (set it non-trainable to keep it fixed).
 
 SGPR (gpflow 2.2.1 ``SGPR.elbo``), with Phi = Kuf Kuf^T, b = Kuf y, s = sum K_diag,
@@ -72,6 +73,16 @@ def _supported_parameters(model) -> Tuple[List[Parameter], List[Parameter], Para
     return ls, list(kern.variances), model.likelihood.variance
 
 
+def _base_variance_parameter(sub):
+    """s^2 of an RBF sub-kernel when it is a Parameter (the reference fixes it to 1 only for the Gaussian
+    measure with shared order variances, oak_kernel.py:163-166)."""
+    if hasattr(sub, "kappa") or hasattr(sub, "p0"):
+        return None
+    base = getattr(sub, "base_kernel", sub)
+    p = getattr(base, "variance", None)
+    return p if isinstance(p, Parameter) else None
+
+
 def _discrete_parameters(model) -> List[Parameter]:
     """W, kappa and (when it is a Parameter) variance of the categorical sub-kernels, variance of the
     binary ones: differentiated through the cotangent of their B tables."""
@@ -87,8 +98,9 @@ def _discrete_parameters(model) -> List[Parameter]:
 
 def _all_supported_ids(model):
     ls, var, noise = _supported_parameters(model)
+    bvar = [_base_variance_parameter(k) for k in model.kernel.kernels]
     return ({id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
-            | {id(p) for p in _discrete_parameters(model)})
+            | {id(p) for p in _discrete_parameters(model)} | {id(p) for p in bvar if p is not None})
 
 
 def freeze_unsupported(model) -> List[Parameter]:
@@ -195,7 +207,8 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
     finally:
         spec.close()
     D, P1 = spec.num_dims, max(spec.depth, 1) + 1
-    model._table_cotangent = (g[D + P1:].copy(), layout)
+    model._table_cotangent = (g[D + P1: len(g) - D].copy(), layout)
+    model._base_variance_grad = g[len(g) - D:].copy()
     return elbo, g[:D].copy(), g[D: D + P1].copy(), float(g_noise)
 
 
@@ -226,7 +239,8 @@ def gpr_lml_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
     finally:
         spec.close()
     D, P1 = spec.num_dims, max(spec.depth, 1) + 1
-    model._table_cotangent = (g[D + P1:].copy(), layout)
+    model._table_cotangent = (g[D + P1: len(g) - D].copy(), layout)
+    model._base_variance_grad = g[len(g) - D:].copy()
     return lml, g[:D].copy(), g[D: D + P1].copy(), g_noise
 
 
@@ -292,6 +306,10 @@ def training_loss_and_grad(model) -> Tuple[float, np.ndarray]:
     for p, g in zip(var, g_var):
         cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
     cgrad[id(noise)] = np.full(noise.numpy().shape, g_noise, dtype=np.float64)
+    for k, g in zip(model.kernel.kernels, model._base_variance_grad):
+        p = _base_variance_parameter(k)
+        if p is not None:
+            cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
     if any(p.trainable for p in _discrete_parameters(model)):
         cgrad.update(discrete_parameter_gradients(model))
     loss = -(val + model.log_prior_density())

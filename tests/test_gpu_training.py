@@ -43,14 +43,14 @@ def test_backward_tiles_match_autograd(D, P):
         lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
         (t(W) * go.oak_K(t(A), t(B), lsT, vT)).sum().backward()
         assert max_rel_err(g[:D], lsT.grad.numpy()) < 1e-10
-        assert max_rel_err(g[D:], vT.grad.numpy()) < 1e-10
+        assert max_rel_err(g[D:D + P + 1], vT.grad.numpy()) < 1e-10
     # K_diag
     w = rng.standard_normal(210)
     g = _device.gram_diag_backward(spec, px, wscale=0.7, w=_device.to_device(w, ndim=1)).cpu().numpy()
     lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
     (0.7 * t(w) * go.oak_K_diag(t(cfg["X"]), lsT, vT)).sum().backward()
     assert max_rel_err(g[:D], lsT.grad.numpy()) < 1e-10
-    assert max_rel_err(g[D:], vT.grad.numpy()) < 1e-10
+    assert max_rel_err(g[D:D + P + 1], vT.grad.numpy()) < 1e-10
     spec.close()
 
 
@@ -221,7 +221,7 @@ def test_backward_tiles_mixed_measures_match_autograd():
     assert max_rel_err(g[:4], lsT.grad.numpy()[:4]) < 1e-10
     assert np.all(g[4:6] == 0.0)  # discrete sub-kernels: no lengthscale, entries untouched
     assert max_rel_err(g[6:9], vT.grad.numpy()) < 1e-10
-    assert g.shape[0] == 6 + 3 + (4 + 2) + (16 + 4) and np.any(g[9:] != 0.0)  # + cotangent of the B tables
+    assert g.shape[0] == 6 + 3 + (4 + 2) + (16 + 4) + 6 and np.any(g[9:35] != 0.0)  # + B tables, base variances
     w = rng.standard_normal(230)
     g = _device.gram_diag_backward(spec, px, wscale=-0.3, w=_device.to_device(w, ndim=1)).cpu().numpy()
     lsT, vT = t(ls).clone().requires_grad_(True), t(var).clone().requires_grad_(True)
@@ -239,8 +239,8 @@ def test_sgpr_gradient_mixed_model_with_frozen_discrete_parameters():
     cfg, ls, var, measures, ref = _mixed_cfg(500, 40, seed=12)
     m = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=128)
     m.likelihood.variance.assign(cfg["noise"])
-    frozen = freeze_unsupported(m)  # Z, base variances, categorical W / kappa
-    assert len(frozen) >= 3
+    frozen = freeze_unsupported(m)  # only the inducing points are left without a gradient
+    assert len(frozen) == 1
     elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
     v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], cfg["Z"], ls, var, cfg["noise"], measures)
     assert abs(v - oo.sgpr_elbo(ref, cfg["X"], cfg["y"], cfg["Z"], cfg["noise"])) < 1e-9 * abs(v)
@@ -282,3 +282,67 @@ def test_categorical_W_kappa_gradients_through_the_table_cotangent():
     assert abs(float(val.detach()) - elbo) < 1e-9 * abs(elbo)
     assert max_rel_err(grads[id(cat.W)], W.grad.numpy()) < 1e-7
     assert max_rel_err(grads[id(cat.kappa)].reshape(-1), kap.grad.numpy()) < 1e-7
+
+
+def test_mixed_input_oak_model_trains_all_its_parameters():
+    """Binary + categorical + empirical-measure + continuous inputs (the oak_model flow of
+    model_utils.py:194-427 without the TFP flow): every trainable parameter of the reference model --
+    bounded lengthscales, order variances, noise, categorical W and kappa -- receives a gradient and
+    BFGS improves the bound."""
+    from oak_b200.model_utils import oak_model
+    from oak_b200.training import optimise, trainable_parameters, training_loss_and_grad
+
+    rng = np.random.default_rng(44)
+    N = 400
+    x_cat = rng.choice([0, 1, 2, 3], size=N, p=[0.2, 0.2, 0.3, 0.3])
+    x_bin = rng.choice([0, 1], size=N, p=[0.8, 0.2])
+    X = np.vstack([x_bin, x_cat, rng.standard_normal(N), np.round(3 * rng.standard_normal(N)) / 3]).T.astype(float)
+    y = (np.sin(X[:, 2]) + X[:, 0] + 0.4 * (X[:, 1] == 2) + 0.3 * X[:, 3] + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
+    oak = oak_model(binary_feature=[0], categorical_feature=[1], max_interaction_depth=2,
+                    use_normalising_flow=False, empirical_measure=[3], sparse=True, num_inducing=50)
+    oak.fit(X, y, optimise=False, initialise_inducing_points=False)
+    params = trainable_parameters(oak.m)
+    # 2 lengthscales, the base variance of the empirical-measure dim (oak_kernel.py:163-166 fixes it only
+    # under the Gaussian measure), 3 order variances, noise, W and kappa
+    assert len(params) == 2 + 1 + 3 + 1 + 2
+    loss0, g = training_loss_and_grad(oak.m)
+    assert g.shape[0] == 2 + 1 + 3 + 1 + 4 * 2 + 4 and np.all(np.isfinite(g)) and np.all(g != 0.0)
+    optimise(oak.m, method="BFGS", maxiter=25)
+    assert oak.m.training_loss() < loss0 - 10.0
+    pred = oak.predict(X)
+    assert float(np.sqrt(np.mean((pred - y[:, 0]) ** 2))) < 0.3
+    sob = oak.get_sobol()
+    assert abs(sob.sum() - 1) < 1e-12 and np.all(sob >= 0)
+
+
+def test_base_variance_gradient_matches_autograd():
+    """d/d s^2 of RBF sub-kernels (k~ is homogeneous of degree one in s^2) for Gaussian, empirical and
+    no measure; oracle: autograd with k~ scaled by s^2."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var, measures, ref = _mixed_cfg(200, 50, seed=14)
+    s2 = np.array([1.3, 0.7, 2.1, 1.0])
+    for d in range(4):
+        cfg["dims"][d]["variance"] = float(s2[d])
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    px, pz = _device.Points(spec, _device.to_device(cfg["X"])), _device.Points(spec, _device.to_device(cfg["Z"]))
+    W = np.random.default_rng(2).standard_normal((200, 50))
+    g = _device.gram_backward(spec, px, _device.to_device(W), px2=pz).cpu().numpy()
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    s2T = t(s2).clone().requires_grad_(True)
+    ks = go._dim_values(t(cfg["X"]), t(cfg["Z"]), t(ls), measures)
+    ks = [ks[d] * s2T[d] for d in range(4)] + ks[4:]
+    (t(W) * go._esp_sum(ks, t(var))).sum().backward()
+    assert max_rel_err(g[-6:-2], s2T.grad.numpy()) < 1e-10
+    assert np.all(g[-2:] == 0.0)
+    gd = _device.gram_diag_backward(spec, px, wscale=1.0).cpu().numpy()
+    s2T = t(s2).clone().requires_grad_(True)
+    kd = [torch.diagonal(v) for v in go._dim_values(t(cfg["X"]), t(cfg["X"]), t(ls), measures)]
+    kd = [kd[d] * s2T[d] for d in range(4)] + kd[4:]
+    go._esp_sum(kd, t(var)).sum().backward()
+    assert max_rel_err(gd[-6:-2], s2T.grad.numpy()) < 1e-10
+    spec.close()
