@@ -151,6 +151,14 @@ int oak_component_predict_f64(const oak_spec* spec, const int32_t* d_subsets,
                               int64_t n, const void* d_points_cond, int64_t m,
                               const double* d_alpha, double* d_out, void* stream);
 
+/* out[i - row_begin] = sum_j K(x_i, x2_j) alpha_j for rows [row_begin, row_end) of `points`
+ * (row_begin a multiple of 64): the mean of gpflow's predict_f, Kus^T alpha
+ * (oak/model_utils.py:429-443), fused so that the N* x M matrix is never formed.
+ * max_interaction_depth <= 8. */
+int oak_gram_matvec_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                        int64_t row_end, const void* d_points2, int64_t n2, const double* d_alpha,
+                        double* d_out, void* stream);
+
 /* Host-buffer convenience (the reference-facing call: NumPy in, NumPy out).  Copies X (and
  * X2) to the device, runs prepare + gram in row blocks and streams K back, overlapping the
  * D2H copies with compute.  h_X2 == NULL => X2 = X. d_work must hold oak_gram_host_work_bytes. */

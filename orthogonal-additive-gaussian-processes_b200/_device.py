@@ -138,6 +138,22 @@ def gram_lower(spec: Spec, px: Points, row_begin: int, row_end: int, out=None):
     return out
 
 
+def gram_matvec(spec: Spec, px: Points, px2: Points, alpha, out=None):
+    """out[i] = sum_j K(px_i, px2_j) alpha_j, fused (no N x N2 matrix)."""
+    torch = _torch()
+    if out is None:
+        out = torch.empty((px.n,), dtype=torch.float64, device=px.buf.device)
+    a = alpha.reshape(-1).contiguous()
+    assert a.numel() == px2.n
+    if px.n > 0:
+        check(
+            _cabi.load().oak_gram_matvec_f64(spec.handle, _p(px.buf), px.n, 0, px.n, _p(px2.buf), px2.n, _p(a),
+                                             _p(out), C.c_void_p(stream_ptr())),
+            "oak_gram_matvec_f64",
+        )
+    return out
+
+
 def gram_diag(spec: Spec, px: Points):
     torch = _torch()
     out = torch.empty((px.n,), dtype=torch.float64, device=px.buf.device)

@@ -587,6 +587,146 @@ static int sm_count(int device) {
   return n;
 }
 
+// ---- fused K(X*, Z) alpha (prediction mean) ------------------------------------------------------
+// out[i] = sum_j K(x_i, z_j) alpha_j without the N* x M matrix (gpflow predict_f mean = Kus^T alpha,
+// oak/model_utils.py:429-443).  One CTA owns a block of TM rows and walks all column
+// tiles; every thread keeps the running sums of its RM rows, the 16 threads of a row group are
+// folded by shuffles at the end: deterministic, no atomics.
+template <int P, int ALGO>
+__global__ void __launch_bounds__(256, 1) gram_matvec_kernel(const GramParams prm, const double* __restrict__ alpha,
+                                                             double* __restrict__ out) {
+  constexpr int TXD = 16, TYD = 16, RM = 2, RN = 4;
+  using L = SmemLayout<TXD, TYD, RM, RN>;
+  constexpr int TM = L::TM, TN = L::TN;
+  constexpr int kThreads = TXD * TYD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sTab = reinterpret_cast<double*>(smem_raw);
+  double2* sStage = reinterpret_cast<double2*>(sTab + L::kTabDoubles);
+  double* sAux = reinterpret_cast<double*>(sStage + 2 * L::kStageDouble2);
+  const int tid = threadIdx.x;
+  const int tx = tid % TXD, ty = tid / TXD;
+  for (int i = tid; i < L::kTabDoubles; i += kThreads) {
+    const int j = i / kExpRepl;
+    const double v = prm.exptab[j];
+    sTab[i] = __hiloint2double(__double2hiint(v) - (j << (20 - kExpBits)), __double2loint(v));
+  }
+  const unsigned char* tab_bytes = smem_raw;
+  const unsigned lane_bits = (unsigned)(tx & (kExpRepl - 1)) * 8u;
+  const int D = prm.D, Dc = prm.Dc;
+  const int num_chunks = (D + kDimChunk - 1) / kDimChunk;
+  const int64_t nrows = prm.row_end - prm.row_begin;
+  __syncthreads();
+
+  auto issue_stage = [&](int64_t row0, int64_t col0, int ch, int buf) {
+    const int d0 = ch * kDimChunk;
+    const int nd = min(kDimChunk, D - d0);
+    double2* dst = sStage + buf * L::kStageDouble2;
+    for (int o = tid; o < TM + TN; o += kThreads) {
+      const double2* src = (o < TM) ? prm.pts_row + (int64_t)d0 * prm.n_row_pad + prm.row_begin + row0 + o
+                                    : prm.pts_col + (int64_t)d0 * prm.n_col_pad + col0 + (o - TM);
+      const int64_t stride = (o < TM) ? prm.n_row_pad : prm.n_col_pad;
+      for (int dl = 0; dl < nd; ++dl) cp_async16(dst + dl * (TM + TN) + o, src + dl * stride);
+    }
+    if (tid < nd) cp_async8(sAux + buf * kDimChunk + tid, prm.dim_aux + d0 + tid);
+    cp_async_commit();
+  };
+
+  const int64_t row_blocks = (nrows + TM - 1) / TM;
+  for (int64_t rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+    const int64_t row0 = rb * TM;
+    double rs[RM];
+#pragma unroll
+    for (int r = 0; r < RM; ++r) rs[r] = 0.0;
+    for (int64_t cb = 0; cb < prm.tiles_n; ++cb) {
+      const int64_t col0 = cb * TN;
+      double acc[RM][RN][P];
+#pragma unroll
+      for (int r = 0; r < RM; ++r)
+#pragma unroll
+        for (int c = 0; c < RN; ++c)
+#pragma unroll
+          for (int p = 0; p < P; ++p) acc[r][c][p] = 0.0;
+      int buf = 0;
+      __syncthreads();  // the previous tile's last buffer is free
+      issue_stage(row0, col0, 0, 0);
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
+        const double2* sRow = sStage + buf * L::kStageDouble2;
+        const double* aux = sAux + buf * kDimChunk;
+        const int d0 = ch * kDimChunk;
+        const int nd = min(kDimChunk, D - d0);
+#pragma unroll 1
+        for (int dl = 0; dl < nd; ++dl) {
+          const double2* rowp = sRow + dl * (TM + TN);
+          const double2* colp = rowp + TM;
+          double2 rv[RM], cv[RN];
+#pragma unroll
+          for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
+#pragma unroll
+          for (int c = 0; c < RN; ++c) cv[c] = colp[tx + TXD * c];
+          if (d0 + dl < Dc) {
+            const double ax = aux[dl];
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+              for (int c = 0; c < RN; ++c) {
+                const double d = rv[r].x - cv[c].x;
+                const double e = exp_neg_scaled(fma(d, d, ax), tab_bytes, lane_bits);
+                accumulate<P, ALGO>(acc[r][c], fma(-rv[r].y, cv[c].y, e));
+              }
+          } else {
+            const double* tbl = prm.tables + (int)__double_as_longlong(aux[dl]);
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+              for (int c = 0; c < RN; ++c)
+                accumulate<P, ALGO>(acc[r][c], __ldg(tbl + __double2hiint(rv[r].x) + __double2loint(cv[c].x)));
+          }
+        }
+        buf ^= 1;
+      }
+#pragma unroll
+      for (int c = 0; c < RN; ++c) {
+        const int64_t col = col0 + tx + TXD * c;
+        const double a = col < prm.n2 ? __ldg(alpha + col) : 0.0;
+#pragma unroll
+        for (int r = 0; r < RM; ++r) rs[r] = fma(finish<P, ALGO>(acc[r][c], prm.sigma2), a, rs[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RM; ++r) {
+      double v = rs[r];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int64_t row = row0 + ty * RM + r;
+      if (tx == 0 && row < nrows) out[row] = v;
+    }
+  }
+  cp_async_wait_all();
+}
+
+template <int P>
+static int launch_matvec(GramParams prm, int algo, int sms, const double* alpha, double* out, cudaStream_t stream) {
+  using L = SmemLayout<16, 16, 2, 4>;
+  prm.tiles_n = (prm.n2 + L::TN - 1) / L::TN;
+  const int64_t row_blocks = (prm.row_end - prm.row_begin + L::TM - 1) / L::TM;
+  const size_t smem = L::bytes(false);
+  const int grid = (int)(row_blocks < sms ? row_blocks : sms);
+  if (algo == OAK_ESP_DIRECT) {
+    auto kern = gram_matvec_kernel<P, OAK_ESP_DIRECT>;
+    OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, stream>>>(prm, alpha, out);
+  } else {
+    auto kern = gram_matvec_kernel<P, OAK_ESP_NEWTON_GIRARD>;
+    OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 256, smem, stream>>>(prm, alpha, out);
+  }
+  OAK_LAUNCHED();
+  return 0;
+}
+
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream) {
@@ -660,6 +800,55 @@ extern "C" int oak_gram_f64(const oak_spec* spec, const void* d_points, int64_t 
   return gram_launch(spec, (const double2*)d_points, padded(n), row_begin, row_end,
                      same ? (const double2*)d_points : (const double2*)d_points2, padded(n2), 0, n2,
                      symmetric ? 1 : 0, d_K, ldk, (cudaStream_t)stream_);
+}
+
+// out[i - row_begin] = sum_j K(x_i, x2_j) alpha_j for rows [row_begin, row_end): the mean of
+// predict_f (Kus^T alpha) and any other Gram-matrix/vector product, without forming the matrix.
+extern "C" int oak_gram_matvec_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                                   int64_t row_end, const void* d_points2, int64_t n2, const double* d_alpha,
+                                   double* d_out, void* stream_) {
+  OAK_REQUIRE(spec && d_points && d_points2 && d_alpha && d_out, "oak_gram_matvec_f64: null argument");
+  OAK_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n, "oak_gram_matvec_f64: bad row range");
+  OAK_REQUIRE(row_begin % 64 == 0, "oak_gram_matvec_f64: row_begin must be a multiple of 64");
+  if (row_end == row_begin) return 0;
+  OAK_REQUIRE(n2 >= 1, "oak_gram_matvec_f64: empty conditioning set");
+  const int depth = spec->depth < 1 ? 1 : spec->depth;
+  OAK_REQUIRE(depth <= 8, "oak_gram_matvec_f64: max_interaction_depth > 8 is not supported");
+  GramParams prm;
+  for (int p = 0; p <= OAK_MAX_DEPTH; ++p) prm.sigma2[p] = spec->sigma2[p];
+  prm.pts_row = (const double2*)d_points;
+  prm.pts_col = (const double2*)d_points2;
+  prm.n_row_pad = padded(n);
+  prm.n_col_pad = padded(n2);
+  prm.dim_aux = spec->d_gram_aux;
+  prm.tables = spec->d_tables;
+  prm.exptab = spec->d_exptab;
+  prm.K = nullptr;
+  prm.ldk = 0;
+  prm.row_begin = row_begin;
+  prm.row_end = row_end;
+  prm.col_begin = 0;
+  prm.n2 = n2;
+  prm.D = spec->D;
+  prm.Dc = spec->Dc;
+  prm.device = spec->device;
+  prm.symmetric = 0;
+  prm.tile_row0 = 0;
+  prm.num_tiles = 0;
+  prm.mm_row = prm.mm_col = nullptr;
+  prm.use_tma = 0;
+  const int sms = sm_count(spec->device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  switch (depth) {
+    case 1: return launch_matvec<1>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    case 2: return launch_matvec<2>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    case 3: return launch_matvec<3>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    case 4: return launch_matvec<4>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    case 5: return launch_matvec<5>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    case 6: return launch_matvec<6>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    case 7: return launch_matvec<7>(prm, spec->algo, sms, d_alpha, d_out, stream);
+    default: return launch_matvec<8>(prm, spec->algo, sms, d_alpha, d_out, stream);
+  }
 }
 
 extern "C" int oak_gram_lower_f64(const oak_spec* spec, const void* d_points, int64_t n,

@@ -273,7 +273,8 @@ class oak_model:
     def predict(self, X, clip=False):
         X = np.asarray(X, dtype=np.float64)
         Xs = self._transform_x(np.clip(X, self.xmin, self.xmax)) if clip else self._transform_x(X)
-        y_pred = self.m.predict_f(Xs)[0]
+        # only the mean of predict_f is used (model_utils.py:441): take the fused mean when there is one
+        y_pred = self.m.predict_mean(Xs) if hasattr(self.m, "predict_mean") else self.m.predict_f(Xs)[0]
         return self.scaler_y.inverse_transform(np.asarray(y_pred))[:, 0]
 
     def get_sobol(self, likelihood_variance=False):

@@ -163,6 +163,21 @@ class SGPR(GPModel):
         """alpha = L^-T LB^-T c, shape (M, 1) (oak/utils.py:195-198)."""
         return self._statistics(True)[1].reshape(-1, 1)
 
+    def predict_mean(self, Xnew):
+        """Mean of ``predict_f`` only (what ``oak_model.predict`` uses, model_utils.py:429-443):
+        Kus^T alpha through the fused Gram-matrix/vector tiles, no (M, N*) intermediate."""
+        host = _device.is_host(Xnew)
+        alpha = self._statistics(True)[1]
+        Xn = self._slice_for_kernel(_device.to_device(Xnew))
+        Zs = self._Z_device()
+        spec = self.kernel._make_spec()
+        try:
+            self.kernel._check_discrete(Xn, spec._keep)
+            mean = _device.gram_matvec(spec, _device.Points(spec, Xn), _device.Points(spec, Zs), alpha)
+        finally:
+            spec.close()
+        return _device.from_device(mean.reshape(-1, 1), host)
+
     def predict_f(self, Xnew, full_cov: bool = False):
         import torch
 

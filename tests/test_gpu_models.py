@@ -249,3 +249,36 @@ def test_oak_model_api_end_to_end():
     assert pred.shape == (N,)
     sob = oak.get_sobol()
     assert len(sob) == 4 + 6 and abs(sob.sum() - 1) < 1e-12 and np.all(sob >= 0)
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 6, 8])
+def test_fused_gram_matvec_matches_matrix_product(depth):
+    """oak_gram_matvec_f64 (prediction mean without the N* x M matrix) == K(X*, Z) @ alpha, and the oracle."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg = mixed_config(n=333, seed=20 + depth, depth=depth)
+    k, ref = build_kernel(cfg), build_oracle(cfg)
+    spec = k._make_spec()
+    Xd, Zd = _device.to_device(cfg["X"]), _device.to_device(cfg["Z"])
+    px, pz = _device.Points(spec, Xd), _device.Points(spec, Zd)
+    alpha = np.random.default_rng(depth).standard_normal(cfg["Z"].shape[0])
+    got = _device.gram_matvec(spec, px, pz, _device.to_device(alpha, ndim=1)).cpu().numpy()
+    full = (_device.gram(spec, px, pz) @ _device.to_device(alpha, ndim=1)).cpu().numpy()
+    want = ref.K(cfg["X"], cfg["Z"]) @ alpha
+    assert max_rel_err(got, full) < 1e-12
+    assert max_rel_err(got, want) < RTOL
+    spec.close()
+
+
+def test_sgpr_predict_mean_matches_predict_f_and_oracle():
+    cfg = mixed_config(n=500, seed=31, depth=2)
+    m, ref = _models(cfg, True), build_oracle(cfg)
+    Xnew = mixed_config(n=170, seed=32, depth=2)["X"]
+    mean = m.predict_mean(Xnew)
+    mean_f, _ = m.predict_f(Xnew)
+    want = oo.sgpr_predict_mean(ref, cfg["X"], cfg["y"], cfg["Z"], cfg["noise"], Xnew)
+    assert max_rel_err(mean, mean_f) < 1e-10
+    assert max_rel_err(mean, want) < 1e-6
