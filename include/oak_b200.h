@@ -219,15 +219,15 @@ int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
  * For a cotangent W = d objective / d K (rows [row_begin,row_end) of points x all of points2,
  * pitch ldw; d_points2 == NULL => the same point set):
  *   d_grad[i]             += sum W * dK/d lengthscale_i   (i = sub-kernel in the caller's order;
- *                            RBF sub-kernels with a Gaussian or empirical measure, or none --
- *                            entries of other sub-kernels are left untouched)
+ *                            RBF sub-kernels under any measure -- entries of discrete
+ *                            sub-kernels are left untouched)
  *   d_grad[num_dims + n]  += sum W * e_n = dK/d sigma2_n  (n = 0..max_interaction_depth)
  *   d_grad[num_dims + depth + 1 + t] += cotangent of entry t of the discrete kernels' table blob
  *                            (binary / categorical B tables and their diagonals; the caller chains
  *                            it to W, kappa, variance -- oak_spec_table_layout gives the offsets)
  *   d_grad[count - num_dims + i] += sum W * dK/d s2_i   (base variance of RBF sub-kernel i)
  * d_grad has count = oak_backward_grad_count(spec) entries.  max_interaction_depth <= 8.  d_work: oak_gram_backward_work_bytes(spec, n_points).
- * Empirical-measure dims need the per-point derivative block d c^/dl of both point sets, written
+ * Empirical / uniform / MOG dims need the per-point derivative block d c^/dl of both point sets, written
  * by oak_prepare_backward_f64 from the prepared points (oak_backward_points_bytes bytes each);
  * pass NULL when the kernel has none. */
 size_t oak_backward_grad_count(const oak_spec* spec);

@@ -34,28 +34,67 @@ def _k_tilde_emp(x, y, l, loc, w):
     return k - cx[:, None] * cy[None, :] / v
 
 
-def _dim_values(X, X2, ls, measures):
+def _k_tilde_general(x, y, l, s2, cx, cy, v):
+    return s2 * torch.exp(-0.5 * (x[:, None] - y[None, :]) ** 2 / l ** 2) - cx[:, None] * cy[None, :] / v
+
+
+def _uniform_parts(x, l, s2, a, b):
+    """cov_X_s / var_s for a uniform measure on [a, b] (ortho_rbf_kernel.py:49-78)."""
+    c = s2 * l * math.sqrt(math.pi / 2) / (b - a) * (torch.erf((b - x) / (math.sqrt(2) * l)) - torch.erf((a - x) / (math.sqrt(2) * l)))
+    y = (b - a) / math.sqrt(2) / l
+    v = 2 / (b - a) ** 2 * s2 * l ** 2 * (math.sqrt(math.pi) * y * torch.erf(y) + torch.exp(-y ** 2) - 1)
+    return c, v
+
+
+def _mog_parts(x, l, s2, means, variances, weights):
+    """cov_X_s / var_s for a mixture of Gaussians (ortho_rbf_kernel.py:124-152)."""
+    S = l ** 2 + variances
+    c = s2 * l * (weights[None, :] * torch.exp(-0.5 * (x[:, None] - means[None, :]) ** 2 / S[None, :]) / torch.sqrt(S)[None, :]).sum(1)
+    T = l ** 2 + variances[:, None] + variances[None, :]
+    v = s2 * l * (weights[:, None] * weights[None, :] * torch.exp(-0.5 * (means[:, None] - means[None, :]) ** 2 / T) / torch.sqrt(T)).sum()
+    return c, v
+
+
+def _dim_values(X, X2, ls, measures, s2=None):
     """Per-dimension constrained kernel matrices.  measures[d]: None -> Gaussian N(0, 1);
-    ("gaussian", mu, var); ("empirical", loc, w); ("none",) -> plain RBF; ("table", B) -> discrete
-    kernel B[x, x'] with a constant table (its parameters are not differentiated)."""
+    ("gaussian", mu, var); ("uniform", a, b); ("empirical", loc, w); ("mog", means, variances, weights);
+    ("none",) -> plain RBF; ("table", B) -> discrete kernel B[x, x'] (B may be a differentiable tensor).
+    s2[d]: base variance of the RBF dims (default 1)."""
     D = X.shape[1]
+    t = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(a, dtype=X.dtype)
     out = []
     for d in range(D):
         m = None if measures is None else measures[d]
-        if m is None:
-            out.append(_k_tilde(X[:, d], X2[:, d], ls[d], 0.0, 1.0))
-        elif m[0] == "gaussian":
-            out.append(_k_tilde(X[:, d], X2[:, d], ls[d], m[1], m[2]))
+        x, y = X[:, d], X2[:, d]
+        if m is not None and m[0] == "table":
+            B = t(m[1])
+            out.append(B[x.long()][:, y.long()])
+            continue
+        l = ls[d]
+        v2 = 1.0 if s2 is None else s2[d]
+        if m is None or m[0] == "gaussian":
+            mu, var = (0.0, 1.0) if m is None else (m[1], m[2])
+            pre = v2 * l / torch.sqrt(l ** 2 + var)
+            cx = pre * torch.exp(-0.5 * (x - mu) ** 2 / (l ** 2 + var))
+            cy = pre * torch.exp(-0.5 * (y - mu) ** 2 / (l ** 2 + var))
+            v = v2 * l / torch.sqrt(l ** 2 + 2 * var)
+        elif m[0] == "uniform":
+            cx, v = _uniform_parts(x, l, v2, m[1], m[2])
+            cy, _ = _uniform_parts(y, l, v2, m[1], m[2])
         elif m[0] == "empirical":
-            out.append(_k_tilde_emp(X[:, d], X2[:, d], ls[d], torch.as_tensor(m[1], dtype=X.dtype).reshape(-1),
-                                    torch.as_tensor(m[2], dtype=X.dtype).reshape(-1)))
+            loc, w = t(m[1]).reshape(-1), t(m[2]).reshape(-1)
+            cx = v2 * (torch.exp(-0.5 * (x[:, None] - loc[None, :]) ** 2 / l ** 2) * w[None, :]).sum(1)
+            cy = v2 * (torch.exp(-0.5 * (y[:, None] - loc[None, :]) ** 2 / l ** 2) * w[None, :]).sum(1)
+            v = v2 * (w[:, None] * torch.exp(-0.5 * (loc[:, None] - loc[None, :]) ** 2 / l ** 2) * w[None, :]).sum()
+        elif m[0] == "mog":
+            cx, v = _mog_parts(x, l, v2, t(m[1]), t(m[2]), t(m[3]))
+            cy, _ = _mog_parts(y, l, v2, t(m[1]), t(m[2]), t(m[3]))
         elif m[0] == "none":
-            out.append(torch.exp(-0.5 * (X[:, d][:, None] - X2[:, d][None, :]) ** 2 / ls[d] ** 2))
-        elif m[0] == "table":
-            B = m[1] if isinstance(m[1], torch.Tensor) else torch.as_tensor(m[1], dtype=X.dtype)
-            out.append(B[X[:, d].long()][:, X2[:, d].long()])
+            out.append(v2 * torch.exp(-0.5 * (x[:, None] - y[None, :]) ** 2 / l ** 2))
+            continue
         else:
             raise ValueError(m[0])
+        out.append(_k_tilde_general(x, y, l, v2, cx, cy, v))
     return out
 
 

@@ -64,8 +64,9 @@ class Points:
     _dbuf = None
 
     def backward_block(self):
-        """Per-point d c^/dl block for the backward tiles (empirical-measure dims), built on first use."""
-        if not any(d.type == _cabi.DIM_RBF and d.measure == _cabi.MEASURE_EMPIRICAL for d in self.spec._keep):
+        """Per-point d c^/dl block for the backward tiles (empirical / uniform / MOG dims), built on first use."""
+        if not any(d.type == _cabi.DIM_RBF and d.measure in (_cabi.MEASURE_EMPIRICAL, _cabi.MEASURE_UNIFORM,
+                                                           _cabi.MEASURE_MOG) for d in self.spec._keep):
             return None  # closed forms only: the library takes NULL
         if self._dbuf is None:
             torch = _torch()

@@ -15,6 +15,8 @@
 // No per-dimension N x N2 derivative matrix is ever formed; W is read once per entry.
 // Reductions are deterministic: warp shuffles -> per-warp shared slots -> per-CTA partials ->
 // one fixed-order pass over the CTAs.
+#include <cmath>
+
 #include "oak_common.cuh"
 
 namespace oak {
@@ -514,6 +516,41 @@ __global__ void __launch_bounds__(256) empirical_dch_kernel(const double* __rest
   if (i < n) out_k[i] = s2 * two_over_l * acc * isv - p.y * half_dlogv;
 }
 
+// d c^/dl per point for the uniform and mixture-of-Gaussians measures (ortho_rbf_kernel.py:49-63,
+// 124-136 differentiated); half_dlogv = v'/(2 v) comes from the host (closed forms, :65-78, :138-152).
+//   uniform [a, b]:  c = s^2 l sqrt(pi/2)/(b-a) [erf(tb) - erf(ta)],  t. = (. - x)/(sqrt(2) l)
+//                    c' = c/l - s^2 sqrt(2)/(b-a) [tb exp(-tb^2) - ta exp(-ta^2)]
+//   MOG:             c = s^2 l sum_k w_k g_k,  g_k = exp(-(x-m_k)^2/(2 S_k))/sqrt(S_k),  S_k = l^2 + var_k
+//                    c' = c/l + s^2 l sum_k w_k g_k [(x-m_k)^2 l/S_k^2 - l/S_k]
+__global__ void __launch_bounds__(256) measure_dch_kernel(DimDev d, const double* __restrict__ inv_sqrt_v_slot,
+                                                          double half_dlogv, const double2* __restrict__ pts_k,
+                                                          int64_t n, double* __restrict__ out_k) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const double2 p = pts_k[i];
+  const double x = p.x / d.xscale;
+  const double l = d.lengthscale;
+  const double isv = *inv_sqrt_v_slot;
+  double dc = 0.0;
+  if (d.measure == OAK_MEASURE_UNIFORM) {
+    const double a = d.c1, b = d.c2;
+    const double ta = (a - x) * d.inv_sqrt2_l, tb = (b - x) * d.inv_sqrt2_l;
+    const double c = d.c0 * (erf(tb) - erf(ta));
+    dc = c / l - d.s2 * sqrt(2.0) / (b - a) * (tb * exp(-tb * tb) - ta * exp(-ta * ta));
+  } else {  // MOG
+    double c = 0.0, extra = 0.0;
+    for (int q = 0; q < d.count; ++q) {
+      const double S = l * l + d.v1[q];
+      const double t = x - d.v0[q];
+      const double g = exp(-0.5 * t * t / S) / sqrt(S) * d.v2[q];
+      c += g;
+      extra = fma(g, t * t * l / (S * S) - l / S, extra);
+    }
+    dc = d.c0 * c / l + d.c0 * extra;  // c0 = s^2 l
+  }
+  out_k[i] = dc * isv - p.y * half_dlogv;
+}
+
 // ---- host side ------------------------------------------------------------------------------
 static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vector<int>& orig_of_pos) {
   out.assign(spec->D, BwDim{0, 0, 0, 0, 0, 0, 0});
@@ -540,8 +577,8 @@ static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vect
       b.half_kappa = 0.5 * (1.0 / l + l / (l * l + 2.0 * delta2) - 2.0 * l / l2d);
       b.uc = l / (l2d * l2d);
       b.kind = 1.0;
-    } else if (dd.measure == OAK_MEASURE_EMPIRICAL) {
-      b.kind = 2.0;
+    } else {
+      b.kind = 2.0;  // empirical / uniform / MOG: per-point block from oak_prepare_backward_f64
     }
     out[k] = b;
   }
@@ -636,6 +673,34 @@ extern "C" int oak_prepare_backward_f64(const oak_spec* spec, const void* d_poin
   const int64_t n_pad = padded(n);
   for (int k = 0; k < spec->Dc; ++k) {
     const DimDev& dd = spec->h_dims[k];
+    if (dd.measure == OAK_MEASURE_UNIFORM || dd.measure == OAK_MEASURE_MOG) {
+      // v'/(2v) on the host: closed forms of var_s differentiated
+      const double l = dd.lengthscale;
+      double v = 0.0, dv = 0.0;
+      if (dd.measure == OAK_MEASURE_UNIFORM) {
+        const double delta = dd.c2 - dd.c1, y = delta / std::sqrt(2.0) / l;
+        const double sp = std::sqrt(M_PI);
+        v = 2.0 / (delta * delta) * dd.s2 * l * l * (sp * y * std::erf(y) + std::exp(-y * y) - 1.0);
+        dv = 2.0 / (delta * delta) * dd.s2 * l * (sp * y * std::erf(y) + 2.0 * std::exp(-y * y) - 2.0);
+      } else {
+        const double* m = spec->h_blob.data() + spec->blob_off0[k];
+        const double* var = spec->h_blob.data() + spec->blob_off1[k];
+        const double* w = spec->h_blob.data() + spec->blob_off2[k];
+        for (int i = 0; i < dd.count; ++i)
+          for (int j = 0; j < dd.count; ++j) {
+            const double T = l * l + var[i] + var[j];
+            const double dist = (m[i] - m[j]) * (m[i] - m[j]);
+            const double h = w[i] * w[j] * std::exp(-0.5 * dist / T) / std::sqrt(T);
+            v += dd.s2 * l * h;
+            dv += dd.s2 * h + dd.s2 * l * h * (dist * l / (T * T) - l / T);
+          }
+      }
+      measure_dch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+          dd, spec->d_inv_sqrt_v + k, 0.5 * dv / v, (const double2*)d_points + (int64_t)k * n_pad, n,
+          (double*)d_dpoints + (int64_t)k * n_pad);
+      OAK_LAUNCHED();
+      continue;
+    }
     if (dd.measure != OAK_MEASURE_EMPIRICAL) continue;
     const int threads = 256;
     const int blocks = (dd.count + threads - 1) / threads;
@@ -691,9 +756,12 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   prm.dch_row = (const double*)d_dpoints;
   prm.dch_col = same ? (const double*)d_dpoints : (const double*)d_dpoints2;
   bool need_dch = false;
-  for (int k = 0; k < spec->Dc; ++k) need_dch |= spec->h_dims[k].measure == OAK_MEASURE_EMPIRICAL;
+  for (int k = 0; k < spec->Dc; ++k) {
+    const int ms = spec->h_dims[k].measure;
+    need_dch |= ms == OAK_MEASURE_EMPIRICAL || ms == OAK_MEASURE_UNIFORM || ms == OAK_MEASURE_MOG;
+  }
   OAK_REQUIRE(!need_dch || (prm.dch_row && prm.dch_col),
-              "oak_gram_backward_f64: empirical-measure dims need the oak_prepare_backward_f64 blocks");
+              "oak_gram_backward_f64: empirical / uniform / MOG dims need the oak_prepare_backward_f64 blocks");
   prm.mm_row = points_minmax(spec, prm.pts_row, prm.n_row_pad);
   prm.mm_col = points_minmax(spec, prm.pts_col, prm.n_col_pad);
   prm.W = d_W;
@@ -731,9 +799,11 @@ extern "C" int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_po
                                           void* d_work, void* stream_) {
   OAK_REQUIRE(spec && d_points && d_grad && d_work, "oak_gram_diag_backward_f64: null argument");
   if (n <= 0) return 0;
-  for (int k = 0; k < spec->Dc; ++k)
-    OAK_REQUIRE(spec->h_dims[k].measure != OAK_MEASURE_EMPIRICAL || d_dpoints,
-                "oak_gram_diag_backward_f64: empirical-measure dims need the oak_prepare_backward_f64 block");
+  for (int k = 0; k < spec->Dc; ++k) {
+    const int ms = spec->h_dims[k].measure;
+    OAK_REQUIRE(!(ms == OAK_MEASURE_EMPIRICAL || ms == OAK_MEASURE_UNIFORM || ms == OAK_MEASURE_MOG) || d_dpoints,
+                "oak_gram_diag_backward_f64: empirical / uniform / MOG dims need the oak_prepare_backward_f64 block");
+  }
   const int depth = spec->depth < 1 ? 1 : spec->depth;
   cudaStream_t stream = (cudaStream_t)stream_;
   const BwDim* d_bw;

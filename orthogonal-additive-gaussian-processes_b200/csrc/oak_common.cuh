@@ -98,6 +98,8 @@ struct oak_spec {
   double* d_tables = nullptr;          // discrete tables blob
   int tables_len = 0;
   double* d_blob = nullptr;            // per-measure arrays
+  std::vector<double> h_blob;          // host copy (backward pass: closed-form d var_s / dl of MOG measures)
+  std::vector<size_t> blob_off0, blob_off1, blob_off2;  // [D] offsets of v0 / v1 / v2 per kernel-order dim
   const double* d_exptab = nullptr;    // 2^(j/256)
 };
 

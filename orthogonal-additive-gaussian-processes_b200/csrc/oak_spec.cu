@@ -319,6 +319,10 @@ extern "C" int oak_spec_create(const oak_kernel_desc* desc, void* stream_, oak_s
     oak_spec_destroy(s);
     return 1;
   };
+  s->h_blob = blob;
+  s->blob_off0 = off0;
+  s->blob_off1 = off1;
+  s->blob_off2 = off2;
   if (!blob.empty()) {
     if (cudaMalloc(&s->d_blob, blob.size() * sizeof(double)) != cudaSuccess) return fail("cudaMalloc");
     if (cudaMemcpyAsync(s->d_blob, blob.data(), blob.size() * sizeof(double),

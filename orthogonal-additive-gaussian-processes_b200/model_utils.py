@@ -83,6 +83,19 @@ def create_model_oak(
     return model
 
 
+def estimate_one_dim_gmm(K: int, X: np.ndarray) -> MOGMeasure:
+    """Spherical Gaussian mixture fitted to one input column (model_utils.py:753-770); host preprocessing."""
+    from sklearn.mixture import GaussianMixture
+
+    X = np.asarray(X, dtype=np.float64)
+    if X.ndim != 1:
+        raise ValueError(f"expected a 1-D array, got shape {X.shape}")
+    assert K > 0
+    gm = GaussianMixture(n_components=int(K), random_state=0, covariance_type="spherical").fit(X.reshape(-1, 1))
+    assert np.allclose(gm.weights_.sum(), 1.0)
+    return MOGMeasure(weights=gm.weights_, means=gm.means_.reshape(-1), variances=gm.covariances_)
+
+
 def _calculate_features(X, categorical_feature, binary_feature):
     """Feature typing and discrete measures (model_utils.py:703-750): p0 = 1 - mean, p = frequencies."""
     if binary_feature is None and categorical_feature is None:
@@ -187,15 +200,16 @@ class oak_model:
                 raise ValueError(
                     f"GMM measure on inputs {idx_gmm} should only be used on continuous inputs {self.continuous_index}"
                 )
-            if len(idx_gmm) > 0:
-                raise NotImplementedError("GMM fitting (sklearn) is host preprocessing outside the hot path; "
-                                          "pass MOGMeasure objects to create_model_oak(gmm_measures=...)")
         self.estimated_gmm_measures = [None] * self.num_dims
+        if self.gmm_measure is not None:  # one-off host preprocessing (:293-300)
+            for i_dim in np.flatnonzero(self.gmm_measure):
+                self.estimated_gmm_measures[i_dim] = estimate_one_dim_gmm(K=self.gmm_measure[i_dim], X=X[:, i_dim])
         self.empirical_locations = [None] * self.num_dims
         self.empirical_weights = [None] * self.num_dims
         self.input_flows = [None] * self.num_dims
         flow_dims = [i for i in self.continuous_index
-                     if not (self.empirical_measure is not None and i in self.empirical_measure)]
+                     if not (self.empirical_measure is not None and i in self.empirical_measure)
+                     and self.estimated_gmm_measures[i] is None]  # (:306-311)
         if self.use_normalising_flow and flow_dims:
             raise NotImplementedError(
                 "normalising flows (TFP bijectors) are preprocessing outside the hot path "

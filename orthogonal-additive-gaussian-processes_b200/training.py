@@ -8,8 +8,8 @@ through the cuSOLVER / cuBLAS bindings of torch -- plumbing), and contracted wit
 backward tiles of ``liboak_b200.so`` (``oak_gram_backward_f64``): no per-dimension derivative
 matrix is ever formed.
 
-Supported trainable parameters: RBF lengthscales of sub-kernels with a Gaussian measure (the OAK
-default after the normalising flow), an empirical measure or no measure, the order variances sigma^2_0..P
+Supported trainable parameters: RBF lengthscales under every measure (Gaussian -- the OAK default
+after the normalising flow --, empirical, uniform, mixture of Gaussians, or none), the order variances sigma^2_0..P
 (``share_var_across_orders=True``), the likelihood variance, the base variances s^2 of the RBF sub-kernels
 where the reference keeps them trainable, and W / kappa of the categorical sub-kernels (through the
 cotangent of their B tables).  Any other *trainable* parameter
@@ -126,11 +126,8 @@ def _check_trainables(model, spec_dims):
     if not getattr(model.kernel, "share_var_across_orders", True):
         raise NotImplementedError("backward tiles need share_var_across_orders=True")
     for p, d in zip(ls, spec_dims):
-        if p is not None and p.trainable:
-            if d.type != _cabi.DIM_RBF or d.measure not in (_cabi.MEASURE_NONE, _cabi.MEASURE_GAUSSIAN,
-                                                            _cabi.MEASURE_EMPIRICAL):
-                raise NotImplementedError("lengthscale gradients exist for RBF sub-kernels with a Gaussian or "
-                                          "empirical measure (or none); set the other lengthscales non-trainable")
+        if p is not None and p.trainable and d.type != _cabi.DIM_RBF:
+            raise NotImplementedError("a lengthscale on a non-RBF sub-kernel cannot be differentiated")
 
 
 # ---- objectives with gradients (constrained space) --------------------------------------------

@@ -346,3 +346,73 @@ def test_base_variance_gradient_matches_autograd():
     go._esp_sum(kd, t(var)).sum().backward()
     assert max_rel_err(gd[-6:-2], s2T.grad.numpy()) < 1e-10
     spec.close()
+
+
+def test_backward_tiles_every_measure_and_base_variances():
+    """helpers.mixed_config: Gaussian, uniform, empirical, MOG and unconstrained RBF dims with s^2 != 1,
+    a binary and a categorical dim.  Lengthscale, base-variance and order-variance gradients of
+    sum W * K and of sum w * K_diag against autograd."""
+    import torch
+
+    from helpers import mixed_config
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg = mixed_config(n=260, seed=5, depth=3)
+    ref = build_oracle(cfg)
+    dims = cfg["dims"]
+    rbf = [0, 1, 2, 3, 6]
+    ls = np.array([dims[i].get("lengthscale", 1.0) for i in range(7)])
+    s2 = np.array([dims[i].get("variance", 1.0) for i in range(7)])
+    var = np.array(cfg["variances"])
+    measures = []
+    for i, d in enumerate(dims):
+        if d["type"] != "rbf":
+            measures.append(("table", ref.dims[i].table()))
+        elif d["measure"] is None:
+            measures.append(("none",))
+        else:
+            measures.append(tuple(d["measure"]))
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    Xt, Zt = t(cfg["X"]), t(cfg["Z"])
+    assert max_rel_err(go._esp_sum(go._dim_values(Zt, Xt, t(ls), measures, t(s2)), t(var)).numpy(),
+                       ref.K(cfg["Z"], cfg["X"])) < 1e-12
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    px, pz = _device.Points(spec, _device.to_device(cfg["X"])), _device.Points(spec, _device.to_device(cfg["Z"]))
+    W = np.random.default_rng(9).standard_normal((260, cfg["Z"].shape[0]))
+    g = _device.gram_backward(spec, px, _device.to_device(W), px2=pz).cpu().numpy()
+    lsT, s2T, vT = (t(a).clone().requires_grad_(True) for a in (ls, s2, var))
+    (t(W) * go._esp_sum(go._dim_values(Xt, Zt, lsT, measures, s2T), vT)).sum().backward()
+    assert max_rel_err(g[rbf], lsT.grad.numpy()[rbf]) < 1e-10
+    assert max_rel_err(g[7:11], vT.grad.numpy()) < 1e-10
+    assert max_rel_err(g[-7:][rbf], s2T.grad.numpy()[rbf]) < 1e-10
+    w = np.random.default_rng(10).standard_normal(260)
+    gd = _device.gram_diag_backward(spec, px, wscale=1.0, w=_device.to_device(w, ndim=1)).cpu().numpy()
+    lsT, s2T, vT = (t(a).clone().requires_grad_(True) for a in (ls, s2, var))
+    kd = [torch.diagonal(v) for v in go._dim_values(Xt, Xt, lsT, measures, s2T)]
+    (t(w) * go._esp_sum(kd, vT)).sum().backward()
+    assert max_rel_err(gd[rbf], lsT.grad.numpy()[rbf]) < 1e-10
+    assert max_rel_err(gd[7:11], vT.grad.numpy()) < 1e-10
+    assert max_rel_err(gd[-7:][rbf], s2T.grad.numpy()[rbf]) < 1e-10
+    spec.close()
+
+
+def test_oak_model_with_gmm_measures_fits_and_trains():
+    """oak_model(gmm_measure=...) (model_utils.py:286-300, 753-770): the mixture is estimated by sklearn on
+    the host, the MOG-constrained kernels run and train on the device (no flow is needed for those inputs)."""
+    from oak_b200.model_utils import oak_model
+    from oak_b200.training import optimise
+
+    rng = np.random.default_rng(21)
+    N = 300
+    X = np.column_stack([np.where(rng.random(N) < 0.4, rng.normal(-2, 0.5, N), rng.normal(1.5, 0.8, N)),
+                         rng.normal(0, 1, N)])
+    y = (np.sin(X[:, 0]) + 0.5 * X[:, 1] + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
+    oak = oak_model(max_interaction_depth=2, gmm_measure=[2, 1], use_normalising_flow=True, sparse=True, num_inducing=40)
+    oak.fit(X, y, optimise=False, initialise_inducing_points=False)
+    assert oak.estimated_gmm_measures[0] is not None and len(oak.estimated_gmm_measures[0].weights) == 2
+    loss0 = oak.m.training_loss()
+    optimise(oak.m, method="BFGS", maxiter=20)
+    assert oak.m.training_loss() < loss0 - 10.0
+    assert float(np.sqrt(np.mean((oak.predict(X) - y[:, 0]) ** 2))) < 0.3
