@@ -23,6 +23,30 @@ from .ortho_rbf_kernel import RBF
 from .utils import compute_sobol_oak
 
 
+def save_model(model, filename) -> None:
+    """Trainable parameter values, in ``model.trainable_parameters`` order, as one object array in an
+    ``.npz`` (model_utils.py:44-63; SVGP, which saves all parameters, is not on this path)."""
+    import os
+    from pathlib import Path
+
+    filename = Path(filename)
+    hyperparams = np.empty(len(model.trainable_parameters), dtype=object)
+    for i, p in enumerate(model.trainable_parameters):
+        hyperparams[i] = p.numpy()
+    os.makedirs(filename.parents[0], exist_ok=True)
+    np.savez(filename, hyperparams=hyperparams)
+
+
+def load_model(model, filename, load_all_parameters: bool = False) -> None:
+    """Inverse of ``save_model`` (model_utils.py:66-87)."""
+    model_params = np.load(str(filename), allow_pickle=True)["hyperparams"]
+    target = model.parameters if load_all_parameters else model.trainable_parameters
+    if len(model_params) < len(target):
+        raise ValueError(f"checkpoint holds {len(model_params)} parameters, the model needs {len(target)}")
+    for i, p in enumerate(target):
+        p.assign(model_params[i])
+
+
 def create_model_oak(
     data,
     max_interaction_depth: int = 2,

@@ -140,3 +140,23 @@ def test_balanced_symmetric_rows_balance_the_triangle(n, world):
     assert sum(work) == n * (n + 1) / 2
     if n >= 4096:
         assert max(work) / min(work) < 1.1
+
+
+def test_save_and_load_model_round_trip(tmp_path):
+    """save_model / load_model (model_utils.py:44-87): trainable parameters in traversal order."""
+    import numpy as np
+
+    from oak_b200.model_utils import create_model_oak, load_model, save_model
+
+    rng = np.random.default_rng(0)
+    X, y = rng.standard_normal((30, 3)), rng.standard_normal((30, 1))
+    a = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=X[:5].copy(), lengthscale_bounds=[1e-3, 1e3])
+    for i, p in enumerate(a.trainable_parameters):
+        p.assign(np.asarray(p.numpy()) * 0 + 0.3 + 0.1 * i)
+    f = tmp_path / "ckpt" / "model.npz"
+    save_model(a, f)
+    b = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=X[:5].copy(), lengthscale_bounds=[1e-3, 1e3])
+    load_model(b, f)
+    assert len(a.trainable_parameters) == len(b.trainable_parameters) == 3 + 3 + 1
+    for p, q in zip(a.trainable_parameters, b.trainable_parameters):
+        np.testing.assert_allclose(p.numpy(), q.numpy(), rtol=1e-12)
