@@ -203,7 +203,7 @@ static int syrk_pick_slices(int tiles, int k_steps, int resident, size_t work_by
   if (max_s > 48) max_s = 48;
   if (max_s < 1) max_s = 1;
   double best_eff = 0.0;
-  double eff[49];
+  double eff[49] = {0.0};
   for (int s = 1; s <= max_s; ++s) {
     const int64_t units = (int64_t)tiles * s;
     eff[s] = 0.0;
