@@ -9,14 +9,20 @@
 //
 // Structure
 //   * persistent CTAs (one per SM), 256 threads as a 16x16 grid, each thread owns an RM x RN
-//     register micro-tile (rows ty+16r, cols tx+16c) -> CTA tile (16 RM) x (16 RN).
+//     register micro-tile (rows ty*RM + r, cols tx + 16c) -> CTA tile (16 RM) x (16 RN); the tile
+//     index is decoded once per CTA and advanced incrementally.
 //   * the prepared row/col point tiles (double2 per point and dim) are staged in shared memory
 //     by cp.async, double buffered over (tile, dim-chunk) stages: one __syncthreads per stage.
-//   * FP64 exp is table driven (oak_common.cuh): the 2^(j/256) table is replicated 16x in shared
-//     memory so that the lookups of a half-warp never bank-conflict.
+//   * FP64 exp is table driven (oak_common.cuh): the 2^(j/1024) table is replicated 8x in shared
+//     memory; a clamp-free body runs when the min/max keys of the prepared coordinates prove the
+//     distances bounded (and s^2 == 1), a general clamped body otherwise -- one uniform decision
+//     per stage.
+//   * epilogue: all Newton-Girard recurrences first, then direct register stores (interior tiles
+//     without bounds checks).
 //   * symmetric mode (X2 = X, full row range): only tiles that intersect the lower triangle are
-//     evaluated; each is also written transposed through a padded shared-memory tile so that the
-//     mirrored stores are coalesced.
+//     evaluated; the transposed tile is staged in 128-byte-swizzled shared memory and leaves through
+//     2-D TMA tensor stores issued after the next stage barrier (no epilogue barrier).
+//   * gram_matvec_kernel: the same tiles contracted with a vector on the fly (prediction mean).
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_pipeline.h>
 
