@@ -181,6 +181,11 @@ size_t oak_sgpr_stats_work_bytes(int64_t m, int64_t chunk);
 int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
                        const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
                        double* d_stats, void* d_work, void* stream);
+/* Same, keeping Kuf for a following backward pass: chunk c is written to d_kuf_store + c*m*chunk
+ * as an m x chunk row-major block (ld = chunk); d_kuf_store holds ceil(n_local/chunk) blocks. */
+int oak_sgpr_stats_keep_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
+                            const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
+                            double* d_stats, void* d_work, double* d_kuf_store, void* stream);
 
 /* M^3 tail of SGPR.elbo (gpflow 2.2.1; re-derived at oak/utils.py:187-198): Cholesky of
  * Kuu + jitter I, whitening of Phi, Cholesky of B, c, the bound and alpha = L^-T LB^-T c.

@@ -86,6 +86,7 @@ SIGNATURES = {
     "oak_sgpr_stats_count": (_sz, [_i64]),
     "oak_sgpr_stats_work_bytes": (_sz, [_i64, _i64]),
     "oak_sgpr_stats_f64": (C.c_int, [_vp, _vp, _i64, _vp, _dp, _i64, _i64, _dp, _vp, _vp]),
+    "oak_sgpr_stats_keep_f64": (C.c_int, [_vp, _vp, _i64, _vp, _dp, _i64, _i64, _dp, _vp, _dp, _vp]),
     "oak_sgpr_finish_work_bytes": (_sz, [_i64]),
     "oak_sgpr_finish_f64": (C.c_int, [_dp, _dp, _i64, _i64, C.c_double, C.c_double, _dp, _dp, _vp, _vp]),
     "oak_gpr_finish_work_bytes": (_sz, [_i64]),

@@ -320,9 +320,9 @@ extern "C" size_t oak_sgpr_stats_work_bytes(int64_t m, int64_t chunk) {
   return (size_t)(m * chunk + chunk) * sizeof(double) + syrk_dmma_work_bytes((int)m);
 }
 
-extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
-                                  const void* d_pointsX, const double* d_y, int64_t n_local,
-                                  int64_t chunk, double* d_stats, void* d_work, void* stream_) {
+static int sgpr_stats_impl(const oak_spec* spec, const void* d_pointsZ, int64_t m, const void* d_pointsX,
+                           const double* d_y, int64_t n_local, int64_t chunk, double* d_stats, void* d_work,
+                           double* d_kuf_store, void* stream_) {
   OAK_REQUIRE(spec && d_pointsZ && d_stats && d_work, "oak_sgpr_stats_f64: null argument");
   OAK_REQUIRE(m >= 1, "oak_sgpr_stats_f64: need at least one inducing point");
   OAK_REQUIRE(n_local >= 0, "oak_sgpr_stats_f64: negative n");
@@ -335,8 +335,8 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
   cublasHandle_t cb;
   if (int rc = handles(&cb, nullptr, stream)) return rc;
 
-  double* kuf = (double*)d_work;           // M x chunk, row-major, ld = chunk
-  double* kdiag = kuf + m * chunk;         // chunk
+  double* kuf_scratch = (double*)d_work;   // M x chunk, row-major, ld = chunk
+  double* kdiag = kuf_scratch + m * chunk; // chunk
   double* partials = kdiag + chunk;        // stream-K partial tiles of the contraction
   const size_t partial_bytes = syrk_dmma_work_bytes((int)m);
   double* phi = d_stats;                   // M x M
@@ -349,6 +349,8 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
 
   for (int64_t c0 = 0; c0 < n_local; c0 += chunk) {
     const int64_t nc = (n_local - c0 < chunk) ? (n_local - c0) : chunk;
+    // the chunk's Kuf block: scratch, or its own slot when the caller keeps Kuf for the backward pass
+    double* kuf = d_kuf_store ? d_kuf_store + (c0 / chunk) * m * chunk : kuf_scratch;
     // Kuf chunk = K(Z, X[c0:c0+nc])    (gpflow Kuf, oak/utils.py:184)
     if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream))
       return rc;
@@ -376,6 +378,23 @@ extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, i
     OAK_LAUNCHED();
   }
   return 0;
+}
+
+extern "C" int oak_sgpr_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
+                                  const void* d_pointsX, const double* d_y, int64_t n_local,
+                                  int64_t chunk, double* d_stats, void* d_work, void* stream_) {
+  return sgpr_stats_impl(spec, d_pointsZ, m, d_pointsX, d_y, n_local, chunk, d_stats, d_work, nullptr, stream_);
+}
+
+// Same, keeping every chunk's Kuf block for the backward pass: chunk c (points [c*chunk, (c+1)*chunk))
+// is written to d_kuf_store + c * m * chunk as an m x chunk row-major block (ld = chunk);
+// d_kuf_store holds ceil(n_local / chunk) such blocks.
+extern "C" int oak_sgpr_stats_keep_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m,
+                                       const void* d_pointsX, const double* d_y, int64_t n_local,
+                                       int64_t chunk, double* d_stats, void* d_work, double* d_kuf_store,
+                                       void* stream_) {
+  OAK_REQUIRE(d_kuf_store, "oak_sgpr_stats_keep_f64: null Kuf store");
+  return sgpr_stats_impl(spec, d_pointsZ, m, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store, stream_);
 }
 
 extern "C" size_t oak_sgpr_finish_work_bytes(int64_t m) {

@@ -146,7 +146,13 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         kern._check_discrete(Zs, spec._keep)
         pz, px = _device.Points(spec, Zs), _device.Points(spec, Xs)
         m, n_local = pz.n, px.n
-        stats = _device.sgpr_stats(spec, pz, px, Yd, chunk=model.chunk)
+        # Kuf is kept for the backward pass when it fits comfortably (8.2 GB at N = 10^6, M = 1024);
+        # otherwise its chunks are recomputed in the second pass
+        keep = 8.0 * m * n_local < 48e9
+        if keep:
+            stats, kuf_blocks, chunk_eff = _device.sgpr_stats(spec, pz, px, Yd, chunk=model.chunk, keep_kuf=True)
+        else:
+            stats = _device.sgpr_stats(spec, pz, px, Yd, chunk=model.chunk)
         n_total = n_local
         if model.distributed:
             parallel.allreduce_sum_(stats)
@@ -187,14 +193,25 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         # second pass over the local points: W^T = 2 Kuf^T G_phi + y g_b^T, contracted by the backward tiles
         nout = int(_cabi.load().oak_backward_grad_count(spec.handle))  # lengthscales | variances | table blob
         grad = torch.zeros(nout, dtype=torch.float64, device=Kuu.device)
-        chunk = max(64, (int(model.chunk) + 63) // 64 * 64)
         G2 = (2.0 * G_phi).contiguous()
-        for c0 in range(0, n_local, chunk):
-            c1 = min(c0 + chunk, n_local)
-            Kt = _device.gram(spec, px, pz, row_begin=c0, row_end=c1)  # (nc, M) = Kuf[:, c0:c1]^T
-            Wt = torch.addmm(Yd[c0:c1].reshape(-1, 1) @ g_b.T, Kt, G2)
-            _device.gram_backward(spec, px, Wt, px2=pz, row_begin=c0, row_end=c1, grad=grad)
-            del Kt, Wt
+        if keep:
+            # W = 2 G_phi Kuf + g_b y^T per kept chunk (M x nc), rows = inducing points
+            for c, Kc in enumerate(kuf_blocks):
+                c0 = c * chunk_eff
+                c1 = c0 + Kc.shape[1]
+                Wc = torch.addmm(g_b @ Yd[c0:c1].reshape(1, -1), G2, Kc)
+                pxc = _device.Points(spec, Xs[c0:c1])
+                _device.gram_backward(spec, pz, Wc, px2=pxc, grad=grad)
+                del Wc, pxc
+            del kuf_blocks
+        else:
+            chunk = max(64, (int(model.chunk) + 63) // 64 * 64)
+            for c0 in range(0, n_local, chunk):
+                c1 = min(c0 + chunk, n_local)
+                Kt = _device.gram(spec, px, pz, row_begin=c0, row_end=c1)  # (nc, M) = Kuf[:, c0:c1]^T
+                Wt = torch.addmm(Yd[c0:c1].reshape(-1, 1) @ g_b.T, Kt, G2)
+                _device.gram_backward(spec, px, Wt, px2=pz, row_begin=c0, row_end=c1, grad=grad)
+                del Kt, Wt
         _device.gram_diag_backward(spec, px, wscale=g_s, grad=grad)
         if model.distributed:
             parallel.allreduce_sum_(grad)
