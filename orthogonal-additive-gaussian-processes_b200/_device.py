@@ -288,9 +288,11 @@ def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad
 
 
 # ---- SGPR / GPR -------------------------------------------------------------------------
-def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 65536, stats=None, keep_kuf: bool = False):
+def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 65536, stats=None, keep_kuf: bool = False,
+               kuf_store=None):
     """Accumulates Phi | Kuf y | sum K_diag | y^T y for the local points into ``stats``.
-    ``keep_kuf``: also returns the list of per-chunk Kuf blocks (M x nc views) for a backward pass."""
+    ``keep_kuf``: also returns the list of per-chunk Kuf blocks (M x nc views) for a backward pass and
+    the (nchunks, M, chunk) buffer holding them (pass it back as ``kuf_store`` to reuse the allocation)."""
     torch = _torch()
     lib = _cabi.load()
     m = pz.n
@@ -304,14 +306,16 @@ def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 65536, stats=
     yv = y.reshape(-1).contiguous()
     if keep_kuf:
         nchunks = max((px.n + chunk - 1) // chunk, 1)
-        store = torch.empty((nchunks, m, chunk), dtype=torch.float64, device=pz.buf.device)
+        store = kuf_store
+        if store is None or tuple(store.shape) != (nchunks, m, chunk) or store.device != pz.buf.device:
+            store = torch.empty((nchunks, m, chunk), dtype=torch.float64, device=pz.buf.device)
         check(
             lib.oak_sgpr_stats_keep_f64(spec.handle, _p(pz.buf), m, _p(px.buf), _p(yv), px.n, chunk, _p(stats),
                                         _p(work), _p(store), C.c_void_p(stream_ptr())),
             "oak_sgpr_stats_keep_f64",
         )
         blocks = [store[c, :, : min(chunk, px.n - c * chunk)] for c in range(nchunks) if px.n - c * chunk > 0]
-        return stats, blocks, chunk
+        return stats, blocks, chunk, store
     check(
         lib.oak_sgpr_stats_f64(spec.handle, _p(pz.buf), m, _p(px.buf), _p(yv), px.n, chunk, _p(stats),
                                _p(work), C.c_void_p(stream_ptr())),

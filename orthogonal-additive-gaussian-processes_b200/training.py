@@ -150,7 +150,9 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         # otherwise its chunks are recomputed in the second pass
         keep = 8.0 * m * n_local < 48e9
         if keep:
-            stats, kuf_blocks, chunk_eff = _device.sgpr_stats(spec, pz, px, Yd, chunk=model.chunk, keep_kuf=True)
+            # the 8 GB buffer is kept on the model between evaluations (an optimiser calls this in a loop)
+            stats, kuf_blocks, chunk_eff, model._kuf_store = _device.sgpr_stats(
+                spec, pz, px, Yd, chunk=model.chunk, keep_kuf=True, kuf_store=getattr(model, "_kuf_store", None))
         else:
             stats = _device.sgpr_stats(spec, pz, px, Yd, chunk=model.chunk)
         n_total = n_local
