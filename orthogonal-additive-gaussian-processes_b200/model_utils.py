@@ -2,11 +2,11 @@
 
 Drop-in for the hot-path entry points of the reference's ``oak/model_utils.py``:
 ``create_model_oak`` (:90-176) and ``oak_model.fit / predict / get_sobol`` (:194-524), with the same
-argument names, defaults and error behaviour.  Host-side preprocessing that the reference does with
-TFP normalising flows / sklearn (k-means inducing points, GMM fitting, plotting) is outside the
-hot path (out of scope); ``oak_model`` therefore supports
-``use_normalising_flow=False`` (standardised continuous inputs, :327-330) and takes inducing points
-from the data (``initialise_inducing_points=False``, :392-393) unless scikit-learn is present.
+argument names, defaults and error behaviour, the BFGS training step (``training.py``: gradients from
+the backward tiles), ``save_model`` / ``load_model``.  The one-off host-side preprocessing of the
+reference stays on the host: the per-column normalising flow (``normalising_flow.py``, NumPy +
+scipy L-BFGS-B instead of TFP), sklearn k-means for the inducing points and sklearn Gaussian
+mixtures for the MOG measures; plotting is out of scope.
 """
 from __future__ import annotations
 
@@ -105,6 +105,18 @@ def create_model_oak(
 
         _optimise(model, method="BFGS")
     return model
+
+
+def apply_normalise_flow(X, input_flows):
+    """Each column through its flow, untouched where there is none (model_utils.py:179-191)."""
+    X = np.asarray(X, dtype=np.float64)
+    X_scaled = np.zeros(X.shape)
+    for ii in range(X.shape[1]):
+        if input_flows is None or input_flows[ii] is None:
+            X_scaled[:, ii] = X[:, ii]
+        else:
+            X_scaled[:, ii] = input_flows[ii].bijector(X[:, ii])
+    return X_scaled
 
 
 def estimate_one_dim_gmm(K: int, X: np.ndarray) -> MOGMeasure:
@@ -234,11 +246,13 @@ class oak_model:
         flow_dims = [i for i in self.continuous_index
                      if not (self.empirical_measure is not None and i in self.empirical_measure)
                      and self.estimated_gmm_measures[i] is None]  # (:306-311)
-        if self.use_normalising_flow and flow_dims:
-            raise NotImplementedError(
-                "normalising flows (TFP bijectors) are preprocessing outside the hot path "
-                "(SURVEY.md section 8(f), next row 3); construct oak_model(use_normalising_flow=False)"
-            )
+        if self.use_normalising_flow:  # one flow per remaining continuous input (:305-317): host preprocessing
+            from .normalising_flow import Normalizer
+
+            for i in flow_dims:
+                n = Normalizer(X[:, i])
+                n.fit()
+                self.input_flows[i] = n
         self.alpha = None
         self.scaler_y = _Standardiser().fit(Y)
         self.Y_scaled = self.scaler_y.transform(Y)
@@ -294,7 +308,7 @@ class oak_model:
         return Z
 
     def _transform_x(self, X):
-        X = np.array(X, dtype=np.float64, copy=True)
+        X = apply_normalise_flow(np.asarray(X, dtype=np.float64), self.input_flows)
         if self.empirical_measure is not None:
             X[:, self.empirical_measure] = self.scaler_X_empirical.transform(X[:, self.empirical_measure])
         if not self.use_normalising_flow:
@@ -314,6 +328,17 @@ class oak_model:
         # only the mean of predict_f is used (model_utils.py:441): take the fused mean when there is one
         y_pred = self.m.predict_mean(Xs) if hasattr(self.m, "predict_mean") else self.m.predict_f(Xs)[0]
         return self.scaler_y.inverse_transform(np.asarray(y_pred))[:, 0]
+
+    def _get_x_inverse_transformer(self, i: int):
+        """Inverse transformation of continuous feature ``i`` (:478-497)."""
+        assert i in self.continuous_index
+        if self.empirical_measure is not None and i in self.empirical_measure:
+            j = self.empirical_measure.index(i)
+            mean_i, std_i = self.scaler_X_empirical.mean_[j], np.sqrt(self.scaler_X_empirical.var_[j])
+            return lambda x: x * std_i + mean_i
+        if self.gmm_measure is not None and i in self.gmm_measure:  # (sic: membership test as in the reference)
+            return None
+        return self.input_flows[i].bijector.inverse
 
     def get_sobol(self, likelihood_variance=False):
         """Normalised Sobol index of each additive term (:499-524)."""

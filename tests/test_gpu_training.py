@@ -416,3 +416,31 @@ def test_oak_model_with_gmm_measures_fits_and_trains():
     optimise(oak.m, method="BFGS", maxiter=20)
     assert oak.m.training_loss() < loss0 - 10.0
     assert float(np.sqrt(np.mean((oak.predict(X) - y[:, 0]) ** 2))) < 0.3
+
+
+def test_default_oak_model_with_normalising_flow_end_to_end():
+    """The reference's default path: oak_model() (use_normalising_flow=True) on skewed positive inputs --
+    flows fitted on the host (normalising_flow.py), GPR on the device, BFGS training, prediction and
+    Sobol indices (cf. examples/uci and test_oak_model.py of the reference)."""
+    from oak_b200.model_utils import oak_model
+
+    rng = np.random.default_rng(5)
+    N = 250
+    X = np.column_stack([np.exp(0.5 * rng.standard_normal(N)), rng.gamma(3.0, 1.0, N), rng.standard_normal(N) ** 2 + 0.1])
+    f = lambda A: np.log(A[:, 0]) ** 2 + 0.5 * A[:, 1] + 0.0 * A[:, 2]
+    y = (f(X) + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
+    oak = oak_model(max_interaction_depth=2)
+    oak.fit(X, y, optimise=False)
+    assert all(fl is not None for fl in oak.input_flows)
+    Xs = oak._transform_x(X)
+    assert np.all(np.abs(Xs.mean(0)) < 0.15) and np.all(np.abs(Xs.std(0) - 1) < 0.15)
+    loss0 = oak.m.training_loss()
+    oak.optimise()
+    assert oak.m.training_loss() < loss0 - 10.0
+    Xt = np.column_stack([np.exp(0.5 * rng.standard_normal(100)), rng.gamma(3.0, 1.0, 100), rng.standard_normal(100) ** 2 + 0.1])
+    rmse = float(np.sqrt(np.mean((oak.predict(Xt, clip=True) - f(Xt)) ** 2)))
+    assert rmse < 0.5
+    sob = oak.get_sobol()
+    assert sob[0] + sob[1] > 0.8 and sob[2] < 0.05
+    inv = oak._get_x_inverse_transformer(0)
+    np.testing.assert_allclose(inv(Xs[:, 0]), X[:, 0], rtol=1e-8)
