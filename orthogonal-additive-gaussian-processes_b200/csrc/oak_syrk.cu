@@ -58,7 +58,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(syrk::kThreads, 2) syrk_lower_dmma_kernel(const SyrkParams prm) {
+#ifndef OAK_SYRK_MINB
+#define OAK_SYRK_MINB 2
+#endif
+__global__ void __launch_bounds__(syrk::kThreads, OAK_SYRK_MINB) syrk_lower_dmma_kernel(const SyrkParams prm) {
   using namespace syrk;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
@@ -122,6 +125,29 @@ __global__ void __launch_bounds__(syrk::kThreads, 2) syrk_lower_dmma_kernel(cons
       // this lane's k values: groups of four consecutive ones, 16 apart (kk -> (kk/4)*16 + 4q + kk%4)
 #pragma unroll
       for (int h = 0; h < kKT / 16; ++h) {
+#ifndef OAK_SYRK_HALF_FRAGS
+#define OAK_SYRK_HALF_FRAGS 0  // 1: hold two k values per fragment load; with OAK_SYRK_MINB=4 (128 registers,
+                               // 4 CTAs / SM) measured SLOWER: 58.0-58.6 vs 55.7 ms per 10^6 points (profiles/)
+#endif
+#if OAK_SYRK_HALF_FRAGS
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          double a[4][2], b[4][2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double2 x = *reinterpret_cast<const double2*>(As + i * 8 * kRowStride + h * 16 + 2 * h2);
+            a[i][0] = x.x; a[i][1] = x.y;
+            const double2 y = *reinterpret_cast<const double2*>(Bs + i * 8 * kRowStride + h * 16 + 2 * h2);
+            b[i][0] = y.x; b[i][1] = y.y;
+          }
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i][kk], b[j][kk]);
+        }
+#else
         double a[4][4], b[4][4];  // [row block][k step]
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -138,6 +164,7 @@ __global__ void __launch_bounds__(syrk::kThreads, 2) syrk_lower_dmma_kernel(cons
           for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i][kk], b[j][kk]);
+#endif
       }
     }
     asm volatile("cp.async.wait_group 0;\n");
