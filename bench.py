@@ -386,7 +386,7 @@ def main():
         b, e = parallel.partition_rows(args.elbo_n, world)[rank]
         kc = build_kernel(cfg_c)
         kc.esp_algorithm = args.algo
-        model = SGPR((cfg_c["X"][b:e], cfg_c["y"][b:e]), kernel=kc, inducing_variable=cfg_c["Z"], chunk=65536,
+        model = SGPR((cfg_c["X"][b:e], cfg_c["y"][b:e]), kernel=kc, inducing_variable=cfg_c["Z"], chunk=262144,
                      distributed=(world > 1))
         model.likelihood.variance.assign(cfg_c["noise"])
         model._device_data()

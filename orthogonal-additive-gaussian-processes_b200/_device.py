@@ -288,7 +288,7 @@ def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad
 
 
 # ---- SGPR / GPR -------------------------------------------------------------------------
-def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 65536, stats=None, keep_kuf: bool = False,
+def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 262144, stats=None, keep_kuf: bool = False,
                kuf_store=None):
     """Accumulates Phi | Kuf y | sum K_diag | y^T y for the local points into ``stats``.
     ``keep_kuf``: also returns the list of per-chunk Kuf blocks (M x nc views) for a backward pass and

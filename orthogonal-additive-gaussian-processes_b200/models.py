@@ -117,7 +117,7 @@ class SGPR(GPModel):
     """Titsias' sparse GP regression bound (gpflow 2.2.1 ``SGPR``; model_utils.py:150-155)."""
 
     def __init__(self, data, kernel, inducing_variable, mean_function=None, noise_variance: float = 1.0,
-                 chunk: int = 65536, distributed: Optional[bool] = None):
+                 chunk: int = 262144, distributed: Optional[bool] = None):
         super().__init__(data, kernel, mean_function, noise_variance)
         if not isinstance(inducing_variable, InducingPoints):
             inducing_variable = InducingPoints(inducing_variable)
