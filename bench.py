@@ -68,15 +68,36 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
         self.nvml, self.handle, self.stop_flag, self.samples = None, None, False, []
         self.max_mhz, self.reason_bits = None, 0
+        self.smi_id = self._physical_id(index)
         try:
             import pynvml
 
             pynvml.nvmlInit()
             self.nvml = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.handle = (pynvml.nvmlDeviceGetHandleByUUID(self.smi_id) if self.smi_id.startswith("GPU-")
+                           else pynvml.nvmlDeviceGetHandleByIndex(int(self.smi_id)))
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
         except Exception:
             self.nvml = None
+
+    @staticmethod
+    def _physical_id(local):
+        """NVML / nvidia-smi identifier of CUDA device `local`: CUDA_VISIBLE_DEVICES may renumber the
+        devices, NVML never does -- go through the UUID (or the visible-devices list)."""
+        try:
+            import torch
+
+            u = str(torch.cuda.get_device_properties(local).uuid)
+            if len(u) >= 32:
+                return u if u.startswith("GPU-") else "GPU-" + u
+        except Exception:
+            pass
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").strip()
+        if vis:
+            toks = [t.strip() for t in vis.split(",") if t.strip()]
+            if local < len(toks):
+                return toks[local]
+        return str(local)
 
     def _poll(self):
         nv = self.nvml
@@ -98,7 +119,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                ["nvidia-smi", "-i", self.smi_id, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                  "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
