@@ -444,3 +444,22 @@ def test_default_oak_model_with_normalising_flow_end_to_end():
     assert sob[0] + sob[1] > 0.8 and sob[2] < 0.05
     inv = oak._get_x_inverse_transformer(0)
     np.testing.assert_allclose(inv(Xs[:, 0]), X[:, 0], rtol=1e-8)
+
+
+def test_oak_model_switches_to_sgpr_with_kmeans_inducing_points_above_1000_points():
+    """N > 1000 -> sparse GP with k-means inducing points (model_utils.py:373-391, utils.py:555-574),
+    flows on the host, training on the device."""
+    from oak_b200.model_utils import oak_model
+    from oak_b200.models import SGPR
+
+    rng = np.random.default_rng(8)
+    N = 1200
+    X = np.column_stack([rng.gamma(2.0, 1.0, N), rng.standard_normal(N)])
+    y = (np.sqrt(X[:, 0]) + np.sin(2 * X[:, 1]) + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
+    oak = oak_model(max_interaction_depth=2, num_inducing=40)
+    oak.fit(X, y, optimise=True)
+    assert isinstance(oak.m, SGPR) and oak.m.inducing_variable.Z.numpy().shape == (40, 2)
+    rmse = float(np.sqrt(np.mean((oak.predict(X) - y[:, 0]) ** 2)))
+    assert rmse < 0.2
+    sob = oak.get_sobol()
+    assert abs(sob.sum() - 1) < 1e-12 and sob[2] < 0.1  # little interaction in an additive target
