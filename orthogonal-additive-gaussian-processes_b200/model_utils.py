@@ -23,6 +23,14 @@ from .ortho_rbf_kernel import RBF
 from .utils import compute_sobol_oak
 
 
+def get_kmeans_centers(X: np.ndarray, K: int = 500) -> np.ndarray:
+    """K-means centres used as inducing points (model_utils.py:31-41); host preprocessing (sklearn)."""
+    from sklearn.cluster import KMeans
+
+    np.random.seed(44)
+    return KMeans(n_clusters=K, random_state=0).fit(X).cluster_centers_
+
+
 def save_model(model, filename) -> None:
     """Trainable parameter values, in ``model.trainable_parameters`` order, as one object array in an
     ``.npz`` (model_utils.py:44-63; SVGP, which saves all parameters, is not on this path)."""
@@ -328,6 +336,12 @@ class oak_model:
         # only the mean of predict_f is used (model_utils.py:441): take the fused mean when there is one
         y_pred = self.m.predict_mean(Xs) if hasattr(self.m, "predict_mean") else self.m.predict_f(Xs)[0]
         return self.scaler_y.inverse_transform(np.asarray(y_pred))[:, 0]
+
+    def get_loglik(self, X, y, clip=False):
+        """Mean predictive log density on (X, y) in the scaled output space (:445-460)."""
+        X = np.asarray(X, dtype=np.float64)
+        Xs = self._transform_x(np.clip(X, self.xmin, self.xmax)) if clip else self._transform_x(X)
+        return float(np.mean(self.m.predict_log_density((Xs, self.scaler_y.transform(np.asarray(y, dtype=np.float64))))))
 
     def _get_x_inverse_transformer(self, i: int):
         """Inverse transformation of continuous feature ``i`` (:478-497)."""

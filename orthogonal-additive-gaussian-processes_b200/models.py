@@ -61,6 +61,16 @@ class GPModel(Module):
     def training_loss_closure(self):
         return self.training_loss
 
+    def predict_log_density(self, data):
+        """gpflow ``GPModel.predict_log_density`` for the Gaussian likelihood: per point
+        log N(y; f_mean, f_var + noise) (used by ``oak_model.get_loglik``, model_utils.py:445-460)."""
+        X, Y = data
+        mean, var = self.predict_f(X)
+        mean, var = np.asarray(mean, dtype=np.float64), np.asarray(var, dtype=np.float64)
+        Y = np.asarray(Y, dtype=np.float64).reshape(mean.shape)
+        s2 = var + scalar_of(self.likelihood.variance)
+        return (-0.5 * np.log(2.0 * np.pi * s2) - 0.5 * (Y - mean) ** 2 / s2).sum(-1)
+
     def training_loss_and_grad(self):
         """(training_loss, d/d unconstrained trainables): what TensorFlow autodiff hands to the scipy
         optimiser in the reference (model_utils.py:168-175); see training.py."""

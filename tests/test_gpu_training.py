@@ -444,6 +444,8 @@ def test_default_oak_model_with_normalising_flow_end_to_end():
     assert sob[0] + sob[1] > 0.8 and sob[2] < 0.05
     inv = oak._get_x_inverse_transformer(0)
     np.testing.assert_allclose(inv(Xs[:, 0]), X[:, 0], rtol=1e-8)
+    ll = oak.get_loglik(Xt, f(Xt).reshape(-1, 1), clip=True)  # mean predictive log density (model_utils.py:445-460)
+    assert np.isfinite(ll) and ll > -1.0
 
 
 def test_oak_model_switches_to_sgpr_with_kmeans_inducing_points_above_1000_points():
