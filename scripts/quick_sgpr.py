@@ -11,14 +11,14 @@ def timeit(fn, reps=3, warm=1):
     for _ in range(reps):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     return float(np.median(ts))
-n = 524_288
+n = 1_000_000
 cfg = config_C(n)
 k = build_kernel(cfg); spec = k._make_spec()
 Xd, Zd, yd = _device.to_device(cfg["X"]), _device.to_device(cfg["Z"]), _device.to_device(cfg["y"])
 pz, px = _device.Points(spec, Zd), _device.Points(spec, Xd)
 peak = 18.37e12
 ref = None
-for chunk in (32768, 65536, 131072, 262144):
+for chunk in (262144,):
     st = _device.sgpr_stats(spec, pz, px, yd, chunk=chunk)
     t = timeit(lambda: _device.sgpr_stats(spec, pz, px, yd, chunk=chunk))
     if ref is None: ref = st.clone()
