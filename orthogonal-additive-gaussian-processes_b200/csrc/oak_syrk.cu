@@ -27,7 +27,7 @@ constexpr int kTile = 64;         // CTA tile (rows and columns of Phi)
 #define OAK_SYRK_KT 16
 #endif
 #ifndef OAK_SYRK_STAGES
-#define OAK_SYRK_STAGES 3  // measured: 3 stages (3 CTAs / SM) 56.7 ms per 10^6 points, 4: 57.9, 6: 56.8; KT=32: 58.0
+#define OAK_SYRK_STAGES 3  // measured (65536-point chunks): 3 stages 56.7 ms per 10^6 points, 4: 57.9, 6: 56.8; KT=32: 58.0
 #endif
 constexpr int kKT = OAK_SYRK_KT;  // k values per pipeline stage (16 or 32)
 constexpr int kStages = OAK_SYRK_STAGES;
@@ -59,7 +59,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 #ifndef OAK_SYRK_MINB
-#define OAK_SYRK_MINB 2
+#define OAK_SYRK_MINB 2  // 182 registers, 2 CTAs / SM: 54.3 ms per 10^6 points; 3 (153 registers): 57.2; 4: 58.0
 #endif
 __global__ void __launch_bounds__(syrk::kThreads, OAK_SYRK_MINB) syrk_lower_dmma_kernel(const SyrkParams prm) {
   using namespace syrk;
