@@ -338,7 +338,11 @@ def main():
         pass
     out_bytes = (n * n if world == 1 else sum((e - b) * e for b, e in strips)) * 8.0
     roofline = {
-        "bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "bound": "fp64",
+        "bound_note": "FP64 (DFMA) pipe: neither of the template's roofs binds -- 8 B of HBM traffic per entry "
+                      "against >= 242 FP64 instructions, no tensor-core work in this kernel; the hbm sub-object "
+                      "carries the HBM line",
+        "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": achieved_tflops / peak_tflops, "traffic": traffic,
         "kernel": "oak::gram_kernel<4,4,4,NG>", "kernel_ms": kern_ms,
         "peak_source": "measured in this run: oak_measure_fp64_peak (register-resident DFMA chains, burst); "
