@@ -456,6 +456,7 @@ def main():
         try:
             from oak_b200.training import freeze_unsupported, sgpr_elbo_and_grad
 
+            model.inducing_variable.Z.trainable = False  # zfixed=True, the reference's default
             freeze_unsupported(model)
             sgpr_elbo_and_grad(model)
             barrier()
@@ -467,6 +468,18 @@ def main():
             ms_grad = max_over_ranks(a.elapsed_time(b2) / 2)
             elbo["training_step"] = {"metric": "SGPR ELBO + gradient evals/sec", "value": 1e3 / ms_grad,
                                      "ms_per_eval": ms_grad, "grad_norm_lengthscales": float(np.abs(g_out[1]).max())}
+            # the same step with trainable inducing points (zfixed=False): adds d/dZ through Kuf and Kuu
+            model.inducing_variable.Z.trainable = True
+            sgpr_elbo_and_grad(model)
+            barrier()
+            a.record()
+            for _ in range(2):
+                sgpr_elbo_and_grad(model)
+            b2.record()
+            torch.cuda.synchronize()
+            ms_gz = max_over_ranks(a.elapsed_time(b2) / 2)
+            elbo["training_step"]["with_inducing_point_gradients"] = {
+                "ms_per_eval": ms_gz, "grad_norm_Z": float(np.abs(model._inducing_grad).max())}
         except Exception as exc:  # the headline must not depend on the widening row
             elbo["training_step"] = {"error": repr(exc)}
 

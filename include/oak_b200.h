@@ -245,6 +245,18 @@ int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, const void
                           int64_t row_begin, int64_t row_end, const void* d_points2,
                           const void* d_dpoints2, int64_t n2, const double* d_W, int64_t ldw,
                           double* d_grad, void* d_work, void* stream);
+/* The same contraction over ALL rows of d_points, plus the gradient with respect to the row points
+ * themselves -- the inducing points Z of SGPR when the reference leaves them trainable
+ * (zfixed=False, oak/model_utils.py:98-101; TensorFlow autodiff through OAKKernel.K(Z, X) and K(Z, Z)):
+ *   d_grad_rows[i * ldg + k] += sum_j W_ij * dK(x_i, y_j) / d x_{i,k}    (k = sub-kernel index, caller's order)
+ * for RBF sub-kernels under every measure; discrete sub-kernels receive nothing (tf.cast / tf.gather carry
+ * no gradient).  Only the FIRST argument of K is differentiated: for a symmetric objective over K(Z, Z)
+ * pass W + W^T.  ldg >= num_dims.  d_work: oak_gram_backward_rows_work_bytes(spec, n, n2). */
+size_t oak_gram_backward_rows_work_bytes(const oak_spec* spec, int64_t n, int64_t n2);
+int oak_gram_backward_rows_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints, int64_t n,
+                               const void* d_points2, const void* d_dpoints2, int64_t n2, const double* d_W,
+                               int64_t ldw, double* d_grad, double* d_grad_rows, int64_t ldg, void* d_work,
+                               void* stream);
 /* Same for wscale * sum_i w_i K_diag(x_i) (d_w == NULL => all ones). */
 int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints,
                                int64_t n, const double* d_w, double wscale, double* d_grad,

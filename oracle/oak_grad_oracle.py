@@ -155,8 +155,9 @@ def gpr_lml(X, Y, ls, variances, noise, measures=None):
     return -0.5 * (a ** 2).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * N * math.log(2 * math.pi)
 
 
-def value_and_grad(fn, X, Y, Z, ls, variances, noise, measures=None):
-    """Returns (value, d/d ls, d/d variances, d/d noise) as floats / numpy arrays."""
+def value_and_grad(fn, X, Y, Z, ls, variances, noise, measures=None, wrt_Z=False):
+    """Returns (value, d/d ls, d/d variances, d/d noise) as floats / numpy arrays; with ``wrt_Z`` also
+    d/d Z (the inducing points, gpflow's ``inducing_variable.Z`` when zfixed=False)."""
     t = lambda a: torch.as_tensor(a, dtype=torch.float64)
     lsT = t(ls).clone().requires_grad_(True)
     vT = t(variances).clone().requires_grad_(True)
@@ -164,6 +165,8 @@ def value_and_grad(fn, X, Y, Z, ls, variances, noise, measures=None):
     if Z is None:
         val = fn(t(X), t(Y), lsT, vT, nT, measures)
     else:
-        val = fn(t(X), t(Y), t(Z), lsT, vT, nT, measures)
+        ZT = t(Z).clone().requires_grad_(bool(wrt_Z))
+        val = fn(t(X), t(Y), ZT, lsT, vT, nT, measures)
     val.backward()
-    return float(val.detach()), lsT.grad.numpy(), vT.grad.numpy(), float(nT.grad)
+    out = (float(val.detach()), lsT.grad.numpy(), vT.grad.numpy(), float(nT.grad))
+    return out + (ZT.grad.numpy(),) if wrt_Z else out

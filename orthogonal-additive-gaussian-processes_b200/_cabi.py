@@ -81,6 +81,8 @@ SIGNATURES = {
     "oak_spec_table_layout": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "oak_backward_points_bytes": (_sz, [_vp, _i64]),
     "oak_prepare_backward_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "oak_gram_backward_rows_work_bytes": (_sz, [_vp, _i64, _i64]),
+    "oak_gram_backward_rows_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _dp, _i64, _vp, _vp]),
     "oak_gram_backward_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _vp, _vp]),
     "oak_gram_diag_backward_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dp, C.c_double, _dp, _vp, _vp]),
     "oak_sgpr_stats_count": (_sz, [_i64]),

@@ -260,6 +260,37 @@ def gram_backward(spec: Spec, px: Points, W, px2: Optional[Points] = None, row_b
     return grad
 
 
+def gram_backward_rows(spec: Spec, px: Points, W, px2: Optional[Points] = None, grad=None, grad_rows=None):
+    """``gram_backward`` over all rows of ``px`` plus ``grad_rows[i, k] += sum_j W_ij dK(x_i, y_j)/dx_{i,k}``
+    (k = sub-kernel index): the gradient with respect to the row points (inducing points)."""
+    torch = _torch()
+    lib = _cabi.load()
+    n = px.n
+    n2 = n if px2 is None else px2.n
+    nout = int(lib.oak_backward_grad_count(spec.handle))
+    if grad is None:
+        grad = torch.zeros(nout, dtype=torch.float64, device=px.buf.device)
+    if grad_rows is None:
+        grad_rows = torch.zeros((n, spec.num_dims), dtype=torch.float64, device=px.buf.device)
+    if grad.numel() != nout or not grad.is_contiguous():
+        raise ValueError(f"gradient buffer must hold oak_backward_grad_count = {nout} contiguous doubles")
+    if grad_rows.shape != (n, spec.num_dims) or grad_rows.stride(1) != 1 or grad_rows.dtype != torch.float64:
+        raise ValueError("row-gradient buffer must be (n, num_dims) float64 with unit column stride")
+    if n > 0 and n2 > 0:
+        assert W.shape == (n, n2) and W.stride(1) == 1
+        work = torch.empty(max(int(lib.oak_gram_backward_rows_work_bytes(spec.handle, n, n2)) // 8, 1),
+                           dtype=torch.float64, device=px.buf.device)
+        check(
+            lib.oak_gram_backward_rows_f64(spec.handle, _p(px.buf), _p(px.backward_block()), n,
+                                           _p(None if px2 is None else px2.buf),
+                                           _p(None if px2 is None else px2.backward_block()), n2, _p(W),
+                                           int(W.stride(0)), _p(grad), _p(grad_rows), int(grad_rows.stride(0)),
+                                           _p(work), C.c_void_p(stream_ptr())),
+            "oak_gram_backward_rows_f64",
+        )
+    return grad, grad_rows
+
+
 def table_layout(spec: Spec, dim: int):
     """(offset, C) of sub-kernel ``dim``'s table inside the table-blob part of the gradient vector."""
     off, cnt = C.c_int32(0), C.c_int32(0)

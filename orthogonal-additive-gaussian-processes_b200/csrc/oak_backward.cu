@@ -15,6 +15,13 @@
 // No per-dimension N x N2 derivative matrix is ever formed; W is read once per entry.
 // Reductions are deterministic: warp shuffles -> per-warp shared slots -> per-CTA partials ->
 // one fixed-order pass over the CTAs.
+//
+// Row-point gradients (the inducing points Z of SGPR when zfixed=False, model_utils.py:98-101):
+//   d k~_d(z, x)/dz = -ex (z - x)/l^2 - c^'(z) c^(x)
+// so per (row, dim) the tiles accumulate A = sum_j W dK/dk~ ex d' and B = sum_j W dK/dk~ c^(x_j)
+// (d' the prepared coordinate difference) over a contiguous segment of column tiles in shared
+// memory, write one partial per (segment, row, dim) and a finishing kernel forms
+//   dZ[m, d] = -A / (xscale l^2) - c^'(z_m) B      (c^' per measure, ortho_rbf_kernel.py:49-136).
 #include <cmath>
 
 #include "oak_common.cuh"
@@ -35,6 +42,7 @@ struct BwDim {      // per sub-kernel (kernel order)
   double inv_xscale;  // prepared coordinate -> x
   double c2;        // (2 / l) * ln2 / kExpTab : ex * d'^2 * c2 = ex * z * 2 / l
   double inv_s2;    // 1 / s^2 (base variance)
+  double zc;        // 1 / (xscale l^2): prepared-coordinate difference -> (z - x)/l^2
   double kind;      // 0: no lengthscale gradient (discrete dim / uniform / MOG measure)
                     // 1: closed form above (Gaussian measure, or no measure: c^ = 0)
                     // 2: d c^/dl read from the per-point array written by oak_prepare_backward_f64
@@ -55,6 +63,9 @@ struct BwParams {
   const unsigned long long* mm_col;
   const double* W;
   double* partial;  // [grid][D + P + 1 + tables_len]
+  double* zpartial;  // row-gradient variant: [segs][zrows][D][2] partial (A, B) sums
+  int64_t zrows;     // row blocks * tile rows
+  int segs;          // column segments per row block
   int64_t n_row_pad, n_col_pad, ldw;
   int64_t row_begin, row_end, n2;
   int64_t tiles_n, num_tiles;
@@ -70,7 +81,7 @@ __device__ __forceinline__ double entry_exp(double d, double ax, const unsigned 
   return exp_neg_scaled(fma(d, d, ax), tab_bytes, lane_bits);
 }
 
-template <int P, int RM, int RN>
+template <int P, int RM, int RN, bool ZG>
 __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const BwParams prm) {
   using namespace bw;
   constexpr int TM = kTYD * RM, TN = kTXD * RN;
@@ -88,6 +99,7 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
   const int D = prm.D, Dc = prm.Dc;
   const int nout = 2 * D + P + 1 + prm.tables_len;
   const int vbase = D + P + 1 + prm.tables_len;  // first base-variance slot
+  double* sZ = sG + 8 * nout;  // ZG: [TM][D][2] (A, B) sums of the current (row block, segment)
   for (int i = tid; i < kTabDoubles; i += kThreads) {
     const int j = i / kExpRepl;
     const double v = prm.exptab[j];
@@ -125,204 +137,165 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
   };
 
   const int64_t nrows = prm.row_end - prm.row_begin;
-  for (int64_t t = blockIdx.x; t < prm.num_tiles; t += gridDim.x) {
-    const int64_t bi = t / prm.tiles_n;
-    const int64_t row0 = bi * TM, col0 = (t - bi * prm.tiles_n) * TN;
-
-    double E[RM][RN][P];  // e_1..e_P (direct recurrence)
-#pragma unroll
-    for (int r = 0; r < RM; ++r)
-#pragma unroll
-      for (int c = 0; c < RN; ++c)
-#pragma unroll
-        for (int p = 0; p < P; ++p) E[r][c][p] = 0.0;
-
-    // ---- sweep 1: elementary symmetric polynomials ------------------------------------------
-    int buf = 0;
-    issue_stage(row0, col0, 0, 0);
-    for (int ch = 0; ch < num_chunks; ++ch) {
-      cp_async_wait_all();
+  // work units: one tile, or (ZG) one row block x one contiguous segment of column tiles
+  const int64_t units = ZG ? (prm.zrows / TM) * prm.segs : prm.num_tiles;
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    int64_t bi, ct0, ct1;
+    int seg = 0;
+    if constexpr (ZG) {
+      bi = u / prm.segs;
+      seg = (int)(u - bi * prm.segs);
+      ct0 = prm.tiles_n * seg / prm.segs;
+      ct1 = prm.tiles_n * (seg + 1) / prm.segs;
+      for (int i = tid; i < TM * D * 2; i += kThreads) sZ[i] = 0.0;
       __syncthreads();
-      if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
-      const double2* sRow = sStage + buf * kStageDouble2;
-      const double* aux = sAux + buf * kDimChunk;
-      const int d0 = ch * kDimChunk;
-      const int nd = min(kDimChunk, D - d0);
-#pragma unroll 1
-      for (int dl = 0; dl < nd; ++dl) {
-        const double2* rowp = sRow + dl * (TM + TN);
-        const double2* colp = rowp + TM;
-        double2 rv[RM], cv[RN];
-#pragma unroll
-        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
-#pragma unroll
-        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
-        const bool cont = d0 + dl < Dc;
-        const double ax = aux[dl];
-        auto fold = [&](int r, int c, double k) {
-#pragma unroll
-          for (int p = P - 1; p >= 1; --p) E[r][c][p] = fma(k, E[r][c][p - 1], E[r][c][p]);
-          E[r][c][0] += k;
-        };
-        if (cont && fast) {
-#pragma unroll
-          for (int r = 0; r < RM; ++r)
-#pragma unroll
-            for (int c = 0; c < RN; ++c)
-              fold(r, c, fma(-rv[r].y, cv[c].y, entry_exp<true>(rv[r].x - cv[c].x, ax, tab_bytes, lane_bits)));
-        } else if (cont) {
-#pragma unroll
-          for (int r = 0; r < RM; ++r)
-#pragma unroll
-            for (int c = 0; c < RN; ++c)
-              fold(r, c, fma(-rv[r].y, cv[c].y, entry_exp<false>(rv[r].x - cv[c].x, ax, tab_bytes, lane_bits)));
-        } else {
-          const double* tbl = prm.tables + (int)__double_as_longlong(ax);
-#pragma unroll
-          for (int r = 0; r < RM; ++r)
-#pragma unroll
-            for (int c = 0; c < RN; ++c)
-              fold(r, c, __ldg(tbl + __double2hiint(rv[r].x) + __double2loint(cv[c].x)));
-        }
-      }
-      buf ^= 1;
+    } else {
+      bi = u / prm.tiles_n;
+      ct0 = u - bi * prm.tiles_n;
+      ct1 = ct0 + 1;
     }
+    const int64_t row0 = bi * TM;
+    for (int64_t ct = ct0; ct < ct1; ++ct) {
+      const int64_t col0 = ct * TN;
 
-    // ---- cotangent tile + order-variance gradients --------------------------------------------
-    double wv[RM][RN];
-    double gs[P + 1];
+      double E[RM][RN][P];  // e_1..e_P (direct recurrence)
 #pragma unroll
-    for (int p = 0; p <= P; ++p) gs[p] = 0.0;
+      for (int r = 0; r < RM; ++r)
 #pragma unroll
-    for (int r = 0; r < RM; ++r)
+        for (int c = 0; c < RN; ++c)
 #pragma unroll
-      for (int c = 0; c < RN; ++c) {
-        const int64_t row = row0 + ty * RM + r, col = col0 + tx + kTXD * c;
-        wv[r][c] = (row < nrows && col < prm.n2) ? __ldcs(prm.W + row * prm.ldw + col) : 0.0;
-        gs[0] += wv[r][c];
-#pragma unroll
-        for (int p = 1; p <= P; ++p) gs[p] = fma(wv[r][c], E[r][c][p - 1], gs[p]);
-      }
-#pragma unroll
-    for (int p = 0; p <= P; ++p) {
-      double v = gs[p];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) myG[D + p] += v;
-    }
+          for (int p = 0; p < P; ++p) E[r][c][p] = 0.0;
 
-    // ---- sweep 2: lengthscale gradients ---------------------------------------------------------
-    __syncthreads();  // everybody has left sweep 1's last buffer before it is overwritten
-    buf = 0;
-    issue_stage(row0, col0, 0, 0);
-    for (int ch = 0; ch < num_chunks; ++ch) {
-      cp_async_wait_all();
-      __syncthreads();
-      if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
-      const double2* sRow = sStage + buf * kStageDouble2;
-      const double* aux = sAux + buf * kDimChunk;
-      const int d0 = ch * kDimChunk;
-      const int nc = max(0, min(min(kDimChunk, D - d0), Dc - d0));  // continuous dims of this chunk
+      // ---- sweep 1: elementary symmetric polynomials ------------------------------------------
+      int buf = 0;
+      issue_stage(row0, col0, 0, 0);
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
+        const double2* sRow = sStage + buf * kStageDouble2;
+        const double* aux = sAux + buf * kDimChunk;
+        const int d0 = ch * kDimChunk;
+        const int nd = min(kDimChunk, D - d0);
 #pragma unroll 1
-      for (int dl = 0; dl < nc; ++dl) {
-        const BwDim bd = prm.bwdims[d0 + dl];
-        const double2* rowp = sRow + dl * (TM + TN);
-        const double2* colp = rowp + TM;
-        double2 rv[RM], cv[RN];
-        double dr[RM], dc[RN];  // d c^/dl of the row / column points
+        for (int dl = 0; dl < nd; ++dl) {
+          const double2* rowp = sRow + dl * (TM + TN);
+          const double2* colp = rowp + TM;
+          double2 rv[RM], cv[RN];
 #pragma unroll
-        for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
+          for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
 #pragma unroll
-        for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
-        if (bd.kind == 0.0) {  // no lengthscale gradient (uniform / MOG measure): base variance only
+          for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
+          const bool cont = d0 + dl < Dc;
+          const double ax = aux[dl];
+          auto fold = [&](int r, int c, double k) {
 #pragma unroll
-          for (int r = 0; r < RM; ++r) dr[r] = 0.0;
+            for (int p = P - 1; p >= 1; --p) E[r][c][p] = fma(k, E[r][c][p - 1], E[r][c][p]);
+            E[r][c][0] += k;
+          };
+          if (cont && fast) {
 #pragma unroll
-          for (int c = 0; c < RN; ++c) dc[c] = 0.0;
-        } else if (bd.kind == 1.0) {
+            for (int r = 0; r < RM; ++r)
 #pragma unroll
-          for (int r = 0; r < RM; ++r) {
-            const double xm = fma(rv[r].x, bd.inv_xscale, -bd.mu);
-            dr[r] = rv[r].y * fma(xm * xm, bd.uc, bd.half_kappa);
+              for (int c = 0; c < RN; ++c)
+                fold(r, c, fma(-rv[r].y, cv[c].y, entry_exp<true>(rv[r].x - cv[c].x, ax, tab_bytes, lane_bits)));
+          } else if (cont) {
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+              for (int c = 0; c < RN; ++c)
+                fold(r, c, fma(-rv[r].y, cv[c].y, entry_exp<false>(rv[r].x - cv[c].x, ax, tab_bytes, lane_bits)));
+          } else {
+            const double* tbl = prm.tables + (int)__double_as_longlong(ax);
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+              for (int c = 0; c < RN; ++c)
+                fold(r, c, __ldg(tbl + __double2hiint(rv[r].x) + __double2loint(cv[c].x)));
           }
-#pragma unroll
-          for (int c = 0; c < RN; ++c) {
-            const double xm = fma(cv[c].x, bd.inv_xscale, -bd.mu);
-            dc[c] = cv[c].y * fma(xm * xm, bd.uc, bd.half_kappa);
-          }
-        } else {
-          const double* gr = prm.dch_row + (int64_t)(d0 + dl) * prm.n_row_pad + prm.row_begin + row0 + ty * RM;
-          const double* gc = prm.dch_col + (int64_t)(d0 + dl) * prm.n_col_pad + col0 + tx;
-#pragma unroll
-          for (int r = 0; r < RM; ++r) dr[r] = __ldg(gr + r);
-#pragma unroll
-          for (int c = 0; c < RN; ++c) dc[c] = __ldg(gc + kTXD * c);
         }
-        const double ax = aux[dl];
-        double acc = 0.0, accv = 0.0;
-        auto entry = [&](int r, int c, double d, double ex) {
-          const double cc = rv[r].y * cv[c].y;
-          const double k = ex - cc;
-          // removal recurrence: g_m = e_m - k g_{m-1}; dK/dk = sum_n sigma2_n g_{n-1}
-          double g = 1.0;
-          double dKdk = prm.sigma2[1];
+        buf ^= 1;
+      }
+
+      // ---- cotangent tile + order-variance gradients --------------------------------------------
+      double wv[RM][RN];
+      double gs[P + 1];
 #pragma unroll
-          for (int m = 1; m < P; ++m) {
-            g = fma(-k, g, E[r][c][m - 1]);
-            dKdk = fma(prm.sigma2[m + 1], g, dKdk);
-          }
-          const double dkdl = fma(ex * (d * d), bd.c2, -fma(dr[r], cv[c].y, rv[r].y * dc[c]));
-          const double wk = wv[r][c] * dKdk;
-          acc = fma(wk, dkdl, acc);
-          accv = fma(wk, k, accv);  // k~ is homogeneous of degree one in s^2: d k~ / d s^2 = k~ / s^2
-        };
-        if (fast) {
+      for (int p = 0; p <= P; ++p) gs[p] = 0.0;
 #pragma unroll
-          for (int r = 0; r < RM; ++r)
+      for (int r = 0; r < RM; ++r)
+#pragma unroll
+        for (int c = 0; c < RN; ++c) {
+          const int64_t row = row0 + ty * RM + r, col = col0 + tx + kTXD * c;
+          wv[r][c] = (row < nrows && col < prm.n2) ? __ldcs(prm.W + row * prm.ldw + col) : 0.0;
+          gs[0] += wv[r][c];
+#pragma unroll
+          for (int p = 1; p <= P; ++p) gs[p] = fma(wv[r][c], E[r][c][p - 1], gs[p]);
+        }
+#pragma unroll
+      for (int p = 0; p <= P; ++p) {
+        double v = gs[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) myG[D + p] += v;
+      }
+
+      // ---- sweep 2: lengthscale gradients ---------------------------------------------------------
+      __syncthreads();  // everybody has left sweep 1's last buffer before it is overwritten
+      buf = 0;
+      issue_stage(row0, col0, 0, 0);
+      for (int ch = 0; ch < num_chunks; ++ch) {
+        cp_async_wait_all();
+        __syncthreads();
+        if (ch + 1 < num_chunks) issue_stage(row0, col0, ch + 1, buf ^ 1);
+        const double2* sRow = sStage + buf * kStageDouble2;
+        const double* aux = sAux + buf * kDimChunk;
+        const int d0 = ch * kDimChunk;
+        const int nc = max(0, min(min(kDimChunk, D - d0), Dc - d0));  // continuous dims of this chunk
+#pragma unroll 1
+        for (int dl = 0; dl < nc; ++dl) {
+          const BwDim bd = prm.bwdims[d0 + dl];
+          const double2* rowp = sRow + dl * (TM + TN);
+          const double2* colp = rowp + TM;
+          double2 rv[RM], cv[RN];
+          double dr[RM], dc[RN];  // d c^/dl of the row / column points
+#pragma unroll
+          for (int r = 0; r < RM; ++r) rv[r] = rowp[ty * RM + r];
+#pragma unroll
+          for (int c = 0; c < RN; ++c) cv[c] = colp[tx + kTXD * c];
+          if (bd.kind == 0.0) {  // no lengthscale gradient (uniform / MOG measure): base variance only
+#pragma unroll
+            for (int r = 0; r < RM; ++r) dr[r] = 0.0;
+#pragma unroll
+            for (int c = 0; c < RN; ++c) dc[c] = 0.0;
+          } else if (bd.kind == 1.0) {
+#pragma unroll
+            for (int r = 0; r < RM; ++r) {
+              const double xm = fma(rv[r].x, bd.inv_xscale, -bd.mu);
+              dr[r] = rv[r].y * fma(xm * xm, bd.uc, bd.half_kappa);
+            }
 #pragma unroll
             for (int c = 0; c < RN; ++c) {
-              const double d = rv[r].x - cv[c].x;
-              entry(r, c, d, entry_exp<true>(d, ax, tab_bytes, lane_bits));
+              const double xm = fma(cv[c].x, bd.inv_xscale, -bd.mu);
+              dc[c] = cv[c].y * fma(xm * xm, bd.uc, bd.half_kappa);
             }
-        } else {
+          } else {
+            const double* gr = prm.dch_row + (int64_t)(d0 + dl) * prm.n_row_pad + prm.row_begin + row0 + ty * RM;
+            const double* gc = prm.dch_col + (int64_t)(d0 + dl) * prm.n_col_pad + col0 + tx;
 #pragma unroll
-          for (int r = 0; r < RM; ++r)
+            for (int r = 0; r < RM; ++r) dr[r] = __ldg(gr + r);
 #pragma unroll
-            for (int c = 0; c < RN; ++c) {
-              const double d = rv[r].x - cv[c].x;
-              entry(r, c, d, entry_exp<false>(d, ax, tab_bytes, lane_bits));
-            }
-        }
+            for (int c = 0; c < RN; ++c) dc[c] = __ldg(gc + kTXD * c);
+          }
+          const double ax = aux[dl];
+          double acc = 0.0, accv = 0.0;
+          double za[RM], zb[RM];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          acc += __shfl_xor_sync(0xffffffffu, acc, o);
-          accv += __shfl_xor_sync(0xffffffffu, accv, o);
-        }
-        if (lane == 0) {
-          if (bd.kind != 0.0) myG[d0 + dl] += acc;
-          myG[vbase + d0 + dl] += accv * bd.inv_s2;
-        }
-      }
-      // discrete dims: cotangent of the table blob (the host chains it to W / kappa / variance)
-      const int nd2 = min(kDimChunk, D - d0);
-#pragma unroll 1
-      for (int dl = nc; dl < nd2; ++dl) {
-        const double2* rowp = sRow + dl * (TM + TN);
-        const double2* colp = rowp + TM;
-        const int toff = (int)__double_as_longlong(aux[dl]);
-        const double* tbl = prm.tables + toff;
-        double* gt = myG + D + P + 1 + toff;
-        int ro[RM], co[RN];
-#pragma unroll
-        for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty * RM + r].x);
-#pragma unroll
-        for (int c = 0; c < RN; ++c) co[c] = __double2loint(colp[tx + kTXD * c].x);
-#pragma unroll
-        for (int r = 0; r < RM; ++r)
-#pragma unroll
-          for (int c = 0; c < RN; ++c) {
-            if (wv[r][c] == 0.0) continue;  // out-of-range entries carry zero cotangent
-            const double k = __ldg(tbl + ro[r] + co[c]);
+          for (int r = 0; r < RM; ++r) za[r] = zb[r] = 0.0;
+          auto entry = [&](int r, int c, double d, double ex) {
+            const double cc = rv[r].y * cv[c].y;
+            const double k = ex - cc;
+            // removal recurrence: g_m = e_m - k g_{m-1}; dK/dk = sum_n sigma2_n g_{n-1}
             double g = 1.0;
             double dKdk = prm.sigma2[1];
 #pragma unroll
@@ -330,12 +303,97 @@ __global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const Bw
               g = fma(-k, g, E[r][c][m - 1]);
               dKdk = fma(prm.sigma2[m + 1], g, dKdk);
             }
-            atomicAdd(gt + ro[r] + co[c], wv[r][c] * dKdk);  // per-warp slots: intra-warp order only
+            const double dkdl = fma(ex * (d * d), bd.c2, -fma(dr[r], cv[c].y, rv[r].y * dc[c]));
+            const double wk = wv[r][c] * dKdk;
+            acc = fma(wk, dkdl, acc);
+            accv = fma(wk, k, accv);  // k~ is homogeneous of degree one in s^2: d k~ / d s^2 = k~ / s^2
+            if constexpr (ZG) {
+              za[r] = fma(wk * ex, d, za[r]);
+              zb[r] = fma(wk, cv[c].y, zb[r]);
+            }
+          };
+          if (fast) {
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+              for (int c = 0; c < RN; ++c) {
+                const double d = rv[r].x - cv[c].x;
+                entry(r, c, d, entry_exp<true>(d, ax, tab_bytes, lane_bits));
+              }
+          } else {
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+#pragma unroll
+              for (int c = 0; c < RN; ++c) {
+                const double d = rv[r].x - cv[c].x;
+                entry(r, c, d, entry_exp<false>(d, ax, tab_bytes, lane_bits));
+              }
           }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            accv += __shfl_xor_sync(0xffffffffu, accv, o);
+          }
+          if (lane == 0) {
+            if (bd.kind != 0.0) myG[d0 + dl] += acc;
+            myG[vbase + d0 + dl] += accv * bd.inv_s2;
+          }
+          if constexpr (ZG) {  // the 16 threads of a half warp share their rows
+#pragma unroll
+            for (int r = 0; r < RM; ++r) {
+              double a = za[r], b = zb[r];
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1) {
+                a += __shfl_xor_sync(0xffffffffu, a, o);
+                b += __shfl_xor_sync(0xffffffffu, b, o);
+              }
+              if (tx == 0) {
+                double* z = sZ + ((ty * RM + r) * D + d0 + dl) * 2;
+                z[0] += a;
+                z[1] += b;
+              }
+            }
+          }
+        }
+        // discrete dims: cotangent of the table blob (the host chains it to W / kappa / variance)
+        const int nd2 = min(kDimChunk, D - d0);
+#pragma unroll 1
+        for (int dl = nc; dl < nd2; ++dl) {
+          const double2* rowp = sRow + dl * (TM + TN);
+          const double2* colp = rowp + TM;
+          const int toff = (int)__double_as_longlong(aux[dl]);
+          const double* tbl = prm.tables + toff;
+          double* gt = myG + D + P + 1 + toff;
+          int ro[RM], co[RN];
+#pragma unroll
+          for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty * RM + r].x);
+#pragma unroll
+          for (int c = 0; c < RN; ++c) co[c] = __double2loint(colp[tx + kTXD * c].x);
+#pragma unroll
+          for (int r = 0; r < RM; ++r)
+#pragma unroll
+            for (int c = 0; c < RN; ++c) {
+              if (wv[r][c] == 0.0) continue;  // out-of-range entries carry zero cotangent
+              const double k = __ldg(tbl + ro[r] + co[c]);
+              double g = 1.0;
+              double dKdk = prm.sigma2[1];
+#pragma unroll
+              for (int m = 1; m < P; ++m) {
+                g = fma(-k, g, E[r][c][m - 1]);
+                dKdk = fma(prm.sigma2[m + 1], g, dKdk);
+              }
+              atomicAdd(gt + ro[r] + co[c], wv[r][c] * dKdk);  // per-warp slots: intra-warp order only
+            }
+        }
+        buf ^= 1;
       }
-      buf ^= 1;
+      __syncthreads();  // stage buffers are re-issued by the next tile
     }
-    __syncthreads();  // stage buffers are re-issued by the next tile
+    if constexpr (ZG) {
+      double* dst = prm.zpartial + ((int64_t)seg * prm.zrows + row0) * (2 * D);
+      for (int i = tid; i < TM * D * 2; i += kThreads) dst[i] = sZ[i];
+      __syncthreads();
+    }
   }
 
   // ---- per-CTA partials (fixed order over the warps) ---------------------------------------------
@@ -551,9 +609,77 @@ __global__ void __launch_bounds__(256) measure_dch_kernel(DimDev d, const double
   out_k[i] = dc * isv - p.y * half_dlogv;
 }
 
+// ---- row-point gradients: finishing pass ---------------------------------------------------------
+// One warp per (row m, continuous dim k): fixed-order sum of the segment partials, c^'(z_m) of the
+// dim's measure (lanes stride the locations / components), dZ[m, orig] += -A zc - c^' B.
+//   Gaussian:  c = c0 exp(-(x-mu)^2 c2)                      c' = -2 (x-mu) c2 c
+//   uniform:   c = c0 [erf(tb) - erf(ta)]                    c' = -c0 (2/sqrt(pi)) [exp(-tb^2) - exp(-ta^2)] / (sqrt(2) l)
+//   MOG:       c = c0 sum_q w_q g_q                          c' = -c0 sum_q w_q g_q (x-m_q)/S_q
+//   empirical: c = c0 sum_q w_q exp(-t_q^2)                  c' = -c0 sum_q w_q exp(-t_q^2) 2 t_q / (sqrt(2) l)
+// with c^ = c / sqrt(var_s) (oak_prepare.cu).
+__global__ void __launch_bounds__(256) rows_finish_kernel(const double* __restrict__ zpartial, int segs, int64_t zrows,
+                                                          int64_t n, int D, int Dc, const DimDev* __restrict__ dims,
+                                                          const BwDim* __restrict__ bwdims,
+                                                          const double2* __restrict__ pts, int64_t n_pad,
+                                                          const double* __restrict__ inv_sqrt_v,
+                                                          double* __restrict__ grad_rows, int64_t ldg) {
+  const int64_t gw = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= n * Dc) return;  // whole warps leave together
+  const int64_t m = gw / Dc;
+  const int k = (int)(gw - m * Dc);
+  double A = 0.0, B = 0.0;
+  for (int s = lane; s < segs; s += 32) {
+    const double* z = zpartial + (((int64_t)s * zrows + m) * D + k) * 2;
+    A += z[0];
+    B += z[1];
+  }
+  const DimDev d = dims[k];
+  const double2 p = pts[(int64_t)k * n_pad + m];
+  const double x = p.x / d.xscale;
+  double dc = 0.0;  // per-lane share of c'(x)
+  switch (d.measure) {
+    case OAK_MEASURE_GAUSSIAN:
+      if (lane == 0) dc = -2.0 * (x - d.c1) * d.c2 * (p.y / inv_sqrt_v[k]);
+      break;
+    case OAK_MEASURE_UNIFORM:
+      if (lane == 0) {
+        const double ta = (d.c1 - x) * d.inv_sqrt2_l, tb = (d.c2 - x) * d.inv_sqrt2_l;
+        dc = -d.c0 * 1.1283791670955126 * (exp(-tb * tb) - exp(-ta * ta)) * d.inv_sqrt2_l;
+      }
+      break;
+    case OAK_MEASURE_MOG: {
+      const double l2 = d.lengthscale * d.lengthscale;
+      for (int q = lane; q < d.count; q += 32) {
+        const double sc = l2 + d.v1[q];
+        const double t = x - d.v0[q];
+        dc -= exp(-0.5 * (t * t) / sc) / sqrt(sc) * d.v2[q] * (t / sc);
+      }
+      dc *= d.c0;
+      break;
+    }
+    case OAK_MEASURE_EMPIRICAL:
+      for (int q = lane; q < d.count; q += 32) {
+        const double t = (x - d.v0[q]) * d.inv_sqrt2_l;
+        dc = fma(-2.0 * t * d.v1[q], exp(-t * t), dc);
+      }
+      dc *= d.c0 * d.inv_sqrt2_l;
+      break;
+    default:
+      break;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    A += __shfl_xor_sync(0xffffffffu, A, o);
+    B += __shfl_xor_sync(0xffffffffu, B, o);
+    dc += __shfl_xor_sync(0xffffffffu, dc, o);
+  }
+  if (lane == 0) grad_rows[m * ldg + d.orig] += -A * bwdims[k].zc - dc * inv_sqrt_v[k] * B;
+}
+
 // ---- host side ------------------------------------------------------------------------------
 static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vector<int>& orig_of_pos) {
-  out.assign(spec->D, BwDim{0, 0, 0, 0, 0, 0, 0});
+  out.assign(spec->D, BwDim{0, 0, 0, 0, 0, 0, 0, 0});
   orig_of_pos.assign(spec->D, 0);
   for (int k = 0; k < spec->D; ++k) {
     const DimDev& dd = spec->h_dims[k];
@@ -564,6 +690,7 @@ static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vect
     b.inv_xscale = 1.0 / dd.xscale;
     b.c2 = (2.0 / l) * kInvXScale2;
     b.inv_s2 = 1.0 / dd.s2;
+    b.zc = 1.0 / (dd.xscale * l * l);
     b.mu = 0.0;
     b.half_kappa = 0.0;
     b.uc = 0.0;
@@ -585,22 +712,52 @@ static int build_bwdims(const oak_spec* spec, std::vector<BwDim>& out, std::vect
   return 0;
 }
 
-template <int P, int RM, int RN>
-static int launch_backward(BwParams prm, int grid_max, cudaStream_t stream, int* grid_out) {
+// tile shape of the backward kernel for a depth (the launch table of oak_gram_backward_f64)
+static void bw_tile_shape(int depth, int* tm, int* tn) {
+  *tm = depth <= 3 ? 64 : 32;
+  *tn = depth <= 4 ? 64 : 32;
+}
+
+// column segments per row block of the row-gradient variant: about four work units per SM
+static int bw_row_segments(int64_t rows, int64_t n2, int depth, int sms) {
+  int tm, tn;
+  bw_tile_shape(depth, &tm, &tn);
+  const int64_t row_blocks = (rows + tm - 1) / tm, tiles_n = (n2 + tn - 1) / tn;
+  int64_t segs = (4 * (int64_t)sms + row_blocks - 1) / row_blocks;
+  if (segs > tiles_n) segs = tiles_n;
+  return (int)(segs < 1 ? 1 : segs);
+}
+
+template <int P, int RM, int RN, bool ZG>
+static int launch_backward_as(BwParams prm, int grid_max, cudaStream_t stream, int* grid_out) {
   using namespace bw;
   constexpr int TM = kTYD * RM, TN = kTXD * RN;
   const int64_t rows = prm.row_end - prm.row_begin;
   prm.tiles_n = (prm.n2 + TN - 1) / TN;
-  prm.num_tiles = ((rows + TM - 1) / TM) * prm.tiles_n;
-  const size_t smem = sizeof(double) * kExpTab * kExpRepl + 2 * sizeof(double2) * kDimChunk * (TM + TN) +
-                      2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (2 * prm.D + P + 1 + prm.tables_len);
-  auto kern = gram_backward_kernel<P, RM, RN>;
+  const int64_t row_blocks = (rows + TM - 1) / TM;
+  prm.num_tiles = row_blocks * prm.tiles_n;
+  size_t smem = sizeof(double) * kExpTab * kExpRepl + 2 * sizeof(double2) * kDimChunk * (TM + TN) +
+                2 * sizeof(double) * kDimChunk + 8 * sizeof(double) * (2 * prm.D + P + 1 + prm.tables_len);
+  int64_t units = prm.num_tiles;
+  if (ZG) {
+    smem += sizeof(double) * TM * prm.D * 2;
+    prm.zrows = row_blocks * TM;
+    units = row_blocks * prm.segs;
+  }
+  OAK_REQUIRE(smem <= 227 * 1024, "backward tiles: too many dimensions / table entries for one CTA's shared memory");
+  auto kern = gram_backward_kernel<P, RM, RN, ZG>;
   OAK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (int)(prm.num_tiles < grid_max ? prm.num_tiles : grid_max);
+  const int grid = (int)(units < grid_max ? units : grid_max);
   *grid_out = grid;
   kern<<<grid, kThreads, smem, stream>>>(prm);
   OAK_LAUNCHED();
   return 0;
+}
+
+template <int P, int RM, int RN>
+static int launch_backward(const BwParams& prm, int grid_max, cudaStream_t stream, int* grid_out) {
+  return prm.zpartial ? launch_backward_as<P, RM, RN, true>(prm, grid_max, stream, grid_out)
+                      : launch_backward_as<P, RM, RN, false>(prm, grid_max, stream, grid_out);
 }
 
 }  // namespace oak
@@ -724,10 +881,10 @@ extern "C" int oak_prepare_backward_f64(const oak_spec* spec, const void* d_poin
 // (points2 == NULL: the same point set), cotangent W (rows x n2, pitch ldw).  d_dpoints /
 // d_dpoints2: the blocks written by oak_prepare_backward_f64 (needed when the kernel has
 // empirical-measure dims; may be NULL otherwise).
-extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints, int64_t n,
-                                     int64_t row_begin, int64_t row_end, const void* d_points2,
-                                     const void* d_dpoints2, int64_t n2, const double* d_W, int64_t ldw,
-                                     double* d_grad, void* d_work, void* stream_) {
+static int gram_backward_impl(const oak_spec* spec, const void* d_points, const void* d_dpoints, int64_t n,
+                              int64_t row_begin, int64_t row_end, const void* d_points2, const void* d_dpoints2,
+                              int64_t n2, const double* d_W, int64_t ldw, double* d_grad, double* d_grad_rows,
+                              int64_t ldg, void* d_work, void* stream_) {
   OAK_REQUIRE(spec && d_points && d_grad && d_work, "oak_gram_backward_f64: null argument");
   const bool same = d_points2 == nullptr;
   if (same) n2 = n;
@@ -775,6 +932,14 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   prm.tables_len = spec->tables_len;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, spec->device);
+  prm.zpartial = nullptr;
+  prm.zrows = 0;
+  prm.segs = 0;
+  if (d_grad_rows) {  // (A, B) partials behind the per-CTA parameter partials
+    const size_t nout_ = 2 * (size_t)spec->D + depth + 1 + spec->tables_len;
+    prm.zpartial = d_partial + ((size_t)sms * nout_ + 7) / 8 * 8;
+    prm.segs = bw_row_segments(row_end - row_begin, n2, depth, sms);
+  }
   int grid = 0, rc = 0;
   switch (depth) {
     case 1: rc = launch_backward<1, 4, 4>(prm, sms, stream, &grid); break;
@@ -790,7 +955,52 @@ extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points,
   const int nout = 2 * spec->D + depth + 1 + spec->tables_len;
   backward_reduce_kernel<<<(nout + 127) / 128, 128, 0, stream>>>(d_partial, grid, nout, spec->D, d_map, d_grad);
   OAK_LAUNCHED();
+  if (d_grad_rows && spec->Dc > 0) {
+    int tm, tn;
+    bw_tile_shape(depth, &tm, &tn);
+    const int64_t rows = row_end - row_begin;
+    const int64_t zrows = (rows + tm - 1) / tm * tm;
+    const int64_t warps = rows * spec->Dc;
+    rows_finish_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        prm.zpartial, prm.segs, zrows, rows, spec->D, spec->Dc, spec->d_dims, d_bw, prm.pts_row, prm.n_row_pad,
+        spec->d_inv_sqrt_v, d_grad_rows, ldg);
+    OAK_LAUNCHED();
+  }
   return 0;
+}
+
+extern "C" int oak_gram_backward_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints, int64_t n,
+                                     int64_t row_begin, int64_t row_end, const void* d_points2,
+                                     const void* d_dpoints2, int64_t n2, const double* d_W, int64_t ldw,
+                                     double* d_grad, void* d_work, void* stream_) {
+  return gram_backward_impl(spec, d_points, d_dpoints, n, row_begin, row_end, d_points2, d_dpoints2, n2, d_W, ldw,
+                            d_grad, nullptr, 0, d_work, stream_);
+}
+
+// Same contraction over all rows of `points`, and additionally the gradient with respect to the row
+// points themselves (the inducing points Z of SGPR with zfixed=False, model_utils.py:98-101):
+//   grad_rows[i * ldg + k] += sum_j W_ij dK(x_i, y_j)/d x_{i,k}     (k = sub-kernel index, caller's order;
+// discrete sub-kernels receive nothing: tf.cast / tf.gather carry no gradient).  Only the FIRST argument
+// of K is differentiated: for a symmetric objective over K(Z, Z) pass W + W^T.
+extern "C" size_t oak_gram_backward_rows_work_bytes(const oak_spec* spec, int64_t n, int64_t n2) {
+  if (!spec || n < 0 || n2 < 0) return 0;
+  const int depth = spec->depth < 1 ? 1 : spec->depth;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, spec->device);
+  int tm, tn;
+  bw_tile_shape(depth, &tm, &tn);
+  const size_t zrows = (size_t)((n + tm - 1) / tm * tm);
+  const size_t segs = (size_t)bw_row_segments(n, n2 > 0 ? n2 : n, depth, sms);
+  return oak_gram_backward_work_bytes(spec, n > n2 ? n : n2) + 64 + segs * zrows * 2 * (size_t)spec->D * sizeof(double);
+}
+
+extern "C" int oak_gram_backward_rows_f64(const oak_spec* spec, const void* d_points, const void* d_dpoints,
+                                          int64_t n, const void* d_points2, const void* d_dpoints2, int64_t n2,
+                                          const double* d_W, int64_t ldw, double* d_grad, double* d_grad_rows,
+                                          int64_t ldg, void* d_work, void* stream_) {
+  OAK_REQUIRE(d_grad_rows && spec && ldg >= spec->D, "oak_gram_backward_rows_f64: bad row-gradient buffer");
+  return gram_backward_impl(spec, d_points, d_dpoints, n, 0, n, d_points2, d_dpoints2, n2, d_W, ldw, d_grad,
+                            d_grad_rows, ldg, d_work, stream_);
 }
 
 // grad += d/d theta of  wscale * sum_i w_i K_diag(x_i)   (w == NULL: all ones)

@@ -12,7 +12,9 @@ Supported trainable parameters: RBF lengthscales under every measure (Gaussian -
 after the normalising flow --, empirical, uniform, mixture of Gaussians, or none), the order variances sigma^2_0..P
 (``share_var_across_orders=True``), the likelihood variance, the base variances s^2 of the RBF sub-kernels
 where the reference keeps them trainable, and W / kappa of the categorical sub-kernels (through the
-cotangent of their B tables).  Any other *trainable* parameter
+cotangent of their B tables), and the inducing points Z of SGPR when ``zfixed=False``
+(``oak_gram_backward_rows_f64``; the columns of discrete sub-kernels carry no gradient, as under
+``tf.cast`` / ``tf.gather``).  Any other *trainable* parameter
 raises ``NotImplementedError`` (set it non-trainable to keep it fixed).
 
 SGPR (gpflow 2.2.1 ``SGPR.elbo``), with Phi = Kuf Kuf^T, b = Kuf y, s = sum K_diag,
@@ -96,16 +98,22 @@ def _discrete_parameters(model) -> List[Parameter]:
     return out
 
 
+def _inducing_parameter(model):
+    iv = getattr(model, "inducing_variable", None)
+    return getattr(iv, "Z", None)
+
+
 def _all_supported_ids(model):
     ls, var, noise = _supported_parameters(model)
     bvar = [_base_variance_parameter(k) for k in model.kernel.kernels]
+    z = _inducing_parameter(model)
     return ({id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
-            | {id(p) for p in _discrete_parameters(model)} | {id(p) for p in bvar if p is not None})
+            | {id(p) for p in _discrete_parameters(model)} | {id(p) for p in bvar if p is not None}
+            | ({id(z)} if z is not None else set()))
 
 
 def freeze_unsupported(model) -> List[Parameter]:
-    """Sets ``trainable=False`` on every parameter the backward tiles cannot differentiate
-    (inducing points, base-kernel variances, categorical W / kappa, ...); returns them."""
+    """Sets ``trainable=False`` on every parameter the backward tiles cannot differentiate; returns them."""
     ok = _all_supported_ids(model)
     frozen = []
     for p in collect_parameters(model):
@@ -121,8 +129,8 @@ def _check_trainables(model, spec_dims):
     for p in collect_parameters(model):
         if p.trainable and id(p) not in ok:
             raise NotImplementedError(
-                "gradient of a trainable parameter outside (RBF lengthscales, order variances, likelihood variance, "
-                f"categorical W / kappa) is not implemented ({p!r}); set it non-trainable (freeze_unsupported)")
+                "gradient of a trainable parameter outside (RBF lengthscales, order / base variances, likelihood "
+                f"variance, categorical W / kappa, inducing points) is not implemented ({p!r}); set it non-trainable (freeze_unsupported)")
     if not getattr(model.kernel, "share_var_across_orders", True):
         raise NotImplementedError("backward tiles need share_var_across_orders=True")
     for p, d in zip(ls, spec_dims):
@@ -148,7 +156,9 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         m, n_local = pz.n, px.n
         # Kuf is kept for the backward pass when it fits comfortably (8.2 GB at N = 10^6, M = 1024);
         # otherwise its chunks are recomputed in the second pass
-        keep = 8.0 * m * n_local < 48e9
+        keep = getattr(model, "keep_kuf", None)
+        if keep is None:
+            keep = 8.0 * m * n_local < 48e9
         if keep:
             # the 8 GB buffer is kept on the model between evaluations (an optimiser calls this in a loop)
             stats, kuf_blocks, chunk_eff, model._kuf_store = _device.sgpr_stats(
@@ -196,16 +206,28 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         nout = int(_cabi.load().oak_backward_grad_count(spec.handle))  # lengthscales | variances | table blob
         grad = torch.zeros(nout, dtype=torch.float64, device=Kuu.device)
         G2 = (2.0 * G_phi).contiguous()
-        if keep:
-            # W = 2 G_phi Kuf + g_b y^T per kept chunk (M x nc), rows = inducing points
-            for c, Kc in enumerate(kuf_blocks):
-                c0 = c * chunk_eff
-                c1 = c0 + Kc.shape[1]
-                Wc = torch.addmm(g_b @ Yd[c0:c1].reshape(1, -1), G2, Kc)
-                pxc = _device.Points(spec, Xs[c0:c1])
+        zpar = _inducing_parameter(model)
+        z_train = zpar is not None and zpar.trainable
+        gZ = torch.zeros((m, spec.num_dims), dtype=torch.float64, device=Kuu.device) if z_train else None
+
+        def rows_chunk(Kc, c0, c1):
+            # W = 2 G_phi Kuf + g_b y^T for one chunk (M x nc), rows = inducing points
+            Wc = torch.addmm(g_b @ Yd[c0:c1].reshape(1, -1), G2, Kc)
+            pxc = _device.Points(spec, Xs[c0:c1])
+            if z_train:
+                _device.gram_backward_rows(spec, pz, Wc, px2=pxc, grad=grad, grad_rows=gZ)
+            else:
                 _device.gram_backward(spec, pz, Wc, px2=pxc, grad=grad)
-                del Wc, pxc
+
+        if keep:
+            for c, Kc in enumerate(kuf_blocks):
+                rows_chunk(Kc, c * chunk_eff, c * chunk_eff + Kc.shape[1])
             del kuf_blocks
+        elif z_train:
+            chunk = max(64, (int(model.chunk) + 63) // 64 * 64)
+            for c0 in range(0, n_local, chunk):
+                c1 = min(c0 + chunk, n_local)
+                rows_chunk(_device.gram(spec, pz, _device.Points(spec, Xs[c0:c1])), c0, c1)
         else:
             chunk = max(64, (int(model.chunk) + 63) // 64 * 64)
             for c0 in range(0, n_local, chunk):
@@ -217,7 +239,23 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         _device.gram_diag_backward(spec, px, wscale=g_s, grad=grad)
         if model.distributed:
             parallel.allreduce_sum_(grad)
-        _device.gram_backward(spec, pz, G_Q.contiguous(), grad=grad)  # Kuu term (replicated, added once)
+            if z_train:
+                parallel.allreduce_sum_(gZ)
+        # Kuu term (replicated, added once)
+        if z_train:
+            # rows only differentiate the first argument of K(Z, Z): cotangent G_Q + G_Q^T, and half of the
+            # parameter gradients it yields
+            g_uu = torch.zeros_like(grad)
+            _device.gram_backward_rows(spec, pz, (G_Q + G_Q.T).contiguous(), grad=g_uu, grad_rows=gZ)
+            grad.add_(g_uu, alpha=0.5)
+            # sub-kernel order -> columns of Z
+            gz_full = np.zeros(zpar.numpy().shape, dtype=np.float64)
+            gz_host = gZ.cpu().numpy()
+            for i, d in enumerate(spec._keep):
+                gz_full[:, d.column] += gz_host[:, i]
+            model._inducing_grad = gz_full
+        else:
+            _device.gram_backward(spec, pz, G_Q.contiguous(), grad=grad)
         g = grad.cpu().numpy()
         layout = [_device.table_layout(spec, i) for i in range(spec.num_dims)]
     finally:
@@ -328,6 +366,9 @@ def training_loss_and_grad(model) -> Tuple[float, np.ndarray]:
             cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
     if any(p.trainable for p in _discrete_parameters(model)):
         cgrad.update(discrete_parameter_gradients(model))
+    zpar = _inducing_parameter(model)
+    if zpar is not None and zpar.trainable:
+        cgrad[id(zpar)] = model._inducing_grad
     loss = -(val + model.log_prior_density())
     parts = []
     for p in trainable_parameters(model):

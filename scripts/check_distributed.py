@@ -15,9 +15,10 @@ cfg = config_C(300_000, 20, 512, 3)
 b, e = parallel.partition_rows(300_000, world)[rank]
 m = SGPR((cfg["X"][b:e], cfg["y"][b:e]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=32768, distributed=True)
 m.likelihood.variance.assign(cfg["noise"])
-freeze_unsupported(m)
+freeze_unsupported(m)  # nothing to freeze: the inducing points are differentiated too
 elbo_d = m.elbo()
 val_d, gl_d, gv_d, gn_d = sgpr_elbo_and_grad(m)
+gz_d = m._inducing_grad
 ok = True
 if rank == 0:
     s = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=32768, distributed=False)
@@ -27,8 +28,10 @@ if rank == 0:
     val_s, gl_s, gv_s, gn_s = sgpr_elbo_and_grad(s)
     rel = lambda a, c: float(np.max(np.abs(np.asarray(a) - np.asarray(c))) / np.max(np.abs(np.asarray(c))))
     print(f"world {world}: elbo {elbo_d:.6f} vs {elbo_s:.6f} (rel {abs(elbo_d-elbo_s)/abs(elbo_s):.2e}); "
-          f"grad ls rel {rel(gl_d, gl_s):.2e}, var rel {rel(gv_d, gv_s):.2e}, noise rel {abs(gn_d-gn_s)/abs(gn_s):.2e}")
-    ok = abs(elbo_d - elbo_s) < 1e-10 * abs(elbo_s) and rel(gl_d, gl_s) < 1e-9 and rel(gv_d, gv_s) < 1e-9
+          f"grad ls rel {rel(gl_d, gl_s):.2e}, var rel {rel(gv_d, gv_s):.2e}, noise rel {abs(gn_d-gn_s)/abs(gn_s):.2e}, "
+          f"Z rel {rel(gz_d, s._inducing_grad):.2e}")
+    ok = (abs(elbo_d - elbo_s) < 1e-10 * abs(elbo_s) and rel(gl_d, gl_s) < 1e-9 and rel(gv_d, gv_s) < 1e-9
+          and rel(gz_d, s._inducing_grad) < 1e-9)
     print("DISTRIBUTED CHECK", "OK" if ok else "FAILED")
 dist.barrier()
 dist.destroy_process_group()

@@ -83,7 +83,8 @@ def test_sgpr_elbo_gradient_matches_autograd(chunk):
     cfg, ls, var = _cfg(600, 5, 3, 48, seed=2)
     m = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=chunk)
     m.likelihood.variance.assign(cfg["noise"])
-    freeze_unsupported(m)  # inducing points (zfixed=True in the reference) and the unit base variances
+    m.inducing_variable.Z.trainable = False  # zfixed=True, the reference's default (model_utils.py:100-101)
+    freeze_unsupported(m)
     elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
     v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], cfg["Z"], ls, var, cfg["noise"])
     ref = oo.sgpr_elbo(build_oracle(cfg), cfg["X"], cfg["y"], cfg["Z"], cfg["noise"])
@@ -239,10 +240,13 @@ def test_sgpr_gradient_mixed_model_with_frozen_discrete_parameters():
     cfg, ls, var, measures, ref = _mixed_cfg(500, 40, seed=12)
     m = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=128)
     m.likelihood.variance.assign(cfg["noise"])
-    frozen = freeze_unsupported(m)  # only the inducing points are left without a gradient
-    assert len(frozen) == 1
+    assert freeze_unsupported(m) == []  # every parameter of the mixed model has a gradient, Z included
     elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
-    v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], cfg["Z"], ls, var, cfg["noise"], measures)
+    v, a_ls, a_var, a_noise, a_Z = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], cfg["Z"], ls, var, cfg["noise"],
+                                                     measures, wrt_Z=True)
+    cont = [i for i, d in enumerate(cfg["dims"]) if d["type"] == "rbf"]
+    assert max_rel_err(m._inducing_grad[:, cont], a_Z[:, cont]) < 1e-7
+    assert np.all(np.delete(m._inducing_grad, cont, axis=1) == 0.0)
     assert abs(v - oo.sgpr_elbo(ref, cfg["X"], cfg["y"], cfg["Z"], cfg["noise"])) < 1e-9 * abs(v)
     assert abs(elbo - v) < 1e-9 * abs(v)
     assert max_rel_err(g_ls[:4], a_ls[:4]) < 1e-7
@@ -465,3 +469,135 @@ def test_oak_model_switches_to_sgpr_with_kmeans_inducing_points_above_1000_point
     assert rmse < 0.2
     sob = oak.get_sobol()
     assert abs(sob.sum() - 1) < 1e-12 and sob[2] < 0.1  # little interaction in an additive target
+
+
+# ---- gradients with respect to the row points (inducing points, zfixed=False) -------------------
+@pytest.mark.parametrize("D,P", [(3, 1), (5, 2), (6, 3), (5, 4), (20, 3), (7, 6), (8, 8)])
+def test_row_point_gradients_match_autograd(D, P):
+    """d/dZ of sum W * K(Z, X) (and of K(Z, Z') in its first argument) by the row-gradient tiles vs autograd;
+    the parameter gradients of the same call equal those of the plain backward tiles."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var = _cfg(333, D, P, 77, seed=20 * D + P)
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    rng = np.random.default_rng(4)
+    Z = cfg["Z"] + 0.3 * rng.standard_normal(cfg["Z"].shape)
+    px, pz = _device.Points(spec, _device.to_device(cfg["X"])), _device.Points(spec, _device.to_device(Z))
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    for pb, B in ((px, cfg["X"]), (None, Z)):
+        W = rng.standard_normal((Z.shape[0], B.shape[0]))
+        Wd = _device.to_device(W)
+        g, gz = _device.gram_backward_rows(spec, pz, Wd, px2=pb)
+        g0 = _device.gram_backward(spec, pz, Wd, px2=pb)
+        assert max_rel_err(g.cpu().numpy(), g0.cpu().numpy()) < 1e-12
+        ZT = t(Z).clone().requires_grad_(True)
+        (t(W) * go.oak_K(ZT, t(B), t(ls), t(var))).sum().backward()
+        assert max_rel_err(gz.cpu().numpy(), ZT.grad.numpy()) < 1e-10
+        # accumulation into a caller's buffer with a pitch
+        buf = torch.ones((Z.shape[0], D + 3), dtype=torch.float64, device="cuda")
+        _device.gram_backward_rows(spec, pz, Wd, px2=pb, grad_rows=buf[:, :D])
+        assert max_rel_err(buf[:, :D].cpu().numpy(), 1.0 + ZT.grad.numpy()) < 1e-10
+        assert float((buf[:, D:] - 1.0).abs().max()) == 0.0
+    spec.close()
+
+
+def test_row_point_gradients_every_measure():
+    """helpers.mixed_config: Gaussian, uniform, empirical, MOG and unconstrained RBF dims with s^2 != 1 get
+    their d/dZ column; the binary and categorical columns get none (tf.cast / tf.gather)."""
+    import torch
+
+    from helpers import mixed_config
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg = mixed_config(n=300, seed=6, depth=3)
+    ref = build_oracle(cfg)
+    dims = cfg["dims"]
+    ls = np.array([dims[i].get("lengthscale", 1.0) for i in range(7)])
+    s2 = np.array([dims[i].get("variance", 1.0) for i in range(7)])
+    var = np.array(cfg["variances"])
+    measures = []
+    for i, d in enumerate(dims):
+        if d["type"] != "rbf":
+            measures.append(("table", ref.dims[i].table()))
+        elif d["measure"] is None:
+            measures.append(("none",))
+        else:
+            measures.append(tuple(d["measure"]))
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    rng = np.random.default_rng(12)
+    Z = cfg["Z"].copy()
+    Z[:, [0, 1, 2, 3, 6]] += 0.2 * rng.standard_normal((Z.shape[0], 5))
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    px, pz = _device.Points(spec, _device.to_device(cfg["X"])), _device.Points(spec, _device.to_device(Z))
+    W = rng.standard_normal((Z.shape[0], 300))
+    g, gz = _device.gram_backward_rows(spec, pz, _device.to_device(W), px2=px)
+    ZT = t(Z).clone().requires_grad_(True)
+    (t(W) * go._esp_sum(go._dim_values(ZT, t(cfg["X"]), t(ls), measures, t(s2)), t(var))).sum().backward()
+    gz = gz.cpu().numpy()
+    assert max_rel_err(gz[:, [0, 1, 2, 3, 6]], ZT.grad.numpy()[:, [0, 1, 2, 3, 6]]) < 1e-10
+    assert np.all(gz[:, [4, 5]] == 0.0)
+    g0 = _device.gram_backward(spec, pz, _device.to_device(W), px2=px)
+    assert max_rel_err(g.cpu().numpy(), g0.cpu().numpy()) < 1e-12
+    spec.close()
+
+
+@pytest.mark.parametrize("chunk,keep", [(128, True), (8192, True), (256, False)])
+def test_sgpr_elbo_gradient_wrt_inducing_points_matches_autograd(chunk, keep):
+    """zfixed=False (model_utils.py:98-101): d ELBO / d Z through Kuf and Kuu, with Kuf kept or recomputed."""
+    from oak_b200.models import SGPR
+    from oak_b200.training import freeze_unsupported, sgpr_elbo_and_grad
+    from oak_b200.workloads import build_kernel
+
+    cfg, ls, var = _cfg(700, 5, 3, 40, seed=7)
+    Z = cfg["Z"] + 0.1 * np.random.default_rng(1).standard_normal(cfg["Z"].shape)
+    m = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=Z, chunk=chunk)
+    m.keep_kuf = keep
+    m.likelihood.variance.assign(cfg["noise"])
+    frozen = freeze_unsupported(m)
+    assert m.inducing_variable.Z.trainable and all(p is not m.inducing_variable.Z for p in frozen)
+    elbo, g_ls, g_var, g_noise = sgpr_elbo_and_grad(m)
+    v, a_ls, a_var, a_noise, a_Z = go.value_and_grad(go.sgpr_elbo, cfg["X"], cfg["y"], Z, ls, var, cfg["noise"],
+                                                     wrt_Z=True)
+    assert abs(elbo - v) < 1e-9 * abs(v)
+    assert max_rel_err(g_ls, a_ls) < 1e-7
+    assert max_rel_err(g_var, a_var) < 1e-7
+    assert abs(g_noise - a_noise) < 1e-7 * abs(a_noise)
+    assert m._inducing_grad.shape == Z.shape
+    assert max_rel_err(m._inducing_grad, a_Z) < 1e-7
+
+
+def test_training_with_trainable_inducing_points_improves_the_bound():
+    """create_model_oak(..., zfixed=False) + BFGS: Z is part of the trainable variables, the loss gradient
+    agrees with central differences along a random direction, and the optimised bound beats zfixed=True's start."""
+    from oak_b200.model_utils import create_model_oak
+    from oak_b200.training import _assign_unconstrained, optimise, trainable_parameters, training_loss_and_grad
+
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((500, 3))
+    y = (np.sin(2 * X[:, 0]) + X[:, 1] * X[:, 2] + 0.1 * rng.standard_normal(500)).reshape(-1, 1)
+    Z0 = X[:25].copy()
+    m = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=Z0, optimise=False, zfixed=False)
+    params = trainable_parameters(m)
+    assert any(p is m.inducing_variable.Z for p in params)
+    u0 = np.concatenate([np.asarray(p.unconstrained_variable, dtype=np.float64).reshape(-1) for p in params])
+    loss0, g0 = training_loss_and_grad(m)
+    assert g0.shape == u0.shape
+    d = rng.standard_normal(u0.shape)
+    d /= np.linalg.norm(d)
+    h = 1e-5
+    _assign_unconstrained(params, u0 + h * d)
+    lp = training_loss_and_grad(m)[0]
+    _assign_unconstrained(params, u0 - h * d)
+    lm = training_loss_and_grad(m)[0]
+    _assign_unconstrained(params, u0)
+    fd = (lp - lm) / (2 * h)
+    assert abs(fd - g0 @ d) < 1e-5 * max(1.0, abs(fd))
+    res = optimise(m, maxiter=30)
+    assert res.fun < loss0 - 1.0
+    assert np.abs(m.inducing_variable.Z.numpy() - Z0).max() > 1e-3
