@@ -262,6 +262,34 @@ int oak_gram_diag_backward_f64(const oak_spec* spec, const void* d_points, const
                                int64_t n, const double* d_w, double wscale, double* d_grad,
                                void* d_work, void* stream);
 
+/* ---- whitened SVGP (diagonal q) with a Bernoulli likelihood ---------------------------------
+ * Replaces, around the Kuf tiles, what gpflow.models.SVGP(kernel=OAK, likelihood=Bernoulli(invlink=inv_logit),
+ * whiten=True, q_diag=True) computes in the reference's classification run
+ * (examples/uci/uci_classification_train.py:108-135: elbo under BFGS, predict_f, predict_log_density).
+ * A = L^-1 Kuf (m x n, row-major, pitch lda) comes from oak_gram_f64 and one triangular solve. */
+enum oak_link {
+  OAK_LINK_LOGIT = 0,  /* sigmoid(f) (1 - 2 jitter) + jitter: the reference's inv_logit (:43-45)           */
+  OAK_LINK_PROBIT = 1  /* 0.5 (1 + erf(f / sqrt 2)) (1 - 2 jitter) + jitter: gpflow's default inv_probit    */
+};
+/* mean_i = sum_r A_ri q_mu_r;  var_i = kdiag_i - sum_r A_ri^2 (1 - q_sqrt_r^2)   (gpflow base_conditional, white) */
+int oak_svgp_moments_f64(const double* d_A, int64_t lda, int32_t m, int64_t n, const double* d_q_mu,
+                         const double* d_q_sqrt, const double* d_kdiag, double* d_mean, double* d_var,
+                         void* stream);
+/* Cotangents of the above: d_Abar (m x n, pitch ldb) = q_mu gmean^T - 2 (1 - q_sqrt^2) A diag(gvar);
+ * d_gq_sqrt[r] += 2 q_sqrt_r sum_i gvar_i A_ri^2. */
+int oak_svgp_moments_backward_f64(const double* d_A, int64_t lda, int32_t m, int64_t n, const double* d_q_mu,
+                                  const double* d_q_sqrt, const double* d_gmean, const double* d_gvar,
+                                  double* d_Abar, int64_t ldb, double* d_gq_sqrt, void* stream);
+/* Gauss-Hermite expectations of the Bernoulli log density under N(mean_i, var_i) (gpflow
+ * Bernoulli.variational_expectations / predict_log_density, NDiagGHQuadrature): nodes d_gh_x (already times
+ * sqrt 2) and weights d_gh_w (already over sqrt pi), n_gh <= 64.  Outputs (each may be NULL):
+ * d_varexp[i] = sum_k w_k log p(y_i | f_k), its derivatives d_gmean / d_gvar with respect to mean_i / var_i,
+ * d_logdensity[i] = log sum_k w_k p(y_i | f_k).  y_i == 1 selects p, anything else 1 - p (tf.where(y == 1, ..)). */
+int oak_bernoulli_quadrature_f64(const double* d_mean, const double* d_var, const double* d_y, int64_t n,
+                                 int32_t link, double jitter, const double* d_gh_x, const double* d_gh_w,
+                                 int32_t n_gh, double* d_varexp, double* d_gmean, double* d_gvar,
+                                 double* d_logdensity, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Dependent-chain DFMA microbenchmark: writes achieved FP64 issue slots / second to
  * *h_slots_per_s (1 slot = one DFMA = 2 flop).  This is the measured FP64 roofline peak. */

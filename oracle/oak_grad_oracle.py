@@ -155,6 +155,74 @@ def gpr_lml(X, Y, ls, variances, noise, measures=None):
     return -0.5 * (a ** 2).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * N * math.log(2 * math.pi)
 
 
+# ---- whitened SVGP, diagonal q(u), Bernoulli likelihood (gpflow 2.2.1; not vendored under /root/reference) ----
+# Call sites: examples/uci/uci_classification_train.py:108-135.  Restated from the published gpflow 2.2.1 sources:
+# models/svgp.py (elbo, prior_kl), kullback_leiblers.py (gauss_kl, K=None, diagonal q_sqrt),
+# conditionals/util.py (base_conditional, white=True), likelihoods (Bernoulli, NDiagGHQuadrature with 20 points,
+# nodes from np.polynomial.hermite.hermgauss scaled by sqrt 2 and 1 / sqrt pi), posteriors.py (alpha = L^-T q_mu).
+# Parity unpinned against a gpflow run (gpflow / TensorFlow are not installed in this image); pinned on the
+# mathematical identities in tests/ (q(u) = prior gives KL = 0 and the prior predictive; quadrature against
+# scipy.integrate.quad).
+def inv_logit(f, jitter=1e-3):
+    return torch.sigmoid(f) * (1 - 2 * jitter) + jitter
+
+
+def inv_probit(f, jitter=1e-3):
+    return 0.5 * (1.0 + torch.erf(f / math.sqrt(2.0))) * (1 - 2 * jitter) + jitter
+
+
+def gh_points_and_weights(n_gh=20):
+    import numpy as np
+
+    x, w = np.polynomial.hermite.hermgauss(n_gh)
+    return torch.as_tensor(x * np.sqrt(2.0)), torch.as_tensor(w / np.sqrt(np.pi))
+
+
+def svgp_conditional(Xnew, Z, ls, variances, q_mu, q_sqrt, measures=None):
+    """base_conditional(Kmn, Kmm + jitter, Knn_diag, f=q_mu, q_sqrt=diag, white=True) -> (mean [N], var [N])."""
+    Kmm = oak_K(Z, Z, ls, variances, measures) + JITTER * torch.eye(Z.shape[0], dtype=Z.dtype)
+    Kmn = oak_K(Z, Xnew, ls, variances, measures)
+    Knn = oak_K_diag(Xnew, ls, variances, measures)
+    Lm = torch.linalg.cholesky(Kmm)
+    A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)
+    fvar = Knn - (A ** 2).sum(0)
+    fmean = (A.T @ q_mu.reshape(-1, 1))[:, 0]
+    LTA = A * q_sqrt.reshape(-1, 1)
+    fvar = fvar + (LTA ** 2).sum(0)
+    return fmean, fvar
+
+
+def bernoulli_log_prob(F, Y, invlink=inv_logit):
+    p = invlink(F)
+    return torch.log(torch.where(Y == 1, p, 1 - p))
+
+
+def bernoulli_variational_expectations(Fmu, Fvar, Y, invlink=inv_logit, n_gh=20):
+    x, w = gh_points_and_weights(n_gh)
+    F = Fmu[:, None] + torch.sqrt(Fvar)[:, None] * x[None, :]
+    return (bernoulli_log_prob(F, Y[:, None], invlink) * w[None, :]).sum(1)
+
+
+def bernoulli_predict_log_density(Fmu, Fvar, Y, invlink=inv_logit, n_gh=20):
+    x, w = gh_points_and_weights(n_gh)
+    F = Fmu[:, None] + torch.sqrt(Fvar)[:, None] * x[None, :]
+    return torch.logsumexp(bernoulli_log_prob(F, Y[:, None], invlink) + torch.log(w)[None, :], dim=1)
+
+
+def svgp_elbo(X, Y, Z, ls, variances, q_mu, q_sqrt, measures=None, invlink=inv_logit, num_data=None):
+    fmean, fvar = svgp_conditional(X, Z, ls, variances, q_mu, q_sqrt, measures)
+    var_exp = bernoulli_variational_expectations(fmean, fvar, Y.reshape(-1), invlink)
+    M = Z.shape[0]
+    two_kl = (q_mu ** 2).sum() - M - torch.log(q_sqrt ** 2).sum() + (q_sqrt ** 2).sum()
+    scale = 1.0 if num_data is None else num_data / X.shape[0]
+    return var_exp.sum() * scale - 0.5 * two_kl
+
+
+def svgp_alpha(Z, ls, variances, q_mu, measures=None):
+    Kmm = oak_K(Z, Z, ls, variances, measures) + JITTER * torch.eye(Z.shape[0], dtype=Z.dtype)
+    return torch.linalg.solve_triangular(torch.linalg.cholesky(Kmm).T, q_mu.reshape(-1, 1), upper=True)
+
+
 def value_and_grad(fn, X, Y, Z, ls, variances, noise, measures=None, wrt_Z=False):
     """Returns (value, d/d ls, d/d variances, d/d noise) as floats / numpy arrays; with ``wrt_Z`` also
     d/d Z (the inducing points, gpflow's ``inducing_variable.Z`` when zfixed=False)."""

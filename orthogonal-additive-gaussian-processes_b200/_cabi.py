@@ -19,6 +19,7 @@ OAK_MAX_DEPTH = 16
 DIM_RBF, DIM_BINARY, DIM_CATEGORICAL = 0, 1, 2
 MEASURE_NONE, MEASURE_GAUSSIAN, MEASURE_UNIFORM, MEASURE_EMPIRICAL, MEASURE_MOG = 0, 1, 2, 3, 4
 ESP_NEWTON_GIRARD, ESP_DIRECT = 0, 1
+LINK_LOGIT, LINK_PROBIT = 0, 1
 
 
 class OakNativeError(RuntimeError):
@@ -81,6 +82,10 @@ SIGNATURES = {
     "oak_spec_table_layout": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "oak_backward_points_bytes": (_sz, [_vp, _i64]),
     "oak_prepare_backward_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "oak_svgp_moments_f64": (C.c_int, [_dp, _i64, C.c_int32, _i64, _dp, _dp, _dp, _dp, _dp, _vp]),
+    "oak_svgp_moments_backward_f64": (C.c_int, [_dp, _i64, C.c_int32, _i64, _dp, _dp, _dp, _dp, _dp, _i64, _dp, _vp]),
+    "oak_bernoulli_quadrature_f64": (C.c_int, [_dp, _dp, _dp, _i64, C.c_int32, C.c_double, _dp, _dp, C.c_int32,
+                                               _dp, _dp, _dp, _dp, _vp]),
     "oak_gram_backward_rows_work_bytes": (_sz, [_vp, _i64, _i64]),
     "oak_gram_backward_rows_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _dp, _i64, _vp, _vp]),
     "oak_gram_backward_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _vp, _vp]),

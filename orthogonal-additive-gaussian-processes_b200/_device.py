@@ -319,6 +319,59 @@ def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad
 
 
 # ---- SGPR / GPR -------------------------------------------------------------------------
+# ---- whitened SVGP / Bernoulli pieces ------------------------------------------------------------
+_GH_CACHE = {}
+
+
+def gauss_hermite(n_gh: int, device):
+    """(x sqrt 2, w / sqrt pi) of ``np.polynomial.hermite.hermgauss`` on the device -- gpflow's own source of
+    the nodes (gpflow/quadrature/gauss_hermite.py gh_points_and_weights)."""
+    key = (int(n_gh), str(device))
+    if key not in _GH_CACHE:
+        torch = _torch()
+        x, w = np.polynomial.hermite.hermgauss(int(n_gh))
+        _GH_CACHE[key] = (torch.as_tensor(x * np.sqrt(2.0), dtype=torch.float64).to(device),
+                          torch.as_tensor(w / np.sqrt(np.pi), dtype=torch.float64).to(device))
+    return _GH_CACHE[key]
+
+
+def svgp_moments(A, q_mu, q_sqrt, kdiag):
+    """mean_i = A[:, i] . q_mu, var_i = kdiag_i - sum_r A_ri^2 (1 - q_sqrt_r^2) for A = L^-1 Kuf (M x n)."""
+    torch = _torch()
+    m, n = A.shape
+    assert A.stride(1) == 1 and q_mu.numel() == m and q_sqrt.numel() == m and kdiag.numel() == n
+    mean = torch.empty(n, dtype=torch.float64, device=A.device)
+    var = torch.empty(n, dtype=torch.float64, device=A.device)
+    check(_cabi.load().oak_svgp_moments_f64(_p(A), int(A.stride(0)), m, n, _p(q_mu), _p(q_sqrt), _p(kdiag), _p(mean),
+                                            _p(var), C.c_void_p(stream_ptr())), "oak_svgp_moments_f64")
+    return mean, var
+
+
+def svgp_moments_backward(A, q_mu, q_sqrt, gmean, gvar, gq_sqrt):
+    """Abar = q_mu gmean^T - 2 (1 - q_sqrt^2) A diag(gvar); gq_sqrt += 2 q_sqrt sum_i gvar_i A_ri^2."""
+    torch = _torch()
+    m, n = A.shape
+    Abar = torch.empty((m, n), dtype=torch.float64, device=A.device)
+    check(_cabi.load().oak_svgp_moments_backward_f64(_p(A), int(A.stride(0)), m, n, _p(q_mu), _p(q_sqrt), _p(gmean),
+                                                     _p(gvar), _p(Abar), int(Abar.stride(0)), _p(gq_sqrt),
+                                                     C.c_void_p(stream_ptr())), "oak_svgp_moments_backward_f64")
+    return Abar
+
+
+def bernoulli_quadrature(mean, var, y, link: int, jitter: float, n_gh: int, want=("varexp", "gmean", "gvar")):
+    """Gauss-Hermite expectations of the Bernoulli log density; returns a dict of the requested arrays out of
+    ("varexp", "gmean", "gvar", "logdensity")."""
+    torch = _torch()
+    n = mean.numel()
+    gx, gw = gauss_hermite(n_gh, mean.device)
+    out = {k: torch.empty(n, dtype=torch.float64, device=mean.device) for k in want}
+    check(_cabi.load().oak_bernoulli_quadrature_f64(
+        _p(mean), _p(var), _p(y), n, int(link), float(jitter), _p(gx), _p(gw), int(n_gh), _p(out.get("varexp")),
+        _p(out.get("gmean")), _p(out.get("gvar")), _p(out.get("logdensity")), C.c_void_p(stream_ptr())),
+        "oak_bernoulli_quadrature_f64")
+    return out
+
+
 def sgpr_stats(spec: Spec, pz: Points, px: Points, y, chunk: int = 262144, stats=None, keep_kuf: bool = False,
                kuf_store=None):
     """Accumulates Phi | Kuf y | sum K_diag | y^T y for the local points into ``stats``.

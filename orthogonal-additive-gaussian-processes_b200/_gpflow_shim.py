@@ -259,6 +259,44 @@ class Gaussian(Module):
         self.variance = Parameter(variance, transform=positive(lower=VARIANCE_LOWER_BOUND))
 
 
+class InvLink:
+    """Inverse link of the Bernoulli likelihood, evaluated on the device by ``oak_bernoulli_quadrature_f64``.
+    ``kind`` 0: ``sigmoid(x) (1 - 2 jitter) + jitter`` -- the ``inv_logit`` the reference defines in
+    examples/uci/uci_classification_train.py:43-45; 1: gpflow's ``inv_probit``."""
+
+    def __init__(self, kind: int, jitter: float = 1e-3):
+        self.kind, self.jitter = int(kind), float(jitter)
+
+    def __call__(self, x):
+        from math import sqrt
+
+        x = np.asarray(x, dtype=np.float64)
+        if self.kind == 0:
+            e = np.exp(-np.abs(x))
+            base = np.where(x >= 0, 1.0 / (1.0 + e), e / (1.0 + e))
+        else:
+            from scipy.special import erf
+
+            base = 0.5 * (1.0 + erf(x / sqrt(2.0)))
+        return base * (1.0 - 2.0 * self.jitter) + self.jitter
+
+
+inv_logit = InvLink(0)
+inv_probit = InvLink(1)
+
+
+class Bernoulli(Module):
+    """``gpflow.likelihoods.Bernoulli(invlink=...)``: 20-point Gauss-Hermite quadrature for the variational
+    expectations and the predictive density (gpflow 2.2.1 ScalarLikelihood defaults)."""
+
+    def __init__(self, invlink: InvLink = inv_probit, num_gauss_hermite_points: int = 20):
+        if not isinstance(invlink, InvLink):
+            raise NotImplementedError("invlink must be oak_b200 inv_logit / inv_probit (an InvLink): arbitrary "
+                                      "Python callables cannot run inside the CUDA quadrature kernel")
+        self.invlink = invlink
+        self.num_gauss_hermite_points = int(num_gauss_hermite_points)
+
+
 class Gamma:
     """Prior placeholder for ``tfd.Gamma(concentration, rate)`` (oak/model_utils.py:163-165)."""
 

@@ -209,3 +209,128 @@ class SGPR(GPModel):
         tmp2 = torch.linalg.solve_triangular(LB, tmp1, upper=False)
         var = (kdiag + (tmp2 * tmp2).sum(0) - (tmp1 * tmp1).sum(0)).reshape(-1, 1)
         return _device.from_device(mean, host), _device.from_device(var, host)
+
+
+class SVGP(Module):
+    """Whitened sparse variational GP with a diagonal q(u) and a Bernoulli likelihood: the model of the
+    reference's classification run, ``gpflow.models.SVGP(kernel, likelihood=Bernoulli(invlink=inv_logit),
+    inducing_variable=Z, whiten=True, q_diag=True)`` trained full-batch with BFGS
+    (examples/uci/uci_classification_train.py:108-124).  gpflow 2.2.1 semantics (``elbo(data)``,
+    ``predict_f``, ``predict_log_density``, ``posterior().alpha``) are restated in csrc/oak_svgp.cu and
+    ``training.svgp_elbo_and_grad``; Kuf / Kuu / K_diag come from the fused OAK tiles, the M x M and M x n
+    triangular algebra from cuSOLVER / cuBLAS."""
+
+    def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps: int = 1,
+                 q_diag: bool = False, q_mu=None, q_sqrt=None, whiten: bool = True, num_data: Optional[int] = None,
+                 chunk: int = 65536):
+        if not (whiten and q_diag):
+            raise NotImplementedError("only whiten=True, q_diag=True (the reference's configuration) is built")
+        if num_latent_gps != 1 or mean_function is not None:
+            raise NotImplementedError("one latent GP with the zero mean function")
+        from ._gpflow_shim import Bernoulli, positive
+
+        if not isinstance(likelihood, Bernoulli):
+            raise NotImplementedError("SVGP is built for the Bernoulli likelihood (classification)")
+        self.kernel = kernel
+        self.likelihood = likelihood
+        if not isinstance(inducing_variable, InducingPoints):
+            inducing_variable = InducingPoints(inducing_variable)
+        self.inducing_variable = inducing_variable
+        m = inducing_variable.num_inducing
+        self.q_mu = Parameter(np.zeros((m, 1)) if q_mu is None else np.asarray(q_mu, dtype=np.float64).reshape(m, 1))
+        self.q_sqrt = Parameter(np.ones((m, 1)) if q_sqrt is None else np.asarray(q_sqrt, dtype=np.float64).reshape(m, 1),
+                                transform=positive())
+        self.num_data = num_data
+        self.mean_function = lambda X: 0.0
+        self.chunk = int(chunk)
+        self.data = None  # the reference assigns oak.m.data before the Sobol step (:145)
+
+    _slice_for_kernel = GPModel._slice_for_kernel
+    log_prior_density = GPModel.log_prior_density
+
+    def _Z_device(self):
+        return self._slice_for_kernel(_device.to_device(value_of(self.inducing_variable.Z)))
+
+    # ---- objective ----------------------------------------------------------------------------
+    def elbo(self, data) -> float:
+        from .training import svgp_elbo_and_grad
+
+        return svgp_elbo_and_grad(self, data, want_grad=False)[0]
+
+    def maximum_log_likelihood_objective(self, data) -> float:
+        return self.elbo(data)
+
+    def training_loss(self, data) -> float:
+        return -(self.elbo(data) + self.log_prior_density())
+
+    def training_loss_closure(self, data):
+        closure = lambda: self.training_loss(data)
+        closure.model, closure.data = self, data  # picked up by training.optimise
+        return closure
+
+    def training_loss_and_grad(self, data):
+        from .training import training_loss_and_grad
+
+        return training_loss_and_grad(self, data)
+
+    # ---- prediction -----------------------------------------------------------------------------
+    def _conditional(self, Xnew):
+        """(mean, var) of q(f) at Xnew on the device (gpflow ``base_conditional``, white=True)."""
+        import torch
+
+        Xn = self._slice_for_kernel(_device.to_device(Xnew))
+        Zs = self._Z_device()
+        q_mu = _device.to_device(self.q_mu.numpy(), ndim=1).reshape(-1)
+        q_sqrt = _device.to_device(self.q_sqrt.numpy(), ndim=1).reshape(-1)
+        spec = self.kernel._make_spec()
+        try:
+            self.kernel._check_discrete(Xn, spec._keep)
+            self.kernel._check_discrete(Zs, spec._keep)
+            pz = _device.Points(spec, Zs)
+            Kuu = _device.gram(spec, pz)
+            Kuu.diagonal().add_(DEFAULT_JITTER)
+            L = torch.linalg.cholesky(Kuu)
+            n = int(Xn.shape[0])
+            mean = torch.empty(n, dtype=torch.float64, device=Xn.device)
+            var = torch.empty(n, dtype=torch.float64, device=Xn.device)
+            for c0 in range(0, n, self.chunk):
+                c1 = min(c0 + self.chunk, n)
+                pxc = _device.Points(spec, Xn[c0:c1])
+                A = torch.linalg.solve_triangular(L, _device.gram(spec, pz, pxc), upper=False).contiguous()
+                mean[c0:c1], var[c0:c1] = _device.svgp_moments(A, q_mu, q_sqrt, _device.gram_diag(spec, pxc))
+        finally:
+            spec.close()
+        return mean, var
+
+    def predict_f(self, Xnew, full_cov: bool = False):
+        if full_cov:
+            raise NotImplementedError("marginal variances only (what the reference reads, :128)")
+        host = _device.is_host(Xnew)
+        mean, var = self._conditional(Xnew)
+        return _device.from_device(mean.reshape(-1, 1), host), _device.from_device(var.reshape(-1, 1), host)
+
+    def predict_log_density(self, data):
+        """log of the Gauss-Hermite predictive density of each (x, y) (gpflow ``predict_log_density``; :135)."""
+        X, Y = data
+        host = _device.is_host(X)
+        mean, var = self._conditional(X)
+        y = _device.to_device(Y, ndim=1).reshape(-1)
+        lk = self.likelihood
+        out = _device.bernoulli_quadrature(mean, var, y, lk.invlink.kind, lk.invlink.jitter,
+                                           lk.num_gauss_hermite_points, want=("logdensity",))["logdensity"]
+        return _device.from_device(out, host)
+
+    def sufficient_statistics(self):
+        """``posterior().alpha`` of the whitened model: L^-T q_mu, shape (M, 1) (oak/utils.py:174-177)."""
+        import torch
+
+        Zs = self._Z_device()
+        spec = self.kernel._make_spec()
+        try:
+            Kuu = _device.gram(spec, _device.Points(spec, Zs))
+        finally:
+            spec.close()
+        Kuu.diagonal().add_(DEFAULT_JITTER)
+        L = torch.linalg.cholesky(Kuu)
+        q_mu = _device.to_device(self.q_mu.numpy()).reshape(-1, 1)
+        return torch.linalg.solve_triangular(L.T, q_mu, upper=True)

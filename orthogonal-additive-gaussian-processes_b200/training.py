@@ -69,10 +69,14 @@ def _lengthscale_parameter(sub):
 
 
 def _supported_parameters(model) -> Tuple[List[Parameter], List[Parameter], Parameter]:
-    """(per-dimension lengthscale Parameters or None, order variances, noise)."""
+    """(per-dimension lengthscale Parameters or None, order variances, noise -- None without a Gaussian likelihood)."""
     kern = model.kernel
     ls = [_lengthscale_parameter(k) for k in kern.kernels]
-    return ls, list(kern.variances), model.likelihood.variance
+    return ls, list(kern.variances), getattr(model.likelihood, "variance", None)
+
+
+def _variational_parameters(model) -> List[Parameter]:
+    return [p for p in (getattr(model, "q_mu", None), getattr(model, "q_sqrt", None)) if isinstance(p, Parameter)]
 
 
 def _base_variance_parameter(sub):
@@ -107,9 +111,9 @@ def _all_supported_ids(model):
     ls, var, noise = _supported_parameters(model)
     bvar = [_base_variance_parameter(k) for k in model.kernel.kernels]
     z = _inducing_parameter(model)
-    return ({id(p) for p in ls if p is not None} | {id(p) for p in var} | {id(noise)}
+    return ({id(p) for p in ls if p is not None} | {id(p) for p in var} | ({id(noise)} if noise is not None else set())
             | {id(p) for p in _discrete_parameters(model)} | {id(p) for p in bvar if p is not None}
-            | ({id(z)} if z is not None else set()))
+            | ({id(z)} if z is not None else set()) | {id(p) for p in _variational_parameters(model)})
 
 
 def freeze_unsupported(model) -> List[Parameter]:
@@ -298,6 +302,109 @@ def gpr_lml_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
     return lml, g[:D].copy(), g[D: D + P1].copy(), g_noise
 
 
+def svgp_elbo_and_grad(model, data, want_grad: bool = True):
+    """Whitened SVGP bound with diagonal q(u) and Bernoulli likelihood (gpflow 2.2.1 ``SVGP.elbo``):
+
+        A = L^-1 Kuf,  mean = A^T q_mu,  var = K_diag - sum_m A^2 (1 - q_sqrt^2)
+        elbo = scale * sum_i E_{N(mean_i, var_i)}[log p(y_i | f)] - KL,   scale = num_data / N (1 when num_data is None)
+        KL = (sum q_mu^2 - M - sum log q_sqrt^2 + sum q_sqrt^2) / 2
+
+    Returns (elbo, d/d lengthscales, d/d order variances, None); the gradients of q_mu / q_sqrt (and of Z when
+    trainable) are left on the model.  Backward chain: Abar = dE/dA from ``oak_svgp_moments_backward_f64``,
+    Kuf-bar = L^-T Abar, L-bar = -tril(L^-T Abar A^T), Kuu-bar by the Cholesky adjoint
+    (1/2) L^-T (P + P^T) L^-1 with P = tril(L^T L-bar), diagonal halved; all contracted with dK/d theta by the
+    backward tiles."""
+    torch = _device._torch()
+    X, Y = data
+    Xs = model._slice_for_kernel(_device.to_device(X))
+    y = _device.to_device(Y, ndim=1).reshape(-1)
+    Zs = model._Z_device()
+    kern = model.kernel
+    lk = model.likelihood
+    spec = kern._make_spec()
+    try:
+        if want_grad:
+            _check_trainables(model, spec._keep)
+        kern._check_discrete(Xs, spec._keep)
+        kern._check_discrete(Zs, spec._keep)
+        pz = _device.Points(spec, Zs)
+        m, n = pz.n, int(Xs.shape[0])
+        if y.numel() != n:
+            raise ValueError("one label per input row")
+        scale = 1.0 if model.num_data is None else float(model.num_data) / n
+        dev = Xs.device
+        q_mu = _device.to_device(model.q_mu.numpy(), ndim=1).reshape(-1)
+        q_sqrt = _device.to_device(model.q_sqrt.numpy(), ndim=1).reshape(-1)
+        Kuu = _device.gram(spec, pz)
+        Kuu.diagonal().add_(DEFAULT_JITTER)
+        L = torch.linalg.cholesky(Kuu)
+        zpar = _inducing_parameter(model)
+        z_train = want_grad and zpar is not None and zpar.trainable
+        if want_grad:
+            nout = int(_cabi.load().oak_backward_grad_count(spec.handle))
+            grad = torch.zeros(nout, dtype=torch.float64, device=dev)
+            gZ = torch.zeros((m, spec.num_dims), dtype=torch.float64, device=dev) if z_train else None
+            G_AA = torch.zeros((m, m), dtype=torch.float64, device=dev)
+            g_qmu = torch.zeros(m, dtype=torch.float64, device=dev)
+            g_qsqrt = torch.zeros(m, dtype=torch.float64, device=dev)
+        ve_sum = torch.zeros((), dtype=torch.float64, device=dev)
+        chunk = max(64, int(model.chunk))
+        for c0 in range(0, n, chunk):
+            c1 = min(c0 + chunk, n)
+            pxc = _device.Points(spec, Xs[c0:c1])
+            A = torch.linalg.solve_triangular(L, _device.gram(spec, pz, pxc), upper=False).contiguous()
+            mean, var = _device.svgp_moments(A, q_mu, q_sqrt, _device.gram_diag(spec, pxc))
+            q = _device.bernoulli_quadrature(mean, var, y[c0:c1].contiguous(), lk.invlink.kind, lk.invlink.jitter,
+                                             lk.num_gauss_hermite_points,
+                                             want=("varexp", "gmean", "gvar") if want_grad else ("varexp",))
+            ve_sum += q["varexp"].sum()
+            if not want_grad:
+                continue
+            gm, gv = q["gmean"].mul_(scale), q["gvar"].mul_(scale)
+            Abar = _device.svgp_moments_backward(A, q_mu, q_sqrt, gm, gv, g_qsqrt)
+            g_qmu += A @ gm
+            G_AA += Abar @ A.T
+            Wc = torch.linalg.solve_triangular(L.T, Abar, upper=True).contiguous()  # L^-T Abar = d/dKuf
+            if z_train:
+                _device.gram_backward_rows(spec, pz, Wc, px2=pxc, grad=grad, grad_rows=gZ)
+            else:
+                _device.gram_backward(spec, pz, Wc, px2=pxc, grad=grad)
+            _device.gram_diag_backward(spec, pxc, w=gv, grad=grad)
+        kl = 0.5 * float((q_mu * q_mu).sum() - m - torch.log(q_sqrt * q_sqrt).sum() + (q_sqrt * q_sqrt).sum())
+        elbo = scale * float(ve_sum) - kl
+        if not want_grad:
+            return elbo, None, None, None
+        g_qmu -= q_mu
+        g_qsqrt -= q_sqrt - 1.0 / q_sqrt
+        Lbar = -torch.tril(torch.linalg.solve_triangular(L.T, G_AA, upper=True))
+        P = torch.tril(L.T @ Lbar)
+        P.diagonal().mul_(0.5)
+        T = torch.linalg.solve_triangular(L.T, P + P.T, upper=True)             # L^-T (P + P^T)
+        G_uu = 0.5 * torch.linalg.solve_triangular(L.T, T.T, upper=True).T     # ... L^-1
+        G_uu = (0.5 * (G_uu + G_uu.T)).contiguous()
+        if z_train:
+            g_uu = torch.zeros_like(grad)
+            _device.gram_backward_rows(spec, pz, (2.0 * G_uu).contiguous(), grad=g_uu, grad_rows=gZ)
+            grad.add_(g_uu, alpha=0.5)
+            gz_full = np.zeros(zpar.numpy().shape, dtype=np.float64)
+            gz_host = gZ.cpu().numpy()
+            for i, d in enumerate(spec._keep):
+                gz_full[:, d.column] += gz_host[:, i]
+            model._inducing_grad = gz_full
+        else:
+            _device.gram_backward(spec, pz, G_uu, grad=grad)
+        g = grad.cpu().numpy()
+        layout = [_device.table_layout(spec, i) for i in range(spec.num_dims)]
+    finally:
+        spec.close()
+    D, P1 = spec.num_dims, max(spec.depth, 1) + 1
+    model._table_cotangent = (g[D + P1: len(g) - D].copy(), layout)
+    model._base_variance_grad = g[len(g) - D:].copy()
+    model._variational_grads = {id(model.q_mu): g_qmu.cpu().numpy().reshape(-1, 1),
+                                id(model.q_sqrt): g_qsqrt.cpu().numpy().reshape(-1, 1)}
+    return elbo, g[:D].copy(), g[D: D + P1].copy(), None
+
+
 def discrete_parameter_gradients(model) -> Dict[int, np.ndarray]:
     """Chains the table-blob cotangent of the last ``*_and_grad`` call to the categorical W / kappa /
     variance and binary variance Parameters (ortho_categorical_kernel.py:34-53, ortho_binary_kernel.py:29-38):
@@ -344,11 +451,14 @@ def trainable_parameters(model) -> List[Parameter]:
     return [p for p in collect_parameters(model) if p.trainable]
 
 
-def training_loss_and_grad(model) -> Tuple[float, np.ndarray]:
-    """-(objective + log prior) and its gradient w.r.t. the concatenated unconstrained trainables."""
-    from .models import SGPR
+def training_loss_and_grad(model, data=None) -> Tuple[float, np.ndarray]:
+    """-(objective + log prior) and its gradient w.r.t. the concatenated unconstrained trainables
+    (``data``: the (X, Y) an SVGP's ``training_loss_closure(data)`` was given)."""
+    from .models import SGPR, SVGP
 
-    if isinstance(model, SGPR):
+    if isinstance(model, SVGP):
+        val, g_ls, g_var, g_noise = svgp_elbo_and_grad(model, data if data is not None else model.data)
+    elif isinstance(model, SGPR):
         val, g_ls, g_var, g_noise = sgpr_elbo_and_grad(model)
     else:
         val, g_ls, g_var, g_noise = gpr_lml_and_grad(model)
@@ -359,7 +469,10 @@ def training_loss_and_grad(model) -> Tuple[float, np.ndarray]:
             cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
     for p, g in zip(var, g_var):
         cgrad[id(p)] = np.full(p.numpy().shape, g, dtype=np.float64)
-    cgrad[id(noise)] = np.full(noise.numpy().shape, g_noise, dtype=np.float64)
+    if noise is not None:
+        cgrad[id(noise)] = np.full(noise.numpy().shape, g_noise, dtype=np.float64)
+    if _variational_parameters(model):
+        cgrad.update(model._variational_grads)
     for k, g in zip(model.kernel.kernels, model._base_variance_grad):
         p = _base_variance_parameter(k)
         if p is not None:
@@ -387,9 +500,13 @@ def _assign_unconstrained(params: List[Parameter], u: np.ndarray):
         off += k
 
 
-def optimise(model, method: str = "BFGS", maxiter: int = 1000, **options):
+def optimise(model, method: str = "BFGS", maxiter: int = 1000, data=None, **options):
     """``gpflow.optimizers.Scipy().minimize(model.training_loss_closure(), model.trainable_variables,
-    method="BFGS")`` (oak/model_utils.py:168-175, 410-427) on the unconstrained variables."""
+    method="BFGS")`` (oak/model_utils.py:168-175, 410-427) on the unconstrained variables.  ``model`` may be
+    an ``SVGP.training_loss_closure(data)``, or an SVGP together with ``data``
+    (examples/uci/uci_classification_train.py:119-124)."""
+    if callable(model) and hasattr(model, "model"):
+        model, data = model.model, model.data
     from scipy.optimize import minimize
 
     params = trainable_parameters(model)
@@ -398,7 +515,7 @@ def optimise(model, method: str = "BFGS", maxiter: int = 1000, **options):
     def fun(u):
         _assign_unconstrained(params, u)
         try:
-            return training_loss_and_grad(model)
+            return training_loss_and_grad(model, data)
         except (RuntimeError, _cabi.OakNativeError) as exc:
             # a line-search trial point whose Kuu / K + noise I is not numerically positive definite:
             # report a huge loss so that the step is shortened (gpflow's Scipy wrapper would abort here)

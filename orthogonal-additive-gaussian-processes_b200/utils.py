@@ -15,9 +15,9 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _cabi, _device
-from ._gpflow_shim import scalar_of, value_of
+from ._gpflow_shim import DEFAULT_JITTER, scalar_of, value_of
 from .input_measures import EmpiricalMeasure, MOGMeasure
-from .models import GPR, SGPR
+from .models import GPR, SGPR, SVGP
 from .oak_kernel import KernelComponenent, OAKKernel, get_list_representation
 from .ortho_binary_kernel import OrthogonalBinary
 from .ortho_categorical_kernel import OrthogonalCategorical
@@ -32,6 +32,25 @@ def get_model_sufficient_statistics(m, get_L: bool = True):
     """
     import torch
 
+    if isinstance(m, SVGP):
+        # posterior().alpha = L^-T q_mu; L = chol(inv(Qinv)), Qinv = L^-T (I - diag(q_sqrt^2)) L^-1 (utils.py:174-179,
+        # gpflow 2.2.1 posteriors.py, whitened q); chol raises when some q_sqrt >= 1, as in the reference
+        alpha = m.sufficient_statistics()
+        alpha_h = alpha.reshape(-1, 1).cpu().numpy()
+        if not get_L:
+            return alpha_h
+        Zs = m._Z_device()
+        spec = m.kernel._make_spec()
+        try:
+            Kuu = _device.gram(spec, _device.Points(spec, Zs))
+        finally:
+            spec.close()
+        Kuu.diagonal().add_(DEFAULT_JITTER)
+        Lm = torch.linalg.cholesky(Kuu)
+        s2 = _device.to_device(m.q_sqrt.numpy(), ndim=1).reshape(-1) ** 2
+        Linv = torch.linalg.solve_triangular(Lm, torch.eye(Lm.shape[0], dtype=Lm.dtype, device=Lm.device), upper=False)
+        Qinv = Linv.T @ ((1.0 - s2)[:, None] * Linv)
+        return alpha_h, torch.linalg.cholesky(torch.linalg.inv(Qinv)).cpu().numpy()
     if isinstance(m, SGPR):
         out, alpha, Lbuf, LBbuf, _ = m._statistics(True)
         alpha_h = alpha.reshape(-1, 1).cpu().numpy()
@@ -113,7 +132,7 @@ def compute_sobol_oak(model, delta: float, mu: float,
     num_dims = np.shape(model.data[0])[1]
     selected_dims_oak, kernel_list = get_list_representation(kern, num_dims=num_dims)
     selected_dims_oak = selected_dims_oak[1:]  # skip constant term
-    if isinstance(model, SGPR):
+    if isinstance(model, (SGPR, SVGP)):
         Xc = model._slice_for_kernel(_device.to_device(value_of(model.inducing_variable.Z)))
     else:
         Xc = model._slice_for_kernel(model._device_data()[0])
@@ -169,7 +188,7 @@ def get_prediction_component(m, alpha, X=None, share_var_across_orders: Optional
     subsets = [sorted(int(i) for i in s) for s in selected_dims[1:]]
     if isinstance(m, GPR):
         Xc = m._slice_for_kernel(m._device_data()[0])
-    elif isinstance(m, SGPR):
+    elif isinstance(m, (SGPR, SVGP)):
         Xc = m._slice_for_kernel(_device.to_device(value_of(m.inducing_variable.Z)))
     else:
         raise NotImplementedError

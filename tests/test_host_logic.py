@@ -222,3 +222,38 @@ def test_bench_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_svgp_host_side_contract():
+    """gpflow.models.SVGP stand-in (examples/uci/uci_classification_train.py:108-118): only the reference's
+    configuration is built, the variational parameters start at the prior, the inverse links evaluate on the host."""
+    from oak_b200._gpflow_shim import Bernoulli, Gaussian, inv_logit, inv_probit, set_trainable
+    from oak_b200.models import SVGP
+    from oak_b200.oak_kernel import OAKKernel
+    from oak_b200.ortho_rbf_kernel import RBF
+    from oak_b200.training import trainable_parameters
+
+    k = OAKKernel([RBF] * 2, num_dims=2, max_interaction_depth=2, constrain_orthogonal=True)
+    Z = np.zeros((5, 2))
+    with pytest.raises(NotImplementedError):
+        SVGP(kernel=k, likelihood=Bernoulli(invlink=inv_logit), inducing_variable=Z, whiten=False, q_diag=True)
+    with pytest.raises(NotImplementedError):
+        SVGP(kernel=k, likelihood=Bernoulli(invlink=inv_logit), inducing_variable=Z, whiten=True, q_diag=False)
+    with pytest.raises(NotImplementedError):
+        SVGP(kernel=k, likelihood=Gaussian(), inducing_variable=Z, whiten=True, q_diag=True)
+    with pytest.raises(NotImplementedError):
+        Bernoulli(invlink=lambda x: x)
+    m = SVGP(kernel=k, likelihood=Bernoulli(invlink=inv_logit), inducing_variable=Z, whiten=True, q_diag=True)
+    assert m.q_mu.numpy().shape == (5, 1) and np.all(m.q_mu.numpy() == 0.0)
+    assert np.allclose(m.q_sqrt.numpy(), 1.0) and m.data is None
+    n_before = len(trainable_parameters(m))
+    set_trainable(m.inducing_variable, False)
+    assert len(trainable_parameters(m)) == n_before - 1
+    x = np.array([-50.0, -1.0, 0.0, 2.0, 50.0])
+    assert np.allclose(inv_logit(x), (1.0 / (1.0 + np.exp(-x))) * 0.998 + 1e-3)
+    assert abs(inv_logit(np.array([-800.0]))[0] - 1e-3) < 1e-15  # no overflow
+    from scipy.stats import norm
+
+    assert np.allclose(inv_probit(x), norm.cdf(x) * 0.998 + 1e-3)
+    closure = m.training_loss_closure((np.zeros((3, 2)), np.zeros((3, 1))))
+    assert closure.model is m and closure.data[0].shape == (3, 2)
