@@ -529,6 +529,37 @@ def main():
         except Exception as exc:
             others = {"error": repr(exc)}
 
+    # ---- widening rows: one timed evaluation each, N=1 only -------------------------
+    widening = None
+    if world == 1 and not args.no_elbo:
+        try:
+            from oak_b200._gpflow_shim import Bernoulli, inv_logit
+            from oak_b200.models import SVGP
+            from oak_b200.training import svgp_elbo_and_grad
+
+            widening = {}
+            rng_w = np.random.default_rng(5)
+            nw, dw, mw = 100_000, 10, 200
+            Xw = rng_w.standard_normal((nw, dw))
+            yw = (rng_w.random((nw, 1)) < 1.0 / (1.0 + np.exp(-2.0 * np.sin(Xw[:, :1]) - Xw[:, 1:2]))).astype(np.float64)
+            cw = {"dims": [{"type": "rbf", "lengthscale": 1.0, "variance": 1.0, "measure": ("gaussian", 0.0, 1.0)}] * dw,
+                  "depth": 4, "variances": [1.0] * 5, "share_var": True}
+            sv = SVGP(kernel=build_kernel(cw), likelihood=Bernoulli(invlink=inv_logit), inducing_variable=Xw[:mw].copy(),
+                      whiten=True, q_diag=True)
+            sv.inducing_variable.Z.trainable = False
+            dataw = (_device.to_device(Xw), _device.to_device(yw))
+            ms, _ = timed(lambda: svgp_elbo_and_grad(sv, dataw), reps=3)
+            widening["svgp_bernoulli_elbo_and_gradient_n100000_d10_m200_depth4"] = {"ms": ms}
+            ms, _ = timed(lambda: sv.elbo(dataw), reps=3)
+            widening["svgp_bernoulli_elbo_n100000_d10_m200_depth4"] = {"ms": ms}
+            # normalising-flow objective: one L-BFGS-B iteration = one pass over a resident column
+            xcol = _device.to_device(np.exp(0.5 * rng_w.standard_normal(4_000_000)) + 2.0, ndim=1)
+            ms, _ = timed(lambda: _device.flow_objective(xcol, 0.5, True, [0.1, -0.5, 0.05, 0.0]), reps=5)
+            widening["flow_objective_pass_n4000000"] = {"ms": ms, "points_per_s": 4e6 / (ms * 1e-3)}
+            del xcol, dataw
+        except Exception as exc:
+            widening = {"error": repr(exc)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -552,7 +583,8 @@ def main():
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu,
-            "extra": {"sgpr_elbo": elbo, "other_configs": others, "fp64_peak_slots_per_s": peak_slots},
+            "extra": {"sgpr_elbo": elbo, "other_configs": others, "widening": widening,
+                      "fp64_peak_slots_per_s": peak_slots},
         }
         print(json.dumps(line))
     spec.close()

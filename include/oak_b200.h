@@ -290,6 +290,23 @@ int oak_bernoulli_quadrature_f64(const double* d_mean, const double* d_var, cons
                                  int32_t n_gh, double* d_varexp, double* d_gmean, double* d_gvar,
                                  double* d_logdensity, void* stream);
 
+/* ---- input pipeline: per-column normalising flow (oak/normalising_flow.py) ---------------------
+ * y = sinh((asinh(z) + skewness) * tailweight), z = (u + shift) * scale, u = use_log ? log(x - offset) : x
+ * -- the bijector chain of normalising_flow.py:46-56 with TFP 0.11's SinhArcsinh (setup.py:33).  One strided
+ * column per call (stride in doubles), so the columns of a row-major X are transformed in place in the
+ * layout oak_prepare_points_f64 reads (model_utils.py:179-191 apply_normalise_flow). */
+int oak_flow_forward_f64(const double* d_x, int64_t n, int64_t stride_in, double offset, int32_t use_log,
+                         double shift, double scale, double skewness, double tailweight, double* d_y,
+                         int64_t stride_out, void* stream);
+/* KL_objective (normalising_flow.py:76-81) J = mean(y^2 / 2) - mean(log |dy/dx|) of one column and its
+ * gradient in the optimiser's variables: d_out5 = [J, dJ/d log(scale), dJ/d shift, dJ/d skewness,
+ * dJ/d log(tailweight)] -- what gpflow.optimizers.Scipy (L-BFGS-B) evaluates per iteration
+ * (model_utils.py:313-317).  d_work: oak_flow_objective_work_bytes(n). */
+size_t oak_flow_objective_work_bytes(int64_t n);
+int oak_flow_objective_f64(const double* d_x, int64_t n, int64_t stride, double offset, int32_t use_log,
+                           double log_scale, double shift, double skewness, double log_tailweight,
+                           double* d_out5, void* d_work, void* stream);
+
 /* ---- measurement helpers ----------------------------------------------------------- */
 /* Dependent-chain DFMA microbenchmark: writes achieved FP64 issue slots / second to
  * *h_slots_per_s (1 slot = one DFMA = 2 flop).  This is the measured FP64 roofline peak. */

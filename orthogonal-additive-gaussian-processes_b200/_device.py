@@ -319,6 +319,38 @@ def gram_diag_backward(spec: Spec, px: Points, wscale: float = 1.0, w=None, grad
 
 
 # ---- SGPR / GPR -------------------------------------------------------------------------
+# ---- input pipeline: normalising flow -------------------------------------------------------------
+def flow_forward(x, offset: float, use_log: bool, shift: float, scale: float, skewness: float, tailweight: float,
+                 out=None):
+    """Transforms one (possibly strided) device column; ``out`` defaults to a new contiguous vector."""
+    torch = _torch()
+    assert x.ndim == 1 and x.dtype == torch.float64
+    n = x.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=x.device)
+    assert out.ndim == 1 and out.numel() == n
+    if n > 0:
+        check(_cabi.load().oak_flow_forward_f64(_p(x), n, int(x.stride(0)), float(offset), int(bool(use_log)),
+                                                float(shift), float(scale), float(skewness), float(tailweight),
+                                                _p(out), int(out.stride(0)), C.c_void_p(stream_ptr())),
+              "oak_flow_forward_f64")
+    return out
+
+
+def flow_objective(x, offset: float, use_log: bool, theta, work=None):
+    """[J, dJ/d theta] of the KL objective for theta = (log scale, shift, skewness, log tailweight): NumPy (5,)."""
+    torch = _torch()
+    lib = _cabi.load()
+    n = x.numel()
+    if work is None:
+        work = torch.empty(max(int(lib.oak_flow_objective_work_bytes(n)) // 8, 1), dtype=torch.float64, device=x.device)
+    out = torch.empty(5, dtype=torch.float64, device=x.device)
+    check(lib.oak_flow_objective_f64(_p(x), n, int(x.stride(0)), float(offset), int(bool(use_log)), float(theta[0]),
+                                     float(theta[1]), float(theta[2]), float(theta[3]), _p(out), _p(work),
+                                     C.c_void_p(stream_ptr())), "oak_flow_objective_f64")
+    return out.cpu().numpy()
+
+
 # ---- whitened SVGP / Bernoulli pieces ------------------------------------------------------------
 _GH_CACHE = {}
 

@@ -3,10 +3,10 @@
 Drop-in for the hot-path entry points of the reference's ``oak/model_utils.py``:
 ``create_model_oak`` (:90-176) and ``oak_model.fit / predict / get_sobol`` (:194-524), with the same
 argument names, defaults and error behaviour, the BFGS training step (``training.py``: gradients from
-the backward tiles), ``save_model`` / ``load_model``.  The one-off host-side preprocessing of the
-reference stays on the host: the per-column normalising flow (``normalising_flow.py``, NumPy +
-scipy L-BFGS-B instead of TFP), sklearn k-means for the inducing points and sklearn Gaussian
-mixtures for the MOG measures; plotting is out of scope.
+the backward tiles), ``save_model`` / ``load_model``.  The per-column normalising flow runs on the device
+(``normalising_flow.py`` / csrc/oak_flow.cu: objective passes under scipy L-BFGS-B instead of TFP, forward
+transform); the remaining one-off preprocessing stays on the host as in the reference: sklearn k-means
+for the inducing points and sklearn Gaussian mixtures for the MOG measures; plotting is out of scope.
 """
 from __future__ import annotations
 
@@ -116,15 +116,24 @@ def create_model_oak(
 
 
 def apply_normalise_flow(X, input_flows):
-    """Each column through its flow, untouched where there is none (model_utils.py:179-191)."""
-    X = np.asarray(X, dtype=np.float64)
-    X_scaled = np.zeros(X.shape)
-    for ii in range(X.shape[1]):
-        if input_flows is None or input_flows[ii] is None:
-            X_scaled[:, ii] = X[:, ii]
-        else:
-            X_scaled[:, ii] = input_flows[ii].bijector(X[:, ii])
-    return X_scaled
+    """Each column through its flow, untouched where there is none (model_utils.py:179-191): the matrix goes
+    to the device once and its flowed columns are rewritten in place by ``oak_flow_forward_f64`` (strided
+    columns of the row-major layout the Gram tiles read).  NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor."""
+    from . import _device
+
+    if input_flows is None or all(f is None for f in input_flows):
+        return np.array(X, dtype=np.float64) if _device.is_host(X) else X.clone()
+    host = _device.is_host(X)
+    Xd = _device.to_device(X)
+    if not host:
+        Xd = Xd.clone()
+    for ii in range(Xd.shape[1]):
+        f = input_flows[ii]
+        if f is not None:
+            col = Xd[:, ii]
+            _device.flow_forward(col, f.offset, f.log, float(f.shift.numpy()), float(f.scale.numpy()),
+                                 float(f.skewness.numpy()), float(f.tailweight.numpy()), out=col)
+    return Xd.cpu().numpy() if host else Xd
 
 
 def estimate_one_dim_gmm(K: int, X: np.ndarray) -> MOGMeasure:
@@ -254,7 +263,7 @@ class oak_model:
         flow_dims = [i for i in self.continuous_index
                      if not (self.empirical_measure is not None and i in self.empirical_measure)
                      and self.estimated_gmm_measures[i] is None]  # (:306-311)
-        if self.use_normalising_flow:  # one flow per remaining continuous input (:305-317): host preprocessing
+        if self.use_normalising_flow:  # one flow per remaining continuous input (:305-317), fitted on the device
             from .normalising_flow import Normalizer
 
             for i in flow_dims:

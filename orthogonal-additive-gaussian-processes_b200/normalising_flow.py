@@ -1,7 +1,6 @@
 """One-dimensional normalising flow of the input pipeline (oak/normalising_flow.py:16-85).
 
-Host-side preprocessing, exactly as in the reference (which runs it in TensorFlow on the CPU before
-any kernel is built): each continuous input column is pushed through
+Each continuous input column is pushed through
 
     x -> x - offset -> log -> + shift -> * scale -> SinhArcsinh(skewness, tailweight)
 
@@ -9,14 +8,19 @@ any kernel is built): each continuous input column is pushed through
 when ``log=False``, :54-56) whose four parameters minimise ``KL_objective`` (:76-81) under L-BFGS-B
 (``gpflow.optimizers.Scipy().minimize`` default, model_utils.py:313-317).  ``SinhArcsinh`` follows
 tensorflow_probability 0.11 (the reference's pin, setup.py:33): ``sinh((arcsinh(x) + skewness) *
-tailweight)`` -- later TFP releases add a tail-weight dependent multiplier.  The optimiser path is
-not TensorFlow's, so the fitted parameters agree with the reference's only to optimiser tolerance;
-parity of the hot path is pinned on the post-flow inputs.
+tailweight)`` -- later TFP releases add a tail-weight dependent multiplier.  The O(N) work runs on the
+device (csrc/oak_flow.cu): every L-BFGS-B iteration is one ``oak_flow_objective_f64`` pass over the resident
+column (objective and its four derivatives, deterministic reduction), the forward transform is
+``oak_flow_forward_f64``.  ``inverse`` and ``forward_log_det_jacobian`` (plotting-side utilities on small
+arrays in the reference) are NumPy.  The optimiser path is not TensorFlow's, so the fitted parameters
+agree with the reference's only to optimiser tolerance; parity of the hot path is pinned on the post-flow
+inputs.
 """
 from __future__ import annotations
 
 import numpy as np
 
+from . import _device
 from ._gpflow_shim import Module, Parameter
 
 
@@ -44,9 +48,13 @@ class _Bijector:
         return u, (u + float(o.shift.numpy())) * float(o.scale.numpy())
 
     def forward(self, x):
+        """Device transform of a column: NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out."""
         o = self._o
-        _, z = self._pre(x)
-        return np.sinh((np.arcsinh(z) + float(o.skewness.numpy())) * float(o.tailweight.numpy()))
+        host = _device.is_host(x)
+        xd = _device.to_device(np.asarray(x, dtype=np.float64).reshape(-1) if host else x.reshape(-1), ndim=1)
+        y = _device.flow_forward(xd, o.offset, o.log, float(o.shift.numpy()), float(o.scale.numpy()),
+                                 float(o.skewness.numpy()), float(o.tailweight.numpy()))
+        return y.cpu().numpy().reshape(np.shape(x)) if host else y.reshape(x.shape)
 
     __call__ = forward
 
@@ -74,7 +82,8 @@ class Normalizer(Module):
     """
 
     def __init__(self, x, log=True, **kwargs):
-        self.x = np.asarray(x, dtype=np.float64)
+        self.x = np.asarray(x, dtype=np.float64).reshape(-1)
+        self._xd = None
         self.log = bool(log)
         self.offset = float(np.min(self.x) - 1.0) if self.log else 0.0
         base = np.log(self.x - self.offset) if self.log else self.x
@@ -86,33 +95,28 @@ class Normalizer(Module):
         self.bijector = _Bijector(self)
 
     # ---- objective (:76-81) and its gradient in the unconstrained variables ----------------------
-    def KL_objective(self) -> float:
-        y = self.bijector.forward(self.x)
-        return float(0.5 * np.mean(y * y) - np.mean(self.bijector.forward_log_det_jacobian(self.x)))
+    def _theta(self):
+        return np.array([float(self.scale.unconstrained_variable), float(self.shift.unconstrained_variable),
+                         float(self.skewness.unconstrained_variable), float(self.tailweight.unconstrained_variable)])
+
+    def _device_column(self):
+        if self._xd is None:
+            self._xd = _device.to_device(self.x, ndim=1)
+        return self._xd
 
     def _objective_and_grad(self, theta):
-        """theta = (log scale, shift, skewness, log tailweight)."""
-        ta, b, eps, tt = (float(t) for t in theta)
-        a, tau = np.exp(ta), np.exp(tt)
-        u = np.log(self.x - self.offset) if self.log else self.x
-        z = (u + b) * a
-        w = (np.arcsinh(z) + eps) * tau
-        y = np.sinh(w)
-        n = self.x.shape[0]
-        ldj = np.log(np.cosh(w)) + tt - 0.5 * np.log1p(z * z) + ta - (u if self.log else 0.0)
-        J = 0.5 * np.mean(y * y) - np.mean(ldj)
-        dJdw = (y * np.cosh(w) - np.tanh(w)) / n
-        dJdz = dJdw * tau / np.sqrt(1.0 + z * z) + (z / (1.0 + z * z)) / n
-        g = np.array([np.sum(dJdz * z) - 1.0, np.sum(dJdz) * a, np.sum(dJdw) * tau, np.sum(dJdw * w) - 1.0])
-        return float(J), g
+        """theta = (log scale, shift, skewness, log tailweight): one device pass over the column."""
+        out = _device.flow_objective(self._device_column(), self.offset, self.log, theta)
+        return float(out[0]), out[1:].copy()
+
+    def KL_objective(self) -> float:
+        return self._objective_and_grad(self._theta())[0]
 
     def fit(self, maxiter: int = 1000):
         """``gpflow.optimizers.Scipy().minimize(n.KL_objective, n.trainable_variables)`` (L-BFGS-B)."""
         from scipy.optimize import minimize
 
-        theta0 = np.array([float(self.scale.unconstrained_variable), float(self.shift.unconstrained_variable),
-                           float(self.skewness.unconstrained_variable), float(self.tailweight.unconstrained_variable)])
-        res = minimize(self._objective_and_grad, theta0, jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter))
+        res = minimize(self._objective_and_grad, self._theta(), jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter))
         self.scale.unconstrained_variable = np.asarray(res.x[0])
         self.shift.unconstrained_variable = np.asarray(res.x[1])
         self.skewness.unconstrained_variable = np.asarray(res.x[2])

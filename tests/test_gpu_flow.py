@@ -1,0 +1,96 @@
+"""Input pipeline on the device: the per-column normalising flow
+(oak/normalising_flow.py, model_utils.py:179-191, 305-317) against the NumPy oracle."""
+import numpy as np
+import pytest
+
+from helpers import max_rel_err
+from oracle import flow_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("log", [True, False])
+@pytest.mark.parametrize("n", [1, 257, 100_003])
+def test_flow_objective_and_gradient_match_oracle(log, n):
+    from oak_b200 import _device
+
+    rng = np.random.default_rng(n)
+    x = np.exp(0.5 * rng.standard_normal(n)) + 2.0
+    offset = x.min() - 1.0 if log else 0.0
+    xd = _device.to_device(x, ndim=1)
+    for theta in ([0.0, 0.0, 0.0, 0.0], [0.3, -0.8, 0.2, -0.15], [-0.4, -1.5, -0.3, 0.25]):
+        out = _device.flow_objective(xd, offset, log, theta)
+        J, g = fo.kl_objective_and_grad(x, offset, log, np.array(theta))
+        assert abs(out[0] - J) < 1e-12 * max(1.0, abs(J))
+        assert max_rel_err(out[1:], g) < 1e-11
+
+
+def test_flow_objective_reads_strided_columns():
+    import torch
+
+    from oak_b200 import _device
+
+    rng = np.random.default_rng(1)
+    X = np.exp(0.4 * rng.standard_normal((5000, 3))) + 1.5
+    Xd = _device.to_device(X)
+    for c in range(3):
+        out = _device.flow_objective(Xd[:, c], X[:, c].min() - 1.0, True, [0.1, -0.4, 0.05, 0.0])
+        J, g = fo.kl_objective_and_grad(X[:, c], X[:, c].min() - 1.0, True, np.array([0.1, -0.4, 0.05, 0.0]))
+        assert abs(out[0] - J) < 1e-12 * max(1.0, abs(J)) and max_rel_err(out[1:], g) < 1e-11
+    assert torch.equal(Xd, _device.to_device(X))  # read-only
+
+
+@pytest.mark.parametrize("log", [True, False])
+def test_normalizer_fit_on_device_gaussianises_and_round_trips(log):
+    from scipy import stats
+
+    from oak_b200.normalising_flow import Normalizer
+
+    rng = np.random.default_rng(0)
+    x = np.exp(0.6 * rng.standard_normal(4000)) + 3.0
+    n = Normalizer(x, log=log)
+    j0 = n.KL_objective()
+    res = n.fit()
+    assert n.KL_objective() <= j0 + 1e-12 and np.isfinite(res.fun)
+    # the optimum of the device objective is a stationary point of the oracle's
+    theta = n._theta()
+    J, g = fo.kl_objective_and_grad(x, n.offset, log, theta)
+    assert abs(J - res.fun) < 1e-12 * max(1.0, abs(J)) and np.abs(g).max() < 1e-3
+    y = n.bijector(x)
+    par = (n.offset, log, float(n.shift.numpy()), float(n.scale.numpy()), float(n.skewness.numpy()),
+           float(n.tailweight.numpy()))
+    assert max_rel_err(y, fo.forward(x, *par)) < 1e-13
+    np.testing.assert_allclose(n.bijector.inverse(y), x, rtol=1e-10)
+    if log:
+        assert abs(y.mean()) < 0.05 and abs(y.std() - 1.0) < 0.05
+        assert stats.kstest(y, "norm")[1] > 0.01
+        assert stats.kstest((x - x.mean()) / x.std(), "norm")[1] < 1e-6  # the raw column is far from normal
+
+
+def test_apply_normalise_flow_transforms_columns_in_place_on_the_device():
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.model_utils import apply_normalise_flow
+    from oak_b200.normalising_flow import Normalizer
+
+    rng = np.random.default_rng(2)
+    X = np.exp(0.5 * rng.standard_normal((3000, 4))) + 1.0
+    X[:, 2] = rng.integers(0, 3, 3000)  # a categorical column: no flow
+    flows = [Normalizer(X[:, 0]), None, None, Normalizer(X[:, 3], log=False)]
+    for f in (flows[0], flows[3]):
+        f.fit(maxiter=20)
+    out = apply_normalise_flow(X, flows)
+    assert isinstance(out, np.ndarray) and out.shape == X.shape
+    for c, f in enumerate(flows):
+        if f is None:
+            assert np.array_equal(out[:, c], X[:, c])
+        else:
+            par = (f.offset, f.log, float(f.shift.numpy()), float(f.scale.numpy()), float(f.skewness.numpy()),
+                   float(f.tailweight.numpy()))
+            assert max_rel_err(out[:, c], fo.forward(X[:, c], *par)) < 1e-13
+    Xd = _device.to_device(X)
+    out_d = apply_normalise_flow(Xd, flows)
+    assert out_d.is_cuda and torch.equal(Xd, _device.to_device(X))  # the caller's tensor is left alone
+    assert max_rel_err(out_d.cpu().numpy(), out) == 0.0
+    assert np.array_equal(apply_normalise_flow(X, [None] * 4), X)
