@@ -211,6 +211,11 @@ int oak_sobol_L_f64(const oak_spec* spec, int32_t dim, const double* d_Xcond, in
                     int64_t ldx, double delta, double mu, double* d_L, int64_t ldl,
                     void* d_work, void* stream);
 size_t oak_sobol_L_work_bytes(const oak_spec* spec, int32_t dim, int64_t m);
+/* The four closed-form terms f1..f4 of the Gaussian-measure L (oak/utils.py:116-165, eq. 44-47 of the paper)
+ * on their own, elementwise over n paired points: d_out[k * n + i] = f_{k+1}(x_i, y_i, sigma, lengthscale,
+ * delta, mu), k = 0..3 (f3(x, y) = f2(y, x)).  The same device functions build L in oak_sobol_L_f64. */
+int oak_sobol_gaussian_terms_f64(const double* d_x, const double* d_y, int64_t n, double sigma,
+                                 double lengthscale, double delta, double mu, double* d_out, void* stream);
 /* Replaces the component loop of compute_sobol_oak (oak/utils.py:369-432):
  * out[c] = scale[c] * alpha^T (prod_{d in S_c} L_d) alpha.  d_Lstack: (num_dims x m x m). */
 int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,

@@ -82,6 +82,8 @@ SIGNATURES = {
     "oak_spec_table_layout": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),
     "oak_backward_points_bytes": (_sz, [_vp, _i64]),
     "oak_prepare_backward_f64": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "oak_sobol_gaussian_terms_f64": (C.c_int, [_dp, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double, _dp,
+                                               _vp]),
     "oak_flow_forward_f64": (C.c_int, [_dp, _i64, _i64, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_double,
                                        C.c_double, _dp, _i64, _vp]),
     "oak_flow_objective_work_bytes": (_sz, [_i64]),

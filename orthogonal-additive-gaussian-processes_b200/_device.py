@@ -490,6 +490,18 @@ def sobol_L(spec: Spec, dim: int, Xcond, delta: float, mu: float, out=None):
     return out
 
 
+def sobol_gaussian_terms(x, y, sigma: float, lengthscale: float, delta: float, mu: float):
+    """(4, n) device tensor [f1, f2, f3, f4](x_i, y_i) of oak/utils.py:116-165."""
+    torch = _torch()
+    n = x.numel()
+    assert y.numel() == n and x.is_contiguous() and y.is_contiguous()
+    out = torch.empty((4, n), dtype=torch.float64, device=x.device)
+    check(_cabi.load().oak_sobol_gaussian_terms_f64(_p(x), _p(y), n, float(sigma), float(lengthscale), float(delta),
+                                                    float(mu), _p(out), C.c_void_p(stream_ptr())),
+          "oak_sobol_gaussian_terms_f64")
+    return out
+
+
 def sobol_quadforms(Lstack, subsets: Sequence[Sequence[int]], scale: Sequence[float], alpha):
     torch = _torch()
     nc = len(subsets)

@@ -37,6 +37,17 @@ __device__ __forceinline__ double sobol_f4(double x, double y, double l, double 
          exp(-(xm * xm + ym * ym) / (2.0 * (l2 + d2)));
 }
 
+// the four terms on their own, elementwise over paired (x_i, y_i) with the caller's sigma^4 (utils.py:116-165)
+__global__ void sobol_terms_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, double s4,
+                                   double l, double delta, double mu, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = s4 * sobol_f1(x[i], y[i], l, delta, mu);
+  out[n + i] = s4 * sobol_f2(x[i], y[i], l, delta, mu);
+  out[2 * n + i] = s4 * sobol_f2(y[i], x[i], l, delta, mu);
+  out[3 * n + i] = s4 * sobol_f4(x[i], y[i], l, delta, mu);
+}
+
 // compute_L (utils.py:221-240): L = f1 - f2 - f3 + f4
 __global__ void sobol_L_gaussian_kernel(const double* __restrict__ X, int64_t m, int64_t ldx, int col,
                                         double l, double delta, double mu, double* __restrict__ L,
@@ -150,6 +161,19 @@ extern "C" size_t oak_sobol_L_work_bytes(const oak_spec* spec, int32_t dim, int6
   const DimDev& dd = spec->h_dims[spec->pos_of_orig[dim]];
   if (dd.type == OAK_DIM_RBF && dd.measure == OAK_MEASURE_EMPIRICAL)
     return (size_t)(2 * (int64_t)dd.count * m + 2 * dd.count + 2 * m) * sizeof(double);
+  return 0;
+}
+
+extern "C" int oak_sobol_gaussian_terms_f64(const double* d_x, const double* d_y, int64_t n, double sigma,
+                                            double lengthscale, double delta, double mu, double* d_out,
+                                            void* stream_) {
+  OAK_REQUIRE(d_x && d_y && d_out, "oak_sobol_gaussian_terms_f64: null argument");
+  OAK_REQUIRE(lengthscale > 0.0, "oak_sobol_gaussian_terms_f64: lengthscale must be positive");
+  if (n <= 0) return 0;
+  const double s2 = sigma * sigma;
+  sobol_terms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(d_x, d_y, n, s2 * s2, lengthscale,
+                                                                                    delta, mu, d_out);
+  OAK_LAUNCHED();
   return 0;
 }
 

@@ -316,13 +316,11 @@ class oak_model:
                                       "initialise_inducing_points=False") from exc
         if (p0 is None) and (p is None):
             return KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs).cluster_centers_
-        Z = np.zeros([self.num_inducing, Xs.shape[1]])
-        for index in self.binary_index + self.categorical_index:
-            km = KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs[:, index][:, None])
-            Z[:, index] = km.cluster_centers_.astype(int)[:, 0]
-        km = KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs[:, self.continuous_index])
-        Z[:, self.continuous_index] = km.cluster_centers_
-        return Z
+        from .utils import initialize_kmeans_with_categorical
+
+        return initialize_kmeans_with_categorical(Xs, binary_index=self.binary_index,
+                                                  categorical_index=self.categorical_index,
+                                                  continuous_index=self.continuous_index, n_clusters=self.num_inducing)
 
     def _transform_x(self, X):
         X = apply_normalise_flow(np.asarray(X, dtype=np.float64), self.input_flows)

@@ -72,6 +72,57 @@ def get_model_sufficient_statistics(m, get_L: bool = True):
     raise NotImplementedError
 
 
+# ---- closed forms of the Gaussian-measure L (utils.py:116-165): eq. (44)-(47) of the paper -------------
+def _sobol_term(k: int, x, y, sigma, lengthscales, delta, mu):
+    """Elementwise over broadcast (x, y); evaluated by the device functions that also build ``compute_L``."""
+    host = _device.is_host(x) and _device.is_host(y)
+    xb, yb = np.broadcast_arrays(np.asarray(value_of(x), dtype=np.float64), np.asarray(value_of(y), dtype=np.float64)) \
+        if host else (x, y)
+    xd = _device.to_device(np.ascontiguousarray(xb).reshape(-1) if host else xb.reshape(-1), ndim=1)
+    yd = _device.to_device(np.ascontiguousarray(yb).reshape(-1) if host else yb.reshape(-1), ndim=1)
+    out = _device.sobol_gaussian_terms(xd, yd, float(sigma), float(lengthscales), float(delta), float(mu))[k]
+    return out.cpu().numpy().reshape(np.shape(xb)) if host else out.reshape(xb.shape)
+
+
+def f1(x, y, sigma, lengthscales, delta, mu):
+    return _sobol_term(0, x, y, sigma, lengthscales, delta, mu)
+
+
+def f2(x, y, sigma, lengthscales, delta, mu):
+    return _sobol_term(1, x, y, sigma, lengthscales, delta, mu)
+
+
+def f3(x, y, sigma, lengthscales, delta, mu):
+    return _sobol_term(2, x, y, sigma, lengthscales, delta, mu)
+
+
+def f4(x, y, sigma, lengthscales, delta, mu):
+    return _sobol_term(3, x, y, sigma, lengthscales, delta, mu)
+
+
+# ---- k-means inducing points with discrete columns (utils.py:533-574): sklearn on the host, as the reference ----
+def initialize_kmeans_with_binary(X, binary_index: list, continuous_index: Optional[list] = None,
+                                  n_clusters: Optional[int] = 200) -> np.ndarray:
+    """One k-means per binary column (centres truncated to integers) and one over the continuous block."""
+    from sklearn.cluster import KMeans
+
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.zeros([n_clusters, X.shape[1]])
+    for index in binary_index:
+        km = KMeans(n_clusters=n_clusters, random_state=0).fit(X[:, index][:, None])
+        Z[:, index] = km.cluster_centers_.astype(int)[:, 0]
+    if continuous_index is not None:
+        km = KMeans(n_clusters=n_clusters, random_state=0).fit(X[:, continuous_index])
+        Z[:, continuous_index] = km.cluster_centers_
+    return Z
+
+
+def initialize_kmeans_with_categorical(X, binary_index: list, categorical_index: list, continuous_index: list,
+                                       n_clusters: Optional[int] = 200) -> np.ndarray:
+    """The same with categorical columns treated like the binary ones (:555-574)."""
+    return initialize_kmeans_with_binary(X, list(binary_index) + list(categorical_index), continuous_index, n_clusters)
+
+
 # ---- single L matrices (same call signatures as the reference) -----------------------------
 def _L_single(dim_spec, Xcol, delta, mu):
     spec = _cabi.Spec([dim_spec], 1, [0.0, 1.0], True, stream=_device.stream_ptr())

@@ -282,3 +282,32 @@ def test_sgpr_predict_mean_matches_predict_f_and_oracle():
     want = oo.sgpr_predict_mean(ref, cfg["X"], cfg["y"], cfg["Z"], cfg["noise"], Xnew)
     assert max_rel_err(mean, mean_f) < 1e-10
     assert max_rel_err(mean, want) < 1e-6
+
+
+def test_sobol_closed_form_terms_match_oracle_and_monte_carlo():
+    """f1..f4 (oak/utils.py:116-165) evaluated by the device functions that build compute_L: against the NumPy
+    oracle to rounding, and -- as the reference's tests/test_sobol.py:34-140 do -- against a Monte-Carlo estimate
+    of the integrals they stand for (f1 = E_s[k(x,s) k(s,y)], f4 = E_s[k(x,s)] E_s'[k(s',y)] c, ...)."""
+    from oak_b200 import utils
+    from oracle import oak_oracle as oo
+
+    rng = np.random.default_rng(3)
+    x, y = rng.standard_normal(500), rng.standard_normal(500)
+    sigma, l, delta, mu = 1.3, 0.8, 1.5, 0.4
+    for name in ("f1", "f2", "f4"):
+        got = getattr(utils, name)(x, y, sigma, l, delta, mu)
+        assert max_rel_err(got, getattr(oo, name)(x, y, sigma, l, delta, mu)) < 1e-13
+    assert max_rel_err(utils.f3(x, y, sigma, l, delta, mu), oo.f2(y, x, sigma, l, delta, mu)) < 1e-13
+    assert utils.f1(x[:6].reshape(2, 3), y[:6].reshape(2, 3), sigma, l, delta, mu).shape == (2, 3)
+    # Monte Carlo: f1(x, y) = E_{s ~ N(mu, delta^2)}[k(x, s) k(s, y)] with k the RBF of variance sigma^2
+    s = mu + delta * rng.standard_normal(400_000)
+    k = lambda a, b: sigma ** 2 * np.exp(-0.5 * (a - b) ** 2 / l ** 2)
+    for i in range(3):
+        mc = np.mean(k(x[i], s) * k(s, y[i]))
+        assert abs(float(utils.f1(x[i], y[i], sigma, l, delta, mu)) - mc) < 5e-3 * sigma ** 4
+    # L = f1 - f2 - f3 + f4 is what compute_L returns (utils.py:221-240)
+    X = np.stack([x[:40], y[:40]], axis=1)
+    L = utils.compute_L(X, l, sigma ** 2, 0, delta, mu)
+    xi, xj = np.meshgrid(X[:, 0], X[:, 0], indexing="ij")
+    want = sum(sgn * getattr(utils, f)(xi, xj, sigma, l, delta, mu) for f, sgn in (("f1", 1), ("f2", -1), ("f3", -1), ("f4", 1)))
+    assert max_rel_err(L, want) < 1e-12

@@ -258,3 +258,25 @@ def test_svgp_host_side_contract():
     assert np.allclose(inv_probit(x), norm.cdf(x) * 0.998 + 1e-3)
     closure = m.training_loss_closure((np.zeros((3, 2)), np.zeros((3, 1))))
     assert closure.model is m and closure.data[0].shape == (3, 2)
+
+
+@pytest.mark.parametrize("binary_index", [[0, 1, 2], [0, 2], [1]])
+@pytest.mark.parametrize("n_cluster", [1, 20])
+def test_kmeans_inducing_points_with_binary_columns(binary_index, n_cluster):
+    """initialize_kmeans_with_binary / _categorical (oak/utils.py:533-574; reference tests/test_utils.py:17-40):
+    host sklearn calls with the reference's seeds; binary columns come back as integers."""
+    from oak_b200.utils import initialize_kmeans_with_binary, initialize_kmeans_with_categorical
+
+    rng = np.random.RandomState(44)
+    cont = sorted(set(range(3)) - set(binary_index))
+    X = np.zeros((100, 3))
+    for i in binary_index:
+        X[:, i] = rng.binomial(1, 0.33, 100)
+    for j in cont:
+        X[:, j] = rng.normal(0, 4, 100)
+    Z = initialize_kmeans_with_binary(X, binary_index, cont if cont else None, n_cluster)
+    assert isinstance(Z, np.ndarray) and Z.shape == (n_cluster, 3)
+    assert set(np.unique(Z[:, binary_index])) <= {0.0, 1.0}
+    if cont and len(binary_index) == 1:
+        Zc = initialize_kmeans_with_categorical(X, [], binary_index, cont, n_cluster)
+        np.testing.assert_array_equal(Zc, Z)
