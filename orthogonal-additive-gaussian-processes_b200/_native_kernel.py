@@ -4,7 +4,6 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
-import numpy as np
 
 from . import _cabi, _device
 from ._cabi import DimSpec

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _cabi, _device
 from ._cabi import DimSpec
-from ._gpflow_shim import Parameter, positive, scalar_of, value_of
+from ._gpflow_shim import Parameter, positive, scalar_of
 from ._native_kernel import NativeKernel
 from .input_measures import EmpiricalMeasure, GaussianMeasure, Measure, MOGMeasure, UniformMeasure
 

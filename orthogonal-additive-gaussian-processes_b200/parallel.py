@@ -8,7 +8,6 @@ exactly one exchange for the SGPR bound: the packed statistics ``Phi | Kuf y | s
 """
 from __future__ import annotations
 
-import os
 from typing import List, Tuple
 
 TILE = 64  # row ranges handed to oak_gram_f64 must start on a tile boundary

@@ -1,7 +1,7 @@
 """A/B timing of the backward tiles at config C's chunk shape (development aid): plain backward, backward with
 row-point gradients, and the full SGPR training step with fixed / trainable inducing points.
 usage: [OAK_B200_LIB=scripts/ubench/liboak_<variant>.so] python scripts/ab_backward.py"""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from oak_b200 import _device
