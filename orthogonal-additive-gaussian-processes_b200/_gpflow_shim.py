@@ -155,24 +155,49 @@ def set_trainable(obj, flag: bool):
 
 
 def collect_parameters(obj, _seen=None) -> List[Parameter]:
-    """Depth-first parameter discovery over attributes, lists and tuples (tf.Module-like)."""
+    """Parameter discovery in ``tf.Module._flatten`` order, which is the order of gpflow's ``parameters`` /
+    ``trainable_parameters`` and therefore of the ``hyperparams`` array in the reference's checkpoints
+    (oak/model_utils.py:44-87): attributes in sorted-name order, lists / tuples / dicts flattened in place,
+    a module's own Parameters first ("walk direct properties first then recurse"), then its sub-modules in the
+    order they were met, each visited once."""
     if _seen is None:
         _seen = set()
-    out: List[Parameter] = []
-    if id(obj) in _seen:
-        return out
-    _seen.add(id(obj))
     if isinstance(obj, Parameter):
+        if id(obj) in _seen:
+            return []
+        _seen.add(id(obj))
         return [obj]
-    if isinstance(obj, (list, tuple)):
-        for o in obj:
-            out += collect_parameters(o, _seen)
-        return out
+    out: List[Parameter] = []
+    submodules: list = []
+
+    def leaves(value):
+        if isinstance(value, (list, tuple)):
+            for v in value:
+                yield from leaves(v)
+        elif isinstance(value, dict):
+            for k in sorted(value):
+                yield from leaves(value[k])
+        else:
+            yield value
+
+    roots = vars(obj) if isinstance(obj, Module) else {"": obj} if isinstance(obj, (list, tuple, dict)) else {}
     if isinstance(obj, Module):
-        for key in sorted(vars(obj)):
-            if key.startswith("_"):
+        _seen.add(id(obj))
+    for key in sorted(roots):
+        if key.startswith("_"):
+            continue
+        for leaf in leaves(roots[key]):
+            if id(leaf) in _seen:
                 continue
-            out += collect_parameters(getattr(obj, key), _seen)
+            if isinstance(leaf, Parameter):
+                _seen.add(id(leaf))
+                out.append(leaf)
+            elif isinstance(leaf, Module):
+                _seen.add(id(leaf))
+                submodules.append(leaf)
+    for sub in submodules:
+        _seen.discard(id(sub))  # visited below; the mark above only de-duplicates the queue
+        out += collect_parameters(sub, _seen)
     return out
 
 

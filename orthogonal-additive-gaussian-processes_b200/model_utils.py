@@ -32,14 +32,18 @@ def get_kmeans_centers(X: np.ndarray, K: int = 500) -> np.ndarray:
 
 
 def save_model(model, filename) -> None:
-    """Trainable parameter values, in ``model.trainable_parameters`` order, as one object array in an
-    ``.npz`` (model_utils.py:44-63; SVGP, which saves all parameters, is not on this path)."""
+    """Parameter values as one object array ``hyperparams`` in an ``.npz`` (model_utils.py:44-63): the trainable
+    ones in ``model.trainable_parameters`` order (gpflow's tf.Module order, reproduced by
+    ``_gpflow_shim.collect_parameters``), all of them for an SVGP."""
     import os
     from pathlib import Path
 
+    from .models import SVGP
+
     filename = Path(filename)
-    hyperparams = np.empty(len(model.trainable_parameters), dtype=object)
-    for i, p in enumerate(model.trainable_parameters):
+    params = model.parameters if isinstance(model, SVGP) else model.trainable_parameters
+    hyperparams = np.empty(len(params), dtype=object)
+    for i, p in enumerate(params):
         hyperparams[i] = p.numpy()
     os.makedirs(filename.parents[0], exist_ok=True)
     np.savez(filename, hyperparams=hyperparams)

@@ -133,7 +133,9 @@ def test_training_loss_gradient_and_bfgs_improve_the_bound():
     # expected: autograd of the ELBO, prior gradient, softplus chain (initial values: l = 1, sigma2 = 1, noise = 0.01)
     v, a_ls, a_var, a_noise = go.value_and_grad(go.sgpr_elbo, X, y, Z, np.ones(3), np.ones(3), 0.01)
     sp = lambda x, lower=0.0: 1.0 - np.exp(-(x - lower))  # d softplus / du at softplus(u) + lower = x
-    want = np.concatenate([-a_ls * sp(1.0), -(a_var - 0.2) * sp(1.0), [-a_noise * sp(0.01, 1e-6)]])
+    # gpflow's (tf.Module) parameter order: the kernel's own order variances, then the sub-kernels, then the likelihood
+    assert params[0] is model.kernel.variances[0] and params[-1] is model.likelihood.variance
+    want = np.concatenate([-(a_var - 0.2) * sp(1.0), -a_ls * sp(1.0), [-a_noise * sp(0.01, 1e-6)]])
     assert max_rel_err(g, want) < 1e-7
     res = optimise(model, method="BFGS", maxiter=15)
     assert model.training_loss() < loss0 - 1.0

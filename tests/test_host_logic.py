@@ -280,3 +280,36 @@ def test_kmeans_inducing_points_with_binary_columns(binary_index, n_cluster):
     if cont and len(binary_index) == 1:
         Zc = initialize_kmeans_with_categorical(X, [], binary_index, cont, n_cluster)
         np.testing.assert_array_equal(Zc, Z)
+
+
+def test_parameter_order_is_gpflows_and_checkpoints_follow_it(tmp_path):
+    """The reference's checkpoints are positional (``hyperparams[i]`` <-> ``model.trainable_parameters[i]``,
+    oak/model_utils.py:44-87), so the traversal order must be gpflow's: tf.Module walks attributes in sorted
+    order, yields a module's own Parameters first and recurses into its sub-modules afterwards.  For an SGPR on
+    an OAK kernel that is: inducing points, order variances, per sub-kernel (lengthscales, variance), noise.
+    An SVGP's own q_mu / q_sqrt precede every sub-module, and all its parameters are saved (:53-56)."""
+    from oak_b200._gpflow_shim import Bernoulli, inv_logit, set_trainable
+    from oak_b200.model_utils import create_model_oak, load_model, save_model
+    from oak_b200.models import SVGP
+
+    rng = np.random.default_rng(1)
+    X, y = rng.standard_normal((20, 2)), rng.standard_normal((20, 1))
+    m = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=X[:4].copy(), zfixed=False)
+    k = m.kernel
+    want = [m.inducing_variable.Z, *k.variances, k.kernels[0].base_kernel.lengthscales,
+            k.kernels[1].base_kernel.lengthscales, m.likelihood.variance]
+    got = list(m.trainable_parameters)
+    assert len(got) == len(want) and all(a is b for a, b in zip(got, want))
+    s = SVGP(kernel=k, likelihood=Bernoulli(invlink=inv_logit), inducing_variable=X[:4].copy(), whiten=True, q_diag=True)
+    set_trainable(s.inducing_variable, False)
+    allp = list(s.parameters)
+    assert allp[0] is s.q_mu and allp[1] is s.q_sqrt and allp[2] is s.inducing_variable.Z and allp[3] is k.variances[0]
+    s.q_mu.assign(rng.standard_normal((4, 1)))
+    f = tmp_path / "svgp.npz"
+    save_model(s, f)
+    assert len(np.load(str(f), allow_pickle=True)["hyperparams"]) == len(allp)  # all parameters, fixed Z included
+    s2 = SVGP(kernel=k, likelihood=Bernoulli(invlink=inv_logit), inducing_variable=np.zeros((4, 2)), whiten=True,
+              q_diag=True)
+    load_model(s2, f, load_all_parameters=True)
+    np.testing.assert_allclose(s2.q_mu.numpy(), s.q_mu.numpy())
+    np.testing.assert_allclose(s2.inducing_variable.Z.numpy(), X[:4])
