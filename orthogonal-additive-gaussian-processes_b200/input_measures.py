@@ -11,45 +11,51 @@ from typing import Optional
 import numpy as np
 
 
+def _weights_sum_to_one(weights: np.ndarray, what: str) -> np.ndarray:
+    weights = np.asarray(weights)
+    total = weights.sum()
+    if not np.isclose(total, 1.0, atol=1e-6):
+        raise AssertionError(f"{what} {total}")  # the reference asserts
+    return weights
+
+
 class Measure:
-    pass
-
-
-class UniformMeasure(Measure):
-    """Uniform(a, b) input density."""
-
-    def __init__(self, a: float, b: float):
-        self.a, self.b = a, b
+    """Base class; the kernels dispatch on the concrete type."""
 
 
 class GaussianMeasure(Measure):
     """N(mu, var) input density."""
 
     def __init__(self, mu: float, var: float):
-        self.mu, self.var = mu, var
+        self.mu = mu
+        self.var = var
 
 
-class EmpiricalMeasure(Measure):
-    """Weighted Dirac measure on ``location`` (M,1); weights default to 1/M and must sum to 1."""
+class UniformMeasure(Measure):
+    """Uniform(a, b) input density."""
 
-    def __init__(self, location: np.ndarray, weights: Optional[np.ndarray] = None):
-        location = np.asarray(location)
-        self.location = location
-        if weights is None:
-            weights = np.full((location.shape[0], 1), 1.0 / len(location))
-        weights = np.asarray(weights)
-        if not np.isclose(weights.sum(), 1.0, atol=1e-6):
-            raise AssertionError(f"not close to 1 {weights.sum()}")
-        self.weights = weights
+    def __init__(self, a: float, b: float):
+        self.a = a
+        self.b = b
 
 
 class MOGMeasure(Measure):
-    """Mixture of K one-dimensional Gaussians."""
+    """Mixture of K one-dimensional Gaussians: vectors ``means``, ``variances``, ``weights`` of length K."""
 
     def __init__(self, means: np.ndarray, variances: np.ndarray, weights: np.ndarray):
-        means, variances, weights = np.asarray(means), np.asarray(variances), np.asarray(weights)
-        if not (means.ndim == variances.ndim == weights.ndim == 1 and len(means) == len(variances) == len(weights)):
+        parts = [np.asarray(v) for v in (means, variances, weights)]
+        if any(v.ndim != 1 for v in parts) or len({len(v) for v in parts}) != 1:
             raise ValueError("means, variances and weights must be vectors of one common length K")
-        if not np.isclose(weights.sum(), 1.0, atol=1e-6):
-            raise AssertionError(f"Weights not close to 1 {weights.sum()}")
-        self.means, self.variances, self.weights = means.astype(float), variances.astype(float), weights
+        self.weights = _weights_sum_to_one(parts[2], "Weights not close to 1")
+        self.means = parts[0].astype(float)
+        self.variances = parts[1].astype(float)
+
+
+class EmpiricalMeasure(Measure):
+    """Weighted Dirac measure on ``location`` (M, 1); weights default to 1/M and must sum to 1."""
+
+    def __init__(self, location: np.ndarray, weights: Optional[np.ndarray] = None):
+        self.location = np.asarray(location)
+        m = self.location.shape[0]
+        self.weights = _weights_sum_to_one(np.full((m, 1), 1.0 / m) if weights is None else weights,
+                                           "not close to 1")
