@@ -4,8 +4,11 @@ imported by the product).
 oak/normalising_flow.py:46-56 chains tfb.Shift(-offset) -> Log -> Shift -> Scale -> SinhArcsinh (without the
 first two when log=False); SinhArcsinh follows tensorflow_probability 0.11 (setup.py:33):
 ``sinh((arcsinh(x) + skewness) * tailweight)``.  KL_objective (:76-81) is
-``mean(y^2 / 2) - mean(forward_log_det_jacobian(x))``.  TensorFlow / TFP are not installed in this image, so
-parity with a TFP run is unpinned; the functions below are pinned on identities in tests/ (analytic gradient
+``mean(y^2 / 2) - mean(forward_log_det_jacobian(x))``.  Pinned (tests/golden/g8_normalising_flow.npz) against
+the reference's own ``Normalizer`` executed over oracle/tf_shim: chain order, offset, standardiser
+initialisation and KL_objective are the reference's code; the individual TFP 0.11 bijectors (Shift, Log, Scale,
+SinhArcsinh and their log-det-Jacobians) are the shim's restatement of the published formulas, since
+TensorFlow / TFP are not installable here -- that part is pinned only on identities in tests/ (analytic gradient
 vs central differences, log-det-Jacobian vs a numerical derivative, forward/inverse round trip)."""
 import numpy as np
 

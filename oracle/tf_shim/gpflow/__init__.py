@@ -379,7 +379,12 @@ kernels = _mod("gpflow.kernels", Kernel=Kernel, RBF=RBF, SquaredExponential=Squa
 utilities = _mod("gpflow.utilities", positive=positive, to_default_float=to_default_float,
                  print_summary=print_summary, set_trainable=set_trainable)
 config = _mod("gpflow.config", default_float=default_float, default_jitter=default_jitter)
-base = _mod("gpflow.base", Parameter=Parameter)
+class _BaseModule(Module):
+    def __init__(self, name=None):
+        pass
+
+
+base = _mod("gpflow.base", Parameter=Parameter, Module=_BaseModule)
 inducing_variables = _mod("gpflow.inducing_variables", InducingPoints=InducingPoints)
 _tm = _mod("gpflow.models.training_mixins", RegressionData=tuple)
 models = _mod("gpflow.models", GPR=GPR, SGPR=SGPR, SVGP=SVGP, GPModel=GPModel, BayesianModel=BayesianModel,

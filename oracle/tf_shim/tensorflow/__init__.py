@@ -115,6 +115,10 @@ def reduce_sum(x, axis=None, keepdims=False):
     return np.sum(_a(x), axis=axis, keepdims=keepdims)
 
 
+def reduce_mean(x, axis=None):
+    return _w(np.mean(_a(x), axis=axis))
+
+
 def reduce_prod(x, axis=None):
     return np.prod(np.asarray(x), axis=axis)
 

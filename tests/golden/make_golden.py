@@ -256,6 +256,31 @@ def main():
     save("g7_empirical_sobol", cfg_from_kernel(kk), X=Xe, Y=Ye, Z=Xe[:20].copy(), noise=np.array(0.01), alpha=alpha,
          sobol=np.array(sobol), restated_objective=np.array(model.elbo()))
 
+    # --- G8: the normalising flow as written in oak/normalising_flow.py (bijector chain and KL_objective are the
+    # reference's; the individual TFP 0.11 bijectors are the shim's restatement) ----------------------------------
+    from oak.normalising_flow import Normalizer
+
+    xs = np.exp(0.6 * rng.standard_normal(64)) + 3.0
+    out = {"x": xs}
+    for tag, log in (("log", True), ("nolog", False)):
+        nz = Normalizer(xs, log=log)
+        sas, scale, shift = nz.bijector.bijectors[0], nz.bijector.bijectors[1], nz.bijector.bijectors[2]
+        for step, bump in enumerate(([0.0, 0.0, 0.0, 0.0], [0.2, -0.3, 0.25, -0.1], [-0.3, 0.4, -0.2, 0.3])):
+            # (log scale, shift, skewness, log tailweight) moved away from the initial standardiser
+            if step:
+                scale.scale.assign(float(scale.scale.numpy()) * np.exp(bump[0]))
+                shift.shift.assign(float(shift.shift.numpy()) + bump[1])
+                sas.skewness.assign(bump[2])
+                sas.tailweight.assign(np.exp(bump[3]))
+            out[f"{tag}_theta_{step}"] = np.array([np.log(float(scale.scale.numpy())), float(shift.shift.numpy()),
+                                                  float(sas.skewness.numpy()), np.log(float(sas.tailweight.numpy()))])
+            out[f"{tag}_y_{step}"] = np.asarray(nz.bijector(xs))
+            out[f"{tag}_ldj_{step}"] = np.asarray(nz.bijector.forward_log_det_jacobian(xs, event_ndims=0))
+            out[f"{tag}_J_{step}"] = np.array(float(nz.KL_objective()))
+        out[f"{tag}_x_back"] = np.asarray(nz.bijector.inverse(nz.bijector(xs)))
+    save("g8_normalising_flow", {"note": "oak/normalising_flow.py Normalizer over oracle/tf_shim (TFP 0.11 bijectors restated)"},
+         **out)
+
 
 if __name__ == "__main__":
     main()

@@ -75,3 +75,37 @@ def test_oracle_empirical_sobol_matches_reference():
     assert max_rel_err(sob, g["sobol"]) < 1e-10
     assert max_rel_err(oo.sgpr_alpha(ref, g["X"], g["Y"], g["Z"], float(g["noise"])), g["alpha"]) < 1e-6
     assert abs(oo.sgpr_elbo(ref, g["X"], g["Y"], g["Z"], float(g["noise"])) - float(g["restated_objective"])) < 1e-7 * abs(float(g["restated_objective"]))
+
+
+def test_flow_oracle_matches_the_references_normalizer():
+    """g8: oak/normalising_flow.py's own Normalizer (bijector chain order, offset, standardiser initialisation,
+    KL_objective) executed over the TF/TFP shim, at the initial and two perturbed parameter settings, with and
+    without the log step: oracle/flow_oracle.py reproduces y, log|dy/dx| and J; the product's host-side inverse
+    round-trips."""
+    import os
+
+    from oak_b200.normalising_flow import Normalizer
+    from oracle import flow_oracle as fo
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g8_normalising_flow.npz"))
+    x = g["x"]
+    for tag, log in (("log", True), ("nolog", False)):
+        nz = Normalizer(x, log=log)
+        offset = x.min() - 1.0 if log else 0.0
+        assert nz.offset == offset
+        # the product initialises the standardiser exactly as the reference does (:23-27)
+        th0 = g[f"{tag}_theta_0"]
+        np.testing.assert_allclose(nz._theta(), th0, rtol=1e-14, atol=1e-15)
+        for step in range(3):
+            th = g[f"{tag}_theta_{step}"]
+            par = (offset, log, th[1], np.exp(th[0]), th[2], np.exp(th[3]))
+            np.testing.assert_allclose(fo.forward(x, *par), g[f"{tag}_y_{step}"], rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(fo.forward_log_det_jacobian(x, *par), g[f"{tag}_ldj_{step}"], rtol=1e-13, atol=1e-14)
+            J = fo.kl_objective_and_grad(x, offset, log, th)[0]
+            assert abs(J - float(g[f"{tag}_J_{step}"])) < 1e-13 * max(1.0, abs(J))
+        th = g[f"{tag}_theta_2"]
+        for prm, v in zip((nz.scale, nz.shift, nz.skewness, nz.tailweight), th):
+            prm.unconstrained_variable = np.asarray(v)
+        np.testing.assert_allclose(nz.bijector.inverse(g[f"{tag}_y_2"]), x, rtol=1e-11)
+        np.testing.assert_allclose(nz.bijector.forward_log_det_jacobian(x), g[f"{tag}_ldj_2"], rtol=1e-13, atol=1e-14)
+        np.testing.assert_allclose(g[f"{tag}_x_back"], x, rtol=1e-11)

@@ -94,3 +94,23 @@ def test_apply_normalise_flow_transforms_columns_in_place_on_the_device():
     assert out_d.is_cuda and torch.equal(Xd, _device.to_device(X))  # the caller's tensor is left alone
     assert max_rel_err(out_d.cpu().numpy(), out) == 0.0
     assert np.array_equal(apply_normalise_flow(X, [None] * 4), X)
+
+
+def test_device_flow_matches_the_references_normalizer_golden():
+    """g8 (the reference's own Normalizer over the TF/TFP shim): the device transform and objective at the initial
+    and the perturbed parameter settings."""
+    import os
+
+    from oak_b200 import _device
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "g8_normalising_flow.npz"))
+    x = g["x"]
+    xd = _device.to_device(x, ndim=1)
+    for tag, log in (("log", True), ("nolog", False)):
+        offset = x.min() - 1.0 if log else 0.0
+        for step in range(3):
+            th = g[f"{tag}_theta_{step}"]
+            y = _device.flow_forward(xd, offset, log, th[1], np.exp(th[0]), th[2], np.exp(th[3])).cpu().numpy()
+            assert max_rel_err(y, g[f"{tag}_y_{step}"]) < 1e-13
+            J = _device.flow_objective(xd, offset, log, th)[0]
+            assert abs(J - float(g[f"{tag}_J_{step}"])) < 1e-12 * max(1.0, abs(J))
