@@ -117,6 +117,7 @@ class Normalizer(Module):
         from scipy.optimize import minimize
 
         res = minimize(self._objective_and_grad, self._theta(), jac=True, method="L-BFGS-B", options=dict(maxiter=maxiter))
+        self._xd = None  # the device copy of the column is only needed while fitting
         self.scale.unconstrained_variable = np.asarray(res.x[0])
         self.shift.unconstrained_variable = np.asarray(res.x[1])
         self.skewness.unconstrained_variable = np.asarray(res.x[2])

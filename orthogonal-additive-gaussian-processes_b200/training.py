@@ -457,7 +457,10 @@ def training_loss_and_grad(model, data=None) -> Tuple[float, np.ndarray]:
     from .models import SGPR, SVGP
 
     if isinstance(model, SVGP):
-        val, g_ls, g_var, g_noise = svgp_elbo_and_grad(model, data if data is not None else model.data)
+        data = data if data is not None else model.data
+        if data is None:
+            raise ValueError("an SVGP holds no data: pass (X, Y) or use model.training_loss_closure((X, Y))")
+        val, g_ls, g_var, g_noise = svgp_elbo_and_grad(model, data)
     elif isinstance(model, SGPR):
         val, g_ls, g_var, g_noise = sgpr_elbo_and_grad(model)
     else:
