@@ -281,6 +281,16 @@ def main():
     save("g8_normalising_flow", {"note": "oak/normalising_flow.py Normalizer over oracle/tf_shim (TFP 0.11 bijectors restated)"},
          **out)
 
+    # --- G9: full interaction depth (config A's shape: D = 8, depth 8), where Newton-Girard cancels the most ----
+    D = 8
+    X9, X92 = rng.standard_normal((30, D)), rng.standard_normal((11, D))
+    k9 = OAKKernel([gpflow.kernels.RBF] * D, num_dims=D, max_interaction_depth=D, constrain_orthogonal=True)
+    for sub, l in zip(k9.kernels, rng.uniform(0.5, 2.5, D)):
+        sub.base_kernel.lengthscales.assign(l)
+    for v, s_ in zip(k9.variances, [0.5, 1.0, 0.8, 0.6, 0.4, 0.3, 0.2, 0.1, 0.05]):
+        v.assign(s_)
+    save("g9_full_depth_d8_p8", cfg_from_kernel(k9), X=X9, X2=X92, **kernel_outputs(k9, X9, X92))
+
 
 if __name__ == "__main__":
     main()

@@ -9,7 +9,7 @@ from helpers import build_oracle, load_golden, max_rel_err
 from oracle import oak_oracle as oo
 
 TIGHT = 1e-12  # same formulas, same op order (expanded RBF): rounding-level agreement
-KERNEL_CASES = ["g1_gaussian_d5_p3", "g2_mixed_p2", "g3_no_share_var", "g4_unconstrained"]
+KERNEL_CASES = ["g1_gaussian_d5_p3", "g2_mixed_p2", "g3_no_share_var", "g4_unconstrained", "g9_full_depth_d8_p8"]
 
 
 @pytest.mark.parametrize("name", KERNEL_CASES)

@@ -8,7 +8,7 @@ import pytest
 from helpers import RTOL, load_golden, max_rel_err
 
 pytestmark = pytest.mark.gpu
-KERNEL_CASES = ["g1_gaussian_d5_p3", "g2_mixed_p2", "g3_no_share_var", "g4_unconstrained"]
+KERNEL_CASES = ["g1_gaussian_d5_p3", "g2_mixed_p2", "g3_no_share_var", "g4_unconstrained", "g9_full_depth_d8_p8"]
 
 
 @pytest.mark.parametrize("name", KERNEL_CASES)
