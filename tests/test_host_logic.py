@@ -313,3 +313,63 @@ def test_parameter_order_is_gpflows_and_checkpoints_follow_it(tmp_path):
     load_model(s2, f, load_all_parameters=True)
     np.testing.assert_allclose(s2.q_mu.numpy(), s.q_mu.numpy())
     np.testing.assert_allclose(s2.inducing_variable.Z.numpy(), X[:4])
+
+
+def test_training_chain_host_pieces_against_finite_differences():
+    """The host side of training.py, no GPU needed: d constrained / d unconstrained of the gpflow transforms, the
+    Gamma-prior gradient (model_utils.py:163-167), and the chain from the cotangent of a categorical / binary B
+    table (what the backward tiles return) to W, kappa and variance (ortho_categorical_kernel.py:34-53,
+    ortho_binary_kernel.py:29-38)."""
+    from types import SimpleNamespace
+
+    from oak_b200._gpflow_shim import Gamma, Identity, Softplus
+    from oak_b200.ortho_binary_kernel import OrthogonalBinary
+    from oak_b200.ortho_categorical_kernel import OrthogonalCategorical
+    from oak_b200.training import _prior_grad, _transform_grad, discrete_parameter_gradients
+    from oracle import oak_oracle as oo
+
+    h = 1e-6
+    for tr, val in ((Identity(), 0.7), (Softplus(0.0), 0.3), (Softplus(1e-6), 2.5), (Sigmoid(0.1, 9.0), 4.2)):
+        p = Parameter(val, transform=tr)
+        u = float(p.unconstrained_variable)
+        fd = (float(tr.forward(u + h)) - float(tr.forward(u - h))) / (2 * h)
+        assert abs(float(_transform_grad(p)) - fd) < 1e-8 * max(1.0, abs(fd))
+    prior = Gamma(1.0, 0.2)
+    for conc, rate, x in ((1.0, 0.2, 0.9), (2.5, 1.3, 0.4)):
+        p = Parameter(x, transform=positive(), prior=Gamma(conc, rate))
+        fd = (float(p.prior.log_prob(x + h)) - float(p.prior.log_prob(x - h))) / (2 * h)
+        assert abs(float(_prior_grad(p)) - fd) < 1e-7
+    assert abs(float(_prior_grad(Parameter(1.0, transform=positive(), prior=prior))) + 0.2) < 1e-15
+
+    rng = np.random.default_rng(5)
+    kc = OrthogonalCategorical(p=np.array([0.2, 0.5, 0.3]).reshape(-1, 1), rank=2, active_dims=[0])
+    kc.W.assign(rng.uniform(0.2, 1.0, (3, 2)))
+    kc.kappa.assign(rng.uniform(0.5, 1.5, kc.kappa.numpy().shape))
+    kc.variance.assign(1.7)
+    kb = OrthogonalBinary(p0=0.35, active_dims=[1])
+    kb.variance.assign(0.8)
+    # cotangents of the two table blocks [C x C | C diagonal], laid out one after the other
+    g_tab = rng.standard_normal(3 * 3 + 3 + 2 * 2 + 2)
+    layout = [(0, 3), (12, 2)]
+    model = SimpleNamespace(kernel=SimpleNamespace(kernels=[kc, kb]), _table_cotangent=(g_tab, layout))
+    grads = discrete_parameter_gradients(model)
+
+    def objective():
+        dc = oo.CategoricalDim(p=kc._p_vector(), W=kc.W.numpy(), kappa=kc.kappa.numpy().reshape(-1),
+                               variance=float(kc.variance.numpy()))
+        db = oo.BinaryDim(kb.p0, float(kb.variance.numpy()))
+        return ((g_tab[0:9].reshape(3, 3) * dc.table()).sum() + (g_tab[9:12] * dc.table_diag()).sum()
+                + (g_tab[12:16].reshape(2, 2) * db.table()).sum() + (g_tab[16:18] * db.table_diag()).sum())
+
+    for prm in (kc.W, kc.kappa, kc.variance, kb.variance):
+        base = prm.numpy().copy()
+        flat = base.reshape(-1)
+        fd = np.zeros(flat.size)
+        for i in range(flat.size):
+            for sgn in (1, -1):
+                v = flat.copy()
+                v[i] += sgn * h
+                prm.assign(v.reshape(base.shape))
+                fd[i] += sgn * objective() / (2 * h)
+        prm.assign(base)
+        assert np.allclose(np.asarray(grads[id(prm)]).reshape(-1), fd, rtol=1e-6, atol=1e-8), prm
