@@ -59,3 +59,50 @@ def test_statistics_space_gradients_match_autograd():
     tot.backward()
     assert np.allclose(lsT.grad.numpy(), a_ls, rtol=1e-8)
     assert np.allclose(vT.grad.numpy(), a_var, rtol=1e-8)
+
+
+def test_svgp_oracle_identities():
+    """The SVGP / Bernoulli restatement of gpflow 2.2.1 in oracle/oak_grad_oracle.py is unpinned against a gpflow
+    run; these identities pin its pieces: the 20-point Gauss-Hermite expectations against adaptive quadrature of
+    the integrals they stand for, KL = 0 and the prior predictive when q(u) is the prior, and the whitened
+    conditional against the textbook un-whitened formulas (mean Kfu Kuu^-1 m, var Kff - Kfu Kuu^-1 (Kuu - S) Kuu^-1 Kuf
+    with m = L q_mu, S = L diag(q_sqrt^2) L^T)."""
+    import torch
+    from scipy import integrate, stats
+
+    from oracle import oak_grad_oracle as go
+
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    for link, inv in (("logit", go.inv_logit), ("probit", go.inv_probit)):
+        for mu, var, y in ((0.7, 1.9, 1.0), (-1.2, 0.4, 0.0), (0.3, 1.0, 0.0)):  # smooth enough for 20 nodes
+            p = lambda f: float(inv(t(f)))
+            lik = lambda f: p(f) if y == 1.0 else 1.0 - p(f)
+            dens = lambda f: stats.norm.pdf(f, mu, np.sqrt(var))
+            ve = float(go.bernoulli_variational_expectations(t([mu]), t([var]), t([y]), inv))
+            ld = float(go.bernoulli_predict_log_density(t([mu]), t([var]), t([y]), inv))
+            assert abs(ve - integrate.quad(lambda f: dens(f) * np.log(lik(f)), mu - 12, mu + 12)[0]) < 1e-4  # the accuracy of 20 nodes on the jitter-clipped log
+            assert abs(ld - np.log(integrate.quad(lambda f: dens(f) * lik(f), mu - 12, mu + 12)[0])) < 1e-4
+    rng = np.random.default_rng(0)
+    X, Z = rng.standard_normal((40, 3)), rng.standard_normal((7, 3))
+    y = (rng.random(40) < 0.5).astype(float)
+    ls, var = t([0.8, 1.3, 2.0]), t([0.4, 1.0, 0.6])
+    # q(u) = prior
+    fm, fv = go.svgp_conditional(t(X), t(Z), ls, var, t(np.zeros(7)), t(np.ones(7)))
+    assert float(fm.abs().max()) == 0.0
+    assert float((fv - go.oak_K_diag(t(X), ls, var)).abs().max()) < 1e-12
+    elbo = go.svgp_elbo(t(X), t(y), t(Z), ls, var, t(np.zeros(7)), t(np.ones(7)))
+    assert abs(float(elbo) - float(go.bernoulli_variational_expectations(fm, fv, t(y)).sum())) < 1e-12
+    # whitened vs un-whitened parametrisation of the same q(u)
+    q_mu, q_sqrt = t(rng.standard_normal(7)), t(rng.uniform(0.3, 1.2, 7))
+    fm, fv = go.svgp_conditional(t(X), t(Z), ls, var, q_mu, q_sqrt)
+    Kuu = go.oak_K(t(Z), t(Z), ls, var) + go.JITTER * torch.eye(7, dtype=torch.float64)
+    Kuf = go.oak_K(t(Z), t(X), ls, var)
+    L = torch.linalg.cholesky(Kuu)
+    m, S = L @ q_mu, L @ torch.diag(q_sqrt ** 2) @ L.T
+    Ki = torch.linalg.inv(Kuu)
+    assert float((fm - Kuf.T @ Ki @ m).abs().max()) < 1e-8
+    want = go.oak_K_diag(t(X), ls, var) - torch.einsum("ij,jk,ki->i", Kuf.T, Ki @ (Kuu - S) @ Ki, Kuf)
+    assert float((fv - want).abs().max()) < 1e-7
+    # alpha of the posterior object: Kfu alpha is the predictive mean
+    alpha = go.svgp_alpha(t(Z), ls, var, q_mu)
+    assert float((Kuf.T @ alpha[:, 0] - fm).abs().max()) < 1e-8
