@@ -14,6 +14,13 @@ _JITTER = 1e-6
 
 
 # ---- config / utilities ---------------------------------------------------------------------
+def _eager(x):
+    """ndarray answering ``.numpy()`` like the EagerTensor gpflow returns."""
+    from tensorflow import EagerArray
+
+    return np.asarray(x).view(EagerArray)
+
+
 def default_float():
     return np.float64
 
@@ -307,7 +314,7 @@ class GPR(GPModel):
         A = _sla.solve_triangular(Lm, self.kernel(X, Xnew), lower=True)
         mean = A.T @ _sla.solve_triangular(Lm, Y, lower=True)
         var = self.kernel(Xnew, full_cov=False) - np.sum(A * A, 0)
-        return mean, var[:, None]
+        return _eager(mean), _eager(var[:, None])
 
 
 class SGPR(GPModel):
@@ -352,7 +359,7 @@ class SGPR(GPModel):
         tmp2 = _sla.solve_triangular(LB, tmp1, lower=True)
         mean = tmp2.T @ c
         var = self.kernel(Xnew, full_cov=False) + np.sum(tmp2 * tmp2, 0) - np.sum(tmp1 * tmp1, 0)
-        return mean, var[:, None]
+        return _eager(mean), _eager(var[:, None])
 
 
 class SVGP(GPModel):

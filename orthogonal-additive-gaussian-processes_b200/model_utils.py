@@ -290,6 +290,19 @@ class oak_model:
                 self.empirical_weights[ii] = (cnt / cnt.sum()).reshape(-1, 1)
                 self.empirical_locations[ii] = loc.reshape(-1, 1)
 
+        # the reference's consistency checks (:346-370).  The last one also rejects use_normalising_flow=False
+        # together with an empirical measure: such a column is standardised twice by _transform_x (:468-475)
+        assert np.allclose(self.X_scaled[:, self.binary_index], X[:, self.binary_index]), "Flow applied to binary inputs"
+        assert np.allclose(self.X_scaled[:, self.categorical_index],
+                           X[:, self.categorical_index]), "Flow applied to categorical inputs"
+        if self.gmm_measure is not None:
+            idx = np.flatnonzero(self.gmm_measure)
+            assert np.allclose(self.X_scaled[:, idx], X[:, idx]), "Flow applied to GMM measure inputs"
+        if self.empirical_measure is not None:
+            back = np.stack([self._get_x_inverse_transformer(i)(self.X_scaled[:, i]) for i in self.empirical_measure],
+                            axis=1)
+            assert np.allclose(back, X[:, self.empirical_measure]), "Flow applied to empirical measure inputs"
+
         Z = None
         if X.shape[0] > 1000 or self.sparse:  # sparse GP switch (:373-374)
             if initialise_inducing_points:

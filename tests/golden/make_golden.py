@@ -291,6 +291,35 @@ def main():
         v.assign(s_)
     save("g9_full_depth_d8_p8", cfg_from_kernel(k9), X=X9, X2=X92, **kernel_outputs(k9, X9, X92))
 
+    # --- G10: the reference's own oak_model pipeline (oak/model_utils.py fit / predict / get_sobol, unmodified):
+    # feature typing, p0 / p, standardisation of X and y, k-means inducing points with discrete columns, kernel
+    # construction.  Flows off (their optimiser is gpflow's), optimise=False (BFGS is gpflow's); the prediction
+    # goes through the shim's restated SGPR.predict_f. ---------------------------------------------------------
+    import warnings
+
+    from oak import model_utils as ref_mu
+
+    warnings.filterwarnings("ignore")
+    N = 90
+    Xp = np.zeros((N, 4))
+    Xp[:, 0] = (rng.random(N) < 0.3).astype(float)
+    Xp[:, 1] = rng.integers(0, 3, N).astype(float)
+    Xp[:, 2] = rng.standard_normal(N) * 2.0 + 1.0
+    Xp[:, 3] = rng.standard_normal(N) * 0.5 - 3.0
+    Yp = (np.sin(Xp[:, 2]) + Xp[:, 0] + 0.5 * (Xp[:, 1] == 2) + 0.3 * Xp[:, 3] + 0.1 * rng.standard_normal(N)).reshape(-1, 1)
+    Xt = Xp[:25] + np.array([0.0, 0.0, 0.3, -0.1])
+    np.random.seed(7)
+    oak = ref_mu.oak_model(max_interaction_depth=2, binary_feature=[0], categorical_feature=[1],
+                           use_normalising_flow=False, sparse=True, num_inducing=12)
+    oak.fit(Xp, Yp, optimise=False)
+    sob = oak.get_sobol()
+    save("g10_oak_model_pipeline", cfg_from_kernel(oak.m.kernel), X=Xp, Y=Yp, X_test=Xt,
+         X_scaled=np.asarray(oak.X_scaled), Y_scaled=np.asarray(oak.Y_scaled),
+         Z=np.asarray(oak.m.inducing_variable.Z.numpy()), noise=np.array(float(oak.m.likelihood.variance.numpy())),
+         y_pred=np.asarray(oak.predict(Xt)), y_pred_clip=np.asarray(oak.predict(Xt, clip=True)),
+         sobol=np.asarray(sob), tuple_of_indices_json=np.array(json.dumps(jsonable(oak.tuple_of_indices))),
+         restated_elbo=np.array(float(oak.m.elbo())))
+
 
 if __name__ == "__main__":
     main()

@@ -109,3 +109,32 @@ def test_flow_oracle_matches_the_references_normalizer():
         np.testing.assert_allclose(nz.bijector.inverse(g[f"{tag}_y_2"]), x, rtol=1e-11)
         np.testing.assert_allclose(nz.bijector.forward_log_det_jacobian(x), g[f"{tag}_ldj_2"], rtol=1e-13, atol=1e-14)
         np.testing.assert_allclose(g[f"{tag}_x_back"], x, rtol=1e-11)
+
+
+def test_oak_model_pipeline_matches_the_references_model_utils():
+    """g10: the reference's own oak_model (oak/model_utils.py fit, unmodified, over the shim) against this
+    repository's: feature typing and the discrete measures p0 / p (:703-750), standardisation of X and y
+    (:318-331), k-means inducing points with discrete columns (utils.py:555-574), kernel construction and the
+    0.01 initial noise (:90-176).  Runs without a GPU: with flows off and optimise=False nothing is evaluated."""
+    import warnings
+
+    from oak_b200.model_utils import oak_model
+
+    cfg, g = load_golden("g10_oak_model_pipeline")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oak = oak_model(max_interaction_depth=2, binary_feature=[0], categorical_feature=[1],
+                        use_normalising_flow=False, sparse=True, num_inducing=12)
+        oak.fit(g["X"], g["Y"], optimise=False)
+    assert (oak.binary_index, oak.categorical_index, oak.continuous_index) == ([0], [1], [2, 3])
+    assert max_rel_err(oak.X_scaled, g["X_scaled"]) < 1e-14
+    assert max_rel_err(oak.Y_scaled, g["Y_scaled"]) < 1e-14
+    assert max_rel_err(oak.m.inducing_variable.Z.numpy(), g["Z"]) < 1e-12
+    assert abs(float(oak.m.likelihood.variance.numpy()) - float(g["noise"])) < 1e-15
+    k = oak.m.kernel
+    assert k.max_interaction_depth == cfg["depth"] and [float(v.numpy()) for v in k.variances] == cfg["variances"]
+    assert abs(k.kernels[0].p0 - cfg["dims"][0]["p0"]) < 1e-15
+    assert max_rel_err(k.kernels[1]._p_vector(), cfg["dims"][1]["p"]) < 1e-15
+    for i in (2, 3):
+        assert abs(float(k.kernels[i].base_kernel.lengthscales.numpy()) - cfg["dims"][i]["lengthscale"]) < 1e-14
+        assert (k.kernels[i].measure.mu, k.kernels[i].measure.var) == (0.0, 1.0)

@@ -108,3 +108,26 @@ def test_cuda_sobol_quadforms_with_reference_alpha():
         sob = _device.sobol_quadforms(Ls, comps, scales, _device.to_device(g[key_a])).cpu().numpy()
         spec.close()
         assert max_rel_err(sob, g[key_s]) < tol
+
+
+def test_cuda_oak_model_pipeline_matches_the_references_model_utils():
+    """g10: predictions (plain and clipped) and normalised Sobol indices of the reference's own oak_model
+    (oak/model_utils.py fit / predict / get_sobol over the shim) against this repository's oak_model on the GPU."""
+    import warnings
+
+    from oak_b200.model_utils import oak_model
+
+    cfg, g = load_golden("g10_oak_model_pipeline")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        oak = oak_model(max_interaction_depth=2, binary_feature=[0], categorical_feature=[1],
+                        use_normalising_flow=False, sparse=True, num_inducing=12)
+        oak.fit(g["X"], g["Y"], optimise=False)
+    # the categorical W is drawn at random in the constructor (ortho_categorical_kernel.py:28): take the reference's
+    oak.m.kernel.kernels[1].W.assign(np.asarray(cfg["dims"][1]["W"]))
+    assert abs(oak.m.elbo() - float(g["restated_elbo"])) < 1e-8 * abs(float(g["restated_elbo"]))
+    assert max_rel_err(oak.predict(g["X_test"]), g["y_pred"]) < 1e-8
+    assert max_rel_err(oak.predict(g["X_test"], clip=True), g["y_pred_clip"]) < 1e-8
+    sob = oak.get_sobol()
+    assert json.loads(str(g["tuple_of_indices_json"])) == [[int(i) for i in t] for t in oak.tuple_of_indices]
+    assert max_rel_err(sob, g["sobol"]) < 1e-7

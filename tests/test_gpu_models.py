@@ -242,7 +242,7 @@ def test_oak_model_api_end_to_end():
     X = np.vstack([x_bin, x_cat, rng.standard_normal(N), rng.standard_normal(N)]).T.astype(float)
     y = (np.sin(X[:, 2]) + X[:, 0] + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
     oak = oak_model(binary_feature=[0], categorical_feature=[1], max_interaction_depth=2,
-                    use_normalising_flow=False, empirical_measure=[3], sparse=True, num_inducing=40)
+                    empirical_measure=[3], sparse=True, num_inducing=40)
     oak.fit(X, y, optimise=False, initialise_inducing_points=False)
     assert not np.isnan(oak.m.elbo())
     pred = oak.predict(X)

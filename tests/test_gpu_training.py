@@ -292,7 +292,7 @@ def test_categorical_W_kappa_gradients_through_the_table_cotangent():
 
 def test_mixed_input_oak_model_trains_all_its_parameters():
     """Binary + categorical + empirical-measure + continuous inputs (the oak_model flow of
-    model_utils.py:194-427 without the TFP flow): every trainable parameter of the reference model --
+    model_utils.py:194-427: a flow on the plain continuous column, standardisation on the empirical one): every trainable parameter of the reference model --
     bounded lengthscales, order variances, noise, categorical W and kappa -- receives a gradient and
     BFGS improves the bound."""
     from oak_b200.model_utils import oak_model
@@ -305,7 +305,7 @@ def test_mixed_input_oak_model_trains_all_its_parameters():
     X = np.vstack([x_bin, x_cat, rng.standard_normal(N), np.round(3 * rng.standard_normal(N)) / 3]).T.astype(float)
     y = (np.sin(X[:, 2]) + X[:, 0] + 0.4 * (X[:, 1] == 2) + 0.3 * X[:, 3] + 0.05 * rng.standard_normal(N)).reshape(-1, 1)
     oak = oak_model(binary_feature=[0], categorical_feature=[1], max_interaction_depth=2,
-                    use_normalising_flow=False, empirical_measure=[3], sparse=True, num_inducing=50)
+                    empirical_measure=[3], sparse=True, num_inducing=50)
     oak.fit(X, y, optimise=False, initialise_inducing_points=False)
     params = trainable_parameters(oak.m)
     # 2 lengthscales, the base variance of the empirical-measure dim (oak_kernel.py:163-166 fixes it only

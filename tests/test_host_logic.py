@@ -373,3 +373,17 @@ def test_training_chain_host_pieces_against_finite_differences():
                 fd[i] += sgn * objective() / (2 * h)
         prm.assign(base)
         assert np.allclose(np.asarray(grads[id(prm)]).reshape(-1), fd, rtol=1e-6, atol=1e-8), prm
+
+
+def test_fit_consistency_checks_follow_the_reference():
+    """oak_model.fit keeps the reference's assertions (model_utils.py:346-370): with use_normalising_flow=False an
+    empirical-measure column is standardised twice by _transform_x (:468-475) and the reference stops with
+    "Flow applied to empirical measure inputs"; so does this implementation (no GPU is reached)."""
+    from oak_b200.model_utils import oak_model
+
+    rng = np.random.default_rng(0)
+    X = np.stack([rng.standard_normal(50), np.round(3 * rng.standard_normal(50)) / 3], axis=1)
+    Y = rng.standard_normal((50, 1))
+    oak = oak_model(use_normalising_flow=False, empirical_measure=[1])
+    with pytest.raises(AssertionError, match="empirical measure inputs"):
+        oak.fit(X, Y, optimise=False)
