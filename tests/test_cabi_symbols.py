@@ -59,3 +59,26 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_header_is_plain_c():
+    """include/oak_b200.h is the boundary a maintainer binds from C / cgo / ctypes: it must parse as C99 on its own
+    (no C++-isms, no torch or CUDA types in the signatures)."""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "hdr.c")
+        with open(src, "w") as f:
+            f.write('#include "oak_b200.h"\nint main(void) { return (int)OAK_LINK_PROBIT - 1; }\n')
+        out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                              "-fsyntax-only", src], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "oak_b200.h")).read(), flags=re.S)
+    assert "torch" not in text and "cudaStream_t" not in text and "at::" not in text  # outside the comments
