@@ -106,3 +106,53 @@ def test_svgp_oracle_identities():
     # alpha of the posterior object: Kfu alpha is the predictive mean
     alpha = go.svgp_alpha(t(Z), ls, var, q_mu)
     assert float((Kuf.T @ alpha[:, 0] - fm).abs().max()) < 1e-8
+
+
+def test_inducing_point_gradient_formulas():
+    """The row-point gradient the CUDA tiles implement, on the CPU: d k~(z, x)/dz = -ex (z - x)/l^2 - c^'(z) c^(x)
+    chained through dK/dk~ by the removal recurrence gives d/dZ of sum W * K(Z, X); here the closed form is
+    assembled in NumPy for the Gaussian measure and compared with autograd, and autograd's d ELBO / dZ is
+    compared with central differences (the reference differentiates Z the same way when zfixed=False)."""
+    X, y, Z, ls, var, noise, _ = _setup(n=60, D=3, P=2, M=9, seed=3)
+    Z = Z + 0.1 * np.random.default_rng(1).standard_normal(Z.shape)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64)
+    rng = np.random.default_rng(2)
+    W = rng.standard_normal((Z.shape[0], X.shape[0]))
+    ZT = t(Z).clone().requires_grad_(True)
+    (t(W) * go.oak_K(ZT, t(X), t(ls), t(var))).sum().backward()
+    # closed form, Gaussian measure N(0, 1): c^(x) = pre exp(-x^2 / (2 (l^2 + 1))) / sqrt(v)
+    D = Z.shape[1]
+    kt, ex, chz, chx = [], [], [], []
+    for d in range(D):
+        l = ls[d]
+        pre = l / np.sqrt(l ** 2 + 1.0)
+        v = l / np.sqrt(l ** 2 + 2.0)
+        cz = pre * np.exp(-0.5 * Z[:, d] ** 2 / (l ** 2 + 1.0)) / np.sqrt(v)
+        cx = pre * np.exp(-0.5 * X[:, d] ** 2 / (l ** 2 + 1.0)) / np.sqrt(v)
+        e = np.exp(-0.5 * (Z[:, d][:, None] - X[:, d][None, :]) ** 2 / l ** 2)
+        kt.append(e - cz[:, None] * cx[None, :])
+        ex.append(e)
+        chz.append(cz)
+        chx.append(cx)
+    # elementary symmetric polynomials with dimension d removed: e_0^{(-d)} = 1, e_1^{(-d)} = e_1 - k_d  (P = 2)
+    e1 = sum(kt)
+    gZ = np.zeros_like(Z)
+    for d in range(D):
+        dKdk = var[1] + var[2] * (e1 - kt[d])
+        wk = W * dKdk
+        l = ls[d]
+        A = (wk * ex[d] * (Z[:, d][:, None] - X[:, d][None, :])).sum(1)
+        B = (wk * chx[d][None, :]).sum(1)
+        dchz = -chz[d] * Z[:, d] / (l ** 2 + 1.0)
+        gZ[:, d] = -A / l ** 2 - dchz * B
+    assert np.allclose(gZ, ZT.grad.numpy(), rtol=1e-10, atol=1e-12)
+    # autograd of the ELBO with respect to Z against central differences
+    _, _, _, _, a_Z = go.value_and_grad(go.sgpr_elbo, X, y, Z, ls, var, noise, wrt_Z=True)
+    h = 1e-6
+    for (i, d) in ((0, 0), (4, 1), (8, 2)):
+        Zp, Zm = Z.copy(), Z.copy()
+        Zp[i, d] += h
+        Zm[i, d] -= h
+        fd = (go.value_and_grad(go.sgpr_elbo, X, y, Zp, ls, var, noise)[0]
+              - go.value_and_grad(go.sgpr_elbo, X, y, Zm, ls, var, noise)[0]) / (2 * h)
+        assert abs(fd - a_Z[i, d]) < 1e-5 * max(1.0, abs(fd))
