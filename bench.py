@@ -12,7 +12,9 @@ JSON line on rank 0.  A *step* is one pass of the hot path over the workload:
   e2e        the same metric through the host-buffer C-ABI call (oak_gram_host_f64): pinned NumPy
              X in, H2D, prepare, row-blocked Gram, D2H of the rows into pinned host memory.
   extra      config C: SGPR ELBO evals/s (N=1M, D=20, M=1024, depth 3), N axis sharded over ranks,
-             one all-reduce of M^2+M+2 doubles, M^3 tail timed separately.
+             one all-reduce of M^2+M+2 doubles, M^3 tail timed separately; the training step (ELBO +
+             gradient through the backward tiles) with fixed and with trainable inducing points; one
+             evaluation of configs A, D, E; the widening rows (SVGP objective, flow objective pass).
   roofline   FP64-pipe bound: algorithmic flop (306 slots x 2 per unique entry) / Gram-kernel time
              (CUDA events on the launch stream) / measured DFMA peak of the same run.
   cpu_baseline  the reference op sequence (oracle/cpu_baseline.py, torch-CPU FP64, all host cores)
