@@ -431,19 +431,37 @@ def main():
         Xs, Ys = model._device_data()
         pz = _device.Points(sp, model._Z_device())
         pxs = _device.Points(sp, Xs)
-        _device.sgpr_stats(sp, pz, pxs, Ys)
+        fac = _device.sgpr_factor(sp, pz, 1e-6)
+        _device.sgpr_stats2(sp, pz, pxs, Ys, fac)
         torch.cuda.synchronize()
         a.record()
         for _ in range(k_e):
-            _device.sgpr_stats(sp, pz, pxs, Ys)
+            _device.sgpr_stats2(sp, pz, pxs, Ys, fac)
         b2.record()
         torch.cuda.synchronize()
         ms_stats = max_over_ranks(a.elapsed_time(b2) / k_e)
+        # the factor-first front (Kuu tiles, bordered Cholesky -> L and L^-1, condition estimate, route flag)
+        a.record()
+        for _ in range(k_e):
+            _device.sgpr_factor(sp, pz, 1e-6, buf=fac.buf)
+        b2.record()
+        torch.cuda.synchronize()
+        ms_factor = max_over_ranks(a.elapsed_time(b2) / k_e)
+        # the tail after the all-reduce (whitening, bordered Cholesky of B, bound)
+        st = _device.sgpr_stats2(sp, pz, pxs, Ys, fac)
+        a.record()
+        for _ in range(k_e):
+            _device.sgpr_finish2(fac, st, args.elbo_n, cfg_c["noise"], want_alpha=False)
+        b2.record()
+        torch.cuda.synchronize()
+        ms_finish = max_over_ranks(a.elapsed_time(b2) / k_e)
         sp.close()
         kuf_entries = float(args.elbo_m) * (e - b)
         elbo = {
             "metric": "SGPR ELBO evals/sec", "value": 1e3 / ms_elbo, "unit": "evals/s", "ms_per_eval": ms_elbo,
             "ms_stats_phase": ms_stats, "ms_tail_and_collective": ms_elbo - ms_stats, "elbo": vals[-1],
+            "ms_factor_front": ms_factor, "ms_finish_tail": ms_finish, "route": model.last_route,
+            "cond_estimate_kuu": model.last_cond_estimate,
             "workload": f"config C: N={args.elbo_n}, D=20, M={args.elbo_m}, depth 3; N axis sharded over {world} "
                         f"rank(s); all-reduce of {args.elbo_m ** 2 + args.elbo_m + 2} doubles",
             "roofline_stats_phase": {

@@ -196,6 +196,64 @@ int oak_sgpr_finish_f64(double* d_Kuu, double* d_stats, int64_t m, int64_t n_tot
                         double jitter, double* d_out, double* d_alpha, void* d_work,
                         void* stream);
 
+/* ---- SGPR, factor-first path (default since round 2) ---------------------------------------
+ * gpflow's SGPR.elbo whitens Kuf BEFORE the contraction: A = L^-1 Kuf / sigma, then A A^T
+ * (oak/utils.py:186-190).  Forming Phi = Kuf Kuf^T first and whitening it once in the tail is cheaper
+ * (no M^2 n triangular product) but its rounding is amplified by cond(Kuu): 2e-6 relative ELBO error at
+ * cond(Kuu) = 2.6e8 (long lengthscales), 1e-13 at 1e4.  Here L = chol(Kuu + jitter I) is computed first
+ * and the route is chosen ON THE DEVICE from a condition estimate, so no host synchronisation is needed:
+ *   route 0  Phi statistics + one whitening in the tail          (cond estimate < threshold)
+ *   route 1  per chunk A_r = L^-1 Kuf_r, Psi = sum A_r A_r^T      (gpflow's operation order)
+ * Both routes all-reduce the same M*M + M + 2 doubles.
+ *
+ * d_fac (oak_sgpr_factor_count(m) doubles, 16-byte aligned): column-major matrix with leading dimension
+ * LD = oak_sgpr_factor_ld(m) = 2 * roundup8(m) and m columns: rows [0, m) hold L (lower triangle), rows
+ * [LD/2, LD/2 + m) hold L^-T (upper triangle) -- i.e. the row-major view d_fac[r*LD + LD/2 + c] is L^-1 --
+ * followed by a 16-double header {cond estimate, ||Kuu||_1, lambda_max(Kuu^-1) estimate, route,
+ * info of chol(Kuu), sum log diag L, threshold, ...} and scratch. */
+size_t oak_sgpr_factor_count(int64_t m);
+int64_t oak_sgpr_factor_ld(int64_t m);
+/* Kuu(iv, kernel) + jitter I (oak/utils.py:185), L = chol(Kuu) (:188), L^-1, the condition estimate and
+ * the route flag.  route: -1 = decide from the estimate (cond_threshold <= 0: default 3e5), 0 / 1 = forced. */
+int oak_sgpr_factor_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, int route,
+                        double cond_threshold, double* d_fac, void* stream);
+/* The chunk loop of oak_sgpr_stats_f64 on the route stored in d_fac: d_stats accumulates
+ * Phi (route 0) or Psi (route 1) | Kuf y | sum K_diag | y^T y.  d_kuf_store may be NULL (else every chunk's
+ * Kuf block is kept as in oak_sgpr_stats_keep_f64). */
+size_t oak_sgpr_stats2_work_bytes(int64_t m, int64_t chunk);
+int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
+                        const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
+                        double* d_stats, void* d_work, double* d_kuf_store, void* stream);
+/* Tail of SGPR.elbo (oak/utils.py:190-198) from the (all-reduced) statistics: B = I + A A^T, LB = chol(B),
+ * c = LB^-1 A err / sigma, the bound, alpha = L^-T LB^-T c.  d_LB: oak_sgpr_lb_ld(m) * m doubles, column-major
+ * with that leading dimension: rows [0, m) = LB (lower triangle), row roundup8(m) = c^T.
+ * d_out[8] = {elbo, sum log diag LB, tr(A A^T), c^T c, info of chol(Kuu), info of chol(B), route, cond
+ * estimate}: a non-zero info (leading minor not positive definite) is reported there, not by a host
+ * synchronisation.  d_alpha[m] may be NULL. */
+int64_t oak_sgpr_lb_ld(int64_t m);
+size_t oak_sgpr_finish2_work_bytes(int64_t m);
+int oak_sgpr_finish2_f64(double* d_fac, double* d_stats, int64_t m, int64_t n_total, double noise,
+                         double* d_out, double* d_alpha, double* d_LB, void* d_work, void* stream);
+
+/* ---- dense building blocks of the tails (csrc/oak_chol.cu, csrc/oak_pgemm.cu) ---------------- */
+/* Cholesky factorisation with border rows in one cooperative launch, replacing the tf.linalg.cholesky +
+ * tf.linalg.triangular_solve pairs of oak/utils.py:188-195.  d_A: column-major, leading dimension ld
+ * (equivalently: the UPPER triangle of a row-major matrix); the n x n symmetric block is read and
+ * overwritten in its lower triangle by L; rows [n, rows) -- stored `gap` rows further down -- are
+ * overwritten by Border * L^-T.  border_identity != 0 declares that border row n + i holds e_i on entry
+ * (rows - n == n), which lets the kernel skip the still-zero part.  *d_info: 0, or k > 0 when the leading
+ * minor of order k is not positive definite.  d_logdet (may be NULL): sum_i log L_ii. */
+int oak_chol_f64(double* d_A, int64_t n, int64_t rows, int64_t gap, int64_t ld, int border_identity,
+                 int32_t* d_info, double* d_logdet, void* stream);
+/* C (m x n, ldc) = T (m x kd, ldt) * B (kd x n, ldb) [+ u v^T], row-major, on the FP64 tensor cores:
+ * the whitening product A_r = L^-1 Kuf_r of route 1 (lower != 0: T is lower triangular with zeros above
+ * the diagonal) and the cotangent W = 2 G_Phi Kuf + g_b y^T of the training step.  Leading dimensions
+ * even, bases 16-byte aligned, ldb >= n rounded up to even.  d_work: oak_panel_gemm_work_bytes(). */
+size_t oak_panel_gemm_work_bytes(void);
+int oak_panel_gemm_f64(const double* d_T, int64_t ldt, const double* d_B, int64_t ldb, double* d_C,
+                       int64_t ldc, int64_t m, int64_t kd, int64_t n, int lower, const double* d_u,
+                       const double* d_v, void* d_work, void* stream);
+
 /* GPR: log N(y; 0, K + noise I) and alpha = (K + noise I)^-1 y (oak/utils.py:206-211;
  * gpflow GPR.log_marginal_likelihood).  d_K (n x n) is overwritten by its Cholesky factor. */
 size_t oak_gpr_finish_work_bytes(int64_t n);

@@ -456,6 +456,141 @@ def sgpr_finish(Kuu, stats, n_total: int, noise: float, jitter: float, want_alph
     return out, alpha
 
 
+# ---- SGPR, factor-first path (L = chol(Kuu) before the statistics; route chosen on the device) ----
+ROUTE_AUTO, ROUTE_PHI, ROUTE_WHITENED = -1, 0, 1
+
+
+class KuuFactor:
+    """[L ; L^-T] of Kuu + jitter I with its header (see ``oak_sgpr_factor_f64`` in include/oak_b200.h)."""
+
+    def __init__(self, buf, m: int):
+        lib = _cabi.load()
+        self.buf, self.m = buf, int(m)
+        self.ld = int(lib.oak_sgpr_factor_ld(m))
+
+    @property
+    def _mat(self):
+        return self.buf[: self.ld * self.m].view(self.m, self.ld)  # row r of this view = column r of the factor
+
+    def L(self):
+        """Lower-triangular factor as a (M, M) tensor (a copy)."""
+        return _torch().tril(self._mat[:, : self.m].T)
+
+    def Linv(self):
+        """L^-1 (row-major view, exact zeros above the diagonal)."""
+        return self._mat[:, self.ld // 2: self.ld // 2 + self.m]
+
+    def header(self):
+        """16 doubles: cond estimate, ||Kuu||_1, lambda_max(Kuu^-1) estimate, route, info, sum log diag L, threshold."""
+        return self.buf[self.ld * self.m: self.ld * self.m + 16]
+
+
+def sgpr_factor(spec: Spec, pz: Points, jitter: float, route: int = ROUTE_AUTO, cond_threshold: float = 0.0,
+                buf=None) -> KuuFactor:
+    torch = _torch()
+    lib = _cabi.load()
+    m = pz.n
+    cnt = int(lib.oak_sgpr_factor_count(m))
+    if buf is None or buf.numel() != cnt:
+        buf = torch.empty(cnt, dtype=torch.float64, device=pz.buf.device)
+    check(lib.oak_sgpr_factor_f64(spec.handle, _p(pz.buf), m, float(jitter), int(route), float(cond_threshold),
+                                  _p(buf), C.c_void_p(stream_ptr())), "oak_sgpr_factor_f64")
+    return KuuFactor(buf, m)
+
+
+def sgpr_stats2(spec: Spec, pz: Points, px: Points, y, fac: KuuFactor, chunk: int = 262144, stats=None,
+                keep_kuf: bool = False, kuf_store=None):
+    """``sgpr_stats`` on the route stored in ``fac``: the first M*M entries are Phi (route 0) or Psi (route 1)."""
+    torch = _torch()
+    lib = _cabi.load()
+    m = pz.n
+    count = int(lib.oak_sgpr_stats_count(m))
+    if stats is None:
+        stats = torch.zeros(count, dtype=torch.float64, device=pz.buf.device)
+    chunk = int(max(64, min(chunk, max(px.n, 64))))
+    chunk = (chunk + 63) // 64 * 64
+    work = torch.empty(max(int(lib.oak_sgpr_stats2_work_bytes(m, chunk)) // 8, 1), dtype=torch.float64,
+                       device=pz.buf.device)
+    yv = y.reshape(-1).contiguous()
+    store = None
+    if keep_kuf:
+        nchunks = max((px.n + chunk - 1) // chunk, 1)
+        store = kuf_store
+        if store is None or tuple(store.shape) != (nchunks, m, chunk) or store.device != pz.buf.device:
+            store = torch.empty((nchunks, m, chunk), dtype=torch.float64, device=pz.buf.device)
+    check(lib.oak_sgpr_stats2_f64(spec.handle, _p(pz.buf), m, _p(fac.buf), _p(px.buf), _p(yv), px.n, chunk, _p(stats),
+                                  _p(work), _p(store), C.c_void_p(stream_ptr())), "oak_sgpr_stats2_f64")
+    if keep_kuf:
+        blocks = [store[c, :, : min(chunk, px.n - c * chunk)] for c in range(nchunks) if px.n - c * chunk > 0]
+        return stats, blocks, chunk, store
+    return stats
+
+
+class SgprTail:
+    """Result of ``sgpr_finish2``: ``out`` (8 doubles on the device), ``alpha`` and the factor of B."""
+
+    def __init__(self, out, alpha, lb_buf, m):
+        self.out, self.alpha, self.lb_buf, self.m = out, alpha, lb_buf, int(m)
+        self.ldb = int(_cabi.load().oak_sgpr_lb_ld(m))
+
+    def LB(self):
+        return _torch().tril(self.lb_buf.view(self.m, self.ldb)[:, : self.m].T)
+
+    def c(self):
+        mp = (self.m + 7) // 8 * 8
+        return self.lb_buf.view(self.m, self.ldb)[:, mp]
+
+    def host(self):
+        """The one read-back of an evaluation; raises when a factorisation failed."""
+        o = self.out.cpu().numpy()
+        if o[4] != 0:
+            raise OakNativeError(f"oak_sgpr: Cholesky of Kuu failed (leading minor {int(o[4])} not positive definite)")
+        if o[5] != 0:
+            raise OakNativeError(f"oak_sgpr: Cholesky of B = A A^T + I failed (leading minor {int(o[5])} not positive "
+                                 "definite)")
+        return o
+
+
+def sgpr_finish2(fac: KuuFactor, stats, n_total: int, noise: float, want_alpha: bool = True) -> SgprTail:
+    torch = _torch()
+    lib = _cabi.load()
+    m = fac.m
+    dev = fac.buf.device
+    out = torch.empty(8, dtype=torch.float64, device=dev)
+    alpha = torch.empty(m, dtype=torch.float64, device=dev) if want_alpha else None
+    lb = torch.empty(int(lib.oak_sgpr_lb_ld(m)) * m, dtype=torch.float64, device=dev)
+    work = torch.empty(max(int(lib.oak_sgpr_finish2_work_bytes(m)) // 8, 1), dtype=torch.float64, device=dev)
+    check(lib.oak_sgpr_finish2_f64(_p(fac.buf), _p(stats), m, int(n_total), float(noise), _p(out), _p(alpha), _p(lb),
+                                   _p(work), C.c_void_p(stream_ptr())), "oak_sgpr_finish2_f64")
+    return SgprTail(out, alpha, lb, m)
+
+
+def chol(A, n: int, rows: int, gap: int = 0, border_identity: bool = False):
+    """In-place bordered Cholesky of a column-major matrix held in the 2-D tensor ``A`` (shape (n, ld): row j of
+    the tensor is column j of the matrix).  Returns (info tensor[1] int32, logdet tensor[1])."""
+    torch = _torch()
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    logdet = torch.zeros(1, dtype=torch.float64, device=A.device)
+    check(_cabi.load().oak_chol_f64(_p(A), int(n), int(rows), int(gap), int(A.stride(0)), int(bool(border_identity)),
+                                    _p(info), _p(logdet), C.c_void_p(stream_ptr())), "oak_chol_f64")
+    return info, logdet
+
+
+def panel_gemm(T, B, lower: bool = False, u=None, v=None, out=None):
+    """out (M x n) = T (M x Kd) @ B (Kd x n) [+ u v^T] on the FP64 tensor cores (row-major, even pitches)."""
+    torch = _torch()
+    M, Kd = T.shape
+    n = B.shape[1]
+    assert B.shape[0] == Kd and T.stride(1) == 1 and B.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, (n + 1) // 2 * 2), dtype=torch.float64, device=T.device)[:, :n]
+    work = torch.zeros(8, dtype=torch.float64, device=T.device)
+    check(_cabi.load().oak_panel_gemm_f64(_p(T), int(T.stride(0)), _p(B), int(B.stride(0)), _p(out), int(out.stride(0)),
+                                          M, Kd, n, int(bool(lower)), _p(u), _p(v), _p(work),
+                                          C.c_void_p(stream_ptr())), "oak_panel_gemm_f64")
+    return out
+
+
 def gpr_finish(K, y, noise: float):
     """Returns (lml tensor[1], alpha[n]); K is overwritten by its Cholesky factor."""
     torch = _torch()

@@ -120,7 +120,14 @@ inline const unsigned long long* points_minmax(const oak_spec* spec, const doubl
 // Phi(lower, column-major) += A A^T on the FP64 tensor cores (oak_syrk.cu)
 size_t syrk_dmma_work_bytes(int m);
 int syrk_lower_dmma(int m, int64_t k, double* A, int64_t lda, double* C, double* work, size_t work_bytes,
+                    int device, cudaStream_t stream, double* A_alt = nullptr, const int* d_route = nullptr);
+// C = T B (+ u v^T) on the FP64 tensor cores (oak_pgemm.cu); d_gate: optional device flag, 0 = no-op
+int panel_gemm_dmma(const double* T, int64_t ldt, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int Kd,
+                    int64_t n, int lower, const double* u, const double* v, const int* d_gate, int* d_counter,
                     int device, cudaStream_t stream);
+// blocked Cholesky with border rows, one cooperative launch (oak_chol.cu)
+int chol_bordered(double* A, int64_t ld, int n, int rows, int gap, int border_identity, int* d_info,
+                  double* d_logdet, int device, cudaStream_t stream);
 int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_t n_pad,
                      double* out, cudaStream_t stream);
 

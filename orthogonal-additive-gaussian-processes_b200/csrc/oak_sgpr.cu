@@ -484,6 +484,338 @@ extern "C" int oak_sgpr_finish_f64(double* d_Kuu, double* d_stats, int64_t m, in
   return 0;
 }
 
+// =====================================================================================================
+// Round-2 SGPR path: L = chol(Kuu) FIRST, then the statistics on a route chosen on the device.
+//
+//   oak_sgpr_factor_f64   Kuu tiles -> [L ; L^-T] by one bordered Cholesky (oak_chol.cu), a condition
+//                         estimate ||Kuu||_1 * lambda_max(Kuu^-1) (three power iterations on L^-T L^-1) and the
+//                         route flag: 0 = accumulate Phi = Kuf Kuf^T and whiten once in the tail (fast),
+//                         1 = gpflow's operation order, A_r = L^-1 Kuf_r per chunk and Psi = sum A_r A_r^T
+//                         (oak/utils.py:186-190) -- needed when Kuu is ill conditioned: the rounding of Phi is
+//                         amplified by cond(Kuu) in the tail (2e-6 relative ELBO error at cond 2.6e8, 1e-13 at
+//                         1e4), the whitened sum only by sqrt(cond).
+//   oak_sgpr_stats2_f64   the chunk loop; the whitening product and the operand of the contraction are gated
+//                         by the device flag, so no host decision (and no synchronisation) is needed.
+//   oak_sgpr_finish2_f64  B = I + AAT assembled with the border row (L^-1 Kuf y) / noise, factored by the same
+//                         bordered Cholesky, which leaves c = LB^-1 Aerr / sigma in the border; bound; alpha.
+//                         Both `info` codes travel in out[4], out[5]: one read-back per evaluation.
+//
+// d_fac layout (doubles): column-major matrix with leading dimension LD = 2 Mp, Mp = roundup8(M), M columns:
+// rows [0, M) = L (lower triangle), rows [Mp, Mp + M) = L^-T (upper triangle; equivalently the row-major view
+// fac[r * LD + Mp + c] is L^-1); then a 16-double header and 4 Mp doubles of scratch.
+namespace oak {
+
+static inline int64_t fac_mp(int64_t m) { return (m + 7) / 8 * 8; }
+static inline int64_t fac_ld(int64_t m) { return 2 * fac_mp(m); }
+static inline int64_t lb_ld(int64_t m) { return fac_mp(m) + 8; }
+constexpr int kHdrDoubles = 16;
+// header: [0] cond estimate, [1] ||Kuu||_1, [2] lambda_max(Kuu^-1) estimate, [3] route, [4] info of chol(Kuu),
+// [5] sum log diag L, [6] threshold; ints at (int*)(h + 8): [0] route, [1] info_L, [2] tile counter, [3] info_B
+__host__ __device__ static inline int* hdr_ints(double* h) { return reinterpret_cast<int*>(h + 8); }
+
+// one CTA per column j of the factor buffer: jitter, zero padding, unit border row, column 1-norm, start vector
+__global__ void __launch_bounds__(256) fac_init_kernel(double* fac, int m, int mp, int64_t ld, double jitter,
+                                                       double* colsum, double* w0) {
+  __shared__ double sh[256];
+  const int j = blockIdx.x;
+  double* col = fac + (int64_t)j * ld;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < (int)ld; i += 256) {
+    if (i < m) {
+      double v = col[i];
+      if (i == j) {
+        v += jitter;
+        col[i] = v;
+      }
+      acc += fabs(v);
+    } else {
+      col[i] = (i == mp + j) ? 1.0 : 0.0;
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    colsum[j] = sh[0];
+    // fixed +-1 pattern (Knuth multiplicative hash bit), normalised
+    w0[j] = ((((unsigned)j * 2654435761u) >> 7) & 1u) ? rsqrt((double)m) : -rsqrt((double)m);
+  }
+}
+
+__global__ void __launch_bounds__(256) route_kernel(double* hdr, const double* colsum, const double* w_lo,
+                                                    const double* w_hi, int m, int force_route, double threshold) {
+  __shared__ double s0[256], s1[256], s2[256];
+  double mx = 0.0, a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < m; i += 256) {
+    mx = fmax(mx, colsum[i]);
+    a = fma(w_lo[i], w_lo[i], a);
+    b = fma(w_hi[i], w_hi[i], b);
+  }
+  s0[threadIdx.x] = mx;
+  s1[threadIdx.x] = a;
+  s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      s0[threadIdx.x] = fmax(s0[threadIdx.x], s0[threadIdx.x + s]);
+      s1[threadIdx.x] += s1[threadIdx.x + s];
+      s2[threadIdx.x] += s2[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int* hi = hdr_ints(hdr);
+    const double lam = sqrt(s2[0] / s1[0]);
+    const double cond = s0[0] * lam;
+    int route = force_route >= 0 ? (force_route != 0) : (cond >= threshold ? 1 : 0);  // NaN -> 0
+    if (hi[1] != 0) route = force_route > 0 ? 1 : 0;  // failed factorisation: the tail reports it
+    hdr[0] = cond;
+    hdr[1] = s0[0];
+    hdr[2] = lam;
+    hdr[3] = (double)route;
+    hdr[4] = (double)hi[1];
+    hdr[6] = threshold;
+    hi[0] = route;
+  }
+}
+
+// B (lower, column-major ld = ldb) = src / noise + I, border row = v / noise, dvec = diag(src) / noise
+__global__ void __launch_bounds__(256) assemble_B_kernel(const double* __restrict__ psi, const double* __restrict__ s2,
+                                                         const int* __restrict__ route, const double* __restrict__ v,
+                                                         int m, int border_row, int64_t ldb, double inv_noise,
+                                                         double* __restrict__ LB, double* __restrict__ dvec) {
+  const int j = blockIdx.x;
+  const double* src = (*route != 0 ? psi : s2) + (int64_t)j * m;
+  double* col = LB + (int64_t)j * ldb;
+  for (int i = j + threadIdx.x; i < m; i += 256) {
+    const double val = src[i] * inv_noise;
+    if (i == j) {
+      dvec[j] = val;
+      col[i] = val + 1.0;
+    } else {
+      col[i] = val;
+    }
+  }
+  if (threadIdx.x == 0) col[border_row] = v[j] * inv_noise;
+}
+
+// gpflow 2.2.1 SGPR.elbo from the factored pieces; out[0..7]
+__global__ void __launch_bounds__(256) sgpr_bound2_kernel(const double* __restrict__ dvec, const double* __restrict__ LB,
+                                                          int64_t ldb, int border_row, int m, const double* scal,
+                                                          const double* tail, double n_total, double noise,
+                                                          const double* hdr, double* out, double* cvec) {
+  __shared__ double s0[256], s1[256];
+  double tr = 0.0, cc = 0.0;
+  for (int i = threadIdx.x; i < m; i += 256) {
+    tr += dvec[i];
+    const double c = LB[(int64_t)i * ldb + border_row];
+    if (cvec) cvec[i] = c;
+    cc = fma(c, c, cc);
+  }
+  s0[threadIdx.x] = tr;
+  s1[threadIdx.x] = cc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      s0[threadIdx.x] += s0[threadIdx.x + s];
+      s1[threadIdx.x] += s1[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double logdet = scal[0], trace = s0[0], ctc = s1[0];
+    double bound = -0.5 * n_total * log(2.0 * M_PI);
+    bound += -logdet;
+    bound -= 0.5 * n_total * log(noise);
+    bound += -0.5 * tail[1] / noise;
+    bound += 0.5 * ctc;
+    bound += -0.5 * tail[0] / noise;
+    bound += 0.5 * trace;
+    const int* hi = reinterpret_cast<const int*>(hdr + 8);
+    out[0] = bound;
+    out[1] = logdet;
+    out[2] = trace;
+    out[3] = ctc;
+    out[4] = (double)hi[1];
+    out[5] = (double)hi[3];
+    out[6] = (double)hi[0];
+    out[7] = hdr[0];
+  }
+}
+
+}  // namespace oak
+
+extern "C" size_t oak_sgpr_factor_count(int64_t m) {
+  if (m < 1) return 0;
+  return (size_t)(fac_ld(m) * m + kHdrDoubles + 4 * fac_mp(m));
+}
+extern "C" int64_t oak_sgpr_factor_ld(int64_t m) { return m < 1 ? 0 : fac_ld(m); }
+extern "C" int64_t oak_sgpr_lb_ld(int64_t m) { return m < 1 ? 0 : lb_ld(m); }
+
+extern "C" int oak_sgpr_factor_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, int route,
+                                   double cond_threshold, double* d_fac, void* stream_) {
+  OAK_REQUIRE(spec && d_pointsZ && d_fac, "oak_sgpr_factor_f64: null argument");
+  OAK_REQUIRE(m >= 1 && m <= INT32_MAX / 8, "oak_sgpr_factor_f64: bad M");
+  OAK_REQUIRE(reinterpret_cast<uintptr_t>(d_fac) % 16 == 0, "oak_sgpr_factor_f64: d_fac must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cublasHandle_t cb;
+  if (int rc = handles(&cb, nullptr, stream)) return rc;
+  const int64_t mp = fac_mp(m), ld = fac_ld(m);
+  const int M = (int)m;
+  double* hdr = d_fac + ld * m;
+  double* scratch = hdr + kHdrDoubles;  // colsum | wa | wb | wc
+  double *colsum = scratch, *wa = scratch + mp, *wb = scratch + 2 * mp, *wc = scratch + 3 * mp;
+  const double2* pz = (const double2*)d_pointsZ;
+  // Kuu(iv, kernel) (oak/utils.py:185): row-major with pitch LD == column-major (symmetric)
+  if (int rc = gram_launch(spec, pz, padded(m), 0, m, pz, padded(m), 0, m, 1, d_fac, ld, stream)) return rc;
+  fac_init_kernel<<<(unsigned)m, 256, 0, stream>>>(d_fac, M, (int)mp, ld, jitter, colsum, wa);
+  OAK_LAUNCHED();
+  // [L ; L^-T]: L = chol(Kuu + jitter I) (utils.py:188) with the identity as border rows
+  if (int rc = chol_bordered(d_fac, ld, M, 2 * M, (int)(mp - m), 1, hdr_ints(hdr) + 1, hdr + 5, spec->device, stream))
+    return rc;
+  // lambda_max(Kuu^-1) = ||L^-T||_2^2: three power iterations on U U^T, U = L^-T
+  const double* U = d_fac + mp;
+  const double one = 1.0, zero = 0.0;
+  const int LDi = (int)ld;
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, M, M, &one, U, LDi, wa, 1, &zero, wb, 1));
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_N, M, M, &one, U, LDi, wb, 1, &zero, wc, 1));
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, M, M, &one, U, LDi, wc, 1, &zero, wb, 1));
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_N, M, M, &one, U, LDi, wb, 1, &zero, wa, 1));
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, M, M, &one, U, LDi, wa, 1, &zero, wb, 1));
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_N, M, M, &one, U, LDi, wb, 1, &zero, wc, 1));
+  g_launches.fetch_add(6);
+  route_kernel<<<1, 256, 0, stream>>>(hdr, colsum, wa, wc, M, route, cond_threshold > 0.0 ? cond_threshold : 3.0e5);
+  OAK_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t oak_sgpr_stats2_work_bytes(int64_t m, int64_t chunk) {
+  if (m < 0 || chunk < 0) return 0;
+  return (size_t)(2 * m * chunk + chunk) * sizeof(double) + syrk_dmma_work_bytes((int)m);
+}
+
+// Phi (route 0) or Psi = sum (L^-1 Kuf)(L^-1 Kuf)^T (route 1) | Kuf y | sum K_diag | y^T y for the local points,
+// accumulated into d_stats; the route is read on the device from the header of d_fac.
+// d_kuf_store (nullable): keeps every chunk's Kuf block as in oak_sgpr_stats_keep_f64.
+extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
+                                   const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
+                                   double* d_stats, void* d_work, double* d_kuf_store, void* stream_) {
+  OAK_REQUIRE(spec && d_pointsZ && d_fac && d_stats && d_work, "oak_sgpr_stats2_f64: null argument");
+  OAK_REQUIRE(m >= 1, "oak_sgpr_stats2_f64: need at least one inducing point");
+  OAK_REQUIRE(n_local >= 0, "oak_sgpr_stats2_f64: negative n");
+  if (n_local == 0) return 0;
+  OAK_REQUIRE(d_pointsX && d_y, "oak_sgpr_stats2_f64: null data");
+  const int T = tile_rows_for_depth(spec->depth);
+  OAK_REQUIRE(chunk >= T && chunk % T == 0, "oak_sgpr_stats2_f64: chunk must be a multiple of 64");
+  OAK_REQUIRE(m <= INT32_MAX && chunk <= INT32_MAX, "oak_sgpr_stats2_f64: size exceeds cuBLAS int");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cublasHandle_t cb;
+  if (int rc = handles(&cb, nullptr, stream)) return rc;
+  const int64_t mp = fac_mp(m), ld = fac_ld(m);
+  double* hdr = d_fac + ld * m;
+  int* d_route = hdr_ints(hdr);
+  int* d_counter = hdr_ints(hdr) + 2;
+  double* kuf_scratch = (double*)d_work;
+  double* abuf = kuf_scratch + m * chunk;
+  double* kdiag = abuf + m * chunk;
+  double* partials = kdiag + chunk;
+  const size_t partial_bytes = syrk_dmma_work_bytes((int)m);
+  double* phi = d_stats;
+  double* kufy = d_stats + m * m;
+  double* tail = kufy + m;
+  const double2* pz = (const double2*)d_pointsZ;
+  const double2* px = (const double2*)d_pointsX;
+  const int64_t m_pad = padded(m), n_pad = padded(n_local);
+  const double one = 1.0;
+  for (int64_t c0 = 0; c0 < n_local; c0 += chunk) {
+    const int64_t nc = (n_local - c0 < chunk) ? (n_local - c0) : chunk;
+    double* kuf = d_kuf_store ? d_kuf_store + (c0 / chunk) * m * chunk : kuf_scratch;
+    if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream)) return rc;
+    // route 1: A_r = L^-1 Kuf_r (utils.py:189), a no-op launch otherwise
+    if (int rc = panel_gemm_dmma(d_fac + mp, ld, kuf, chunk, abuf, chunk, (int)m, (int)m, nc, 1, nullptr, nullptr,
+                                 d_route, d_counter, spec->device, stream))
+      return rc;
+    if (int rc = syrk_lower_dmma((int)m, nc, kuf, chunk, phi, partials, partial_bytes, spec->device, stream, abuf,
+                                 d_route))
+      return rc;
+    OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, (int)nc, (int)m, &one, kuf, (int)chunk, d_y + c0, 1, &one, kufy, 1));
+    g_launches.fetch_add(1);
+    if (int rc = gram_diag_launch(spec, px + c0, nc, n_pad, kdiag, stream)) return rc;
+    reduce_accumulate_kernel<<<1, 1024, 0, stream>>>(kdiag, nullptr, nc, tail + 0);
+    OAK_LAUNCHED();
+  }
+  {
+    const int64_t seg = 4096;
+    int64_t blocks = (n_local + seg - 1) / seg;
+    if (blocks > chunk) blocks = chunk;
+    const int64_t seg_len = (n_local + blocks - 1) / blocks;
+    reduce_segments_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_y, d_y, n_local, seg_len, kdiag);
+    OAK_LAUNCHED();
+    reduce_accumulate_kernel<<<1, 1024, 0, stream>>>(kdiag, nullptr, blocks, tail + 1);
+    OAK_LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" size_t oak_sgpr_finish2_work_bytes(int64_t m) {
+  if (m < 1) return 0;
+  return (size_t)(2 * m * m + 4 * fac_mp(m) + 16) * sizeof(double);
+}
+
+// d_LB: lb_ld(m) * m doubles, column-major: rows [0, M) = LB (lower), row Mp = c^T.
+// d_out[8] = elbo, sum log diag LB, tr(AAT), c^T c, info of chol(Kuu), info of chol(B), route, cond estimate.
+extern "C" int oak_sgpr_finish2_f64(double* d_fac, double* d_stats, int64_t m, int64_t n_total, double noise,
+                                    double* d_out, double* d_alpha, double* d_LB, void* d_work, void* stream_) {
+  OAK_REQUIRE(d_fac && d_stats && d_out && d_LB && d_work, "oak_sgpr_finish2_f64: null argument");
+  OAK_REQUIRE(m >= 1 && m <= INT32_MAX / 8, "oak_sgpr_finish2_f64: bad M");
+  OAK_REQUIRE(noise > 0.0, "oak_sgpr_finish2_f64: likelihood variance must be positive");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cublasHandle_t cb;
+  if (int rc = handles(&cb, nullptr, stream)) return rc;
+  int dev = 0;
+  OAK_CUDA(cudaGetDevice(&dev));
+  const int64_t mp = fac_mp(m), ld = fac_ld(m), ldb = lb_ld(m);
+  const int M = (int)m;
+  double* hdr = d_fac + ld * m;
+  int* hi = hdr_ints(hdr);
+  const double* U = d_fac + mp;  // L^-T, column-major upper
+  double* W = (double*)d_work;
+  double* S2 = W + m * m;
+  double* vtmp = S2 + m * m;
+  double* dvec = vtmp + mp;
+  double* cvec = dvec + mp;
+  double* scal = cvec + mp;  // [0] sum log diag LB
+  double* phi = d_stats;
+  double* kufy = d_stats + m * m;
+  double* tail = kufy + m;
+  const double one = 1.0, zero = 0.0;
+  // route 0: sigma^2 AAT = L^-1 Phi L^-T = U^T (Phi U)   (utils.py:189-190 with A = L^-1 Kuf / sigma);
+  // computed unconditionally (0.2 ms), the assemble kernel picks its source by the device flag
+  OAK_CUBLAS(cublasDsymm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, M, M, &one, phi, M, U, (int)ld, &zero, W, M));
+  OAK_CUBLAS(cublasDtrmm(cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, M, &one,
+                         U, (int)ld, W, M, S2, M));
+  // sigma Aerr = L^-1 Kuf y   (utils.py:194)
+  OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, M, M, &one, U, (int)ld, kufy, 1, &zero, vtmp, 1));
+  g_launches.fetch_add(3);
+  // B = AAT + I (utils.py:190-191) with the border row Aerr / sigma; LB = chol(B) leaves c in the border
+  assemble_B_kernel<<<(unsigned)m, 256, 0, stream>>>(phi, S2, hi, vtmp, M, (int)mp, ldb, 1.0 / noise, d_LB, dvec);
+  OAK_LAUNCHED();
+  if (int rc = chol_bordered(d_LB, ldb, M, M + 1, (int)(mp - m), 0, hi + 3, scal, dev, stream)) return rc;
+  sgpr_bound2_kernel<<<1, 256, 0, stream>>>(dvec, d_LB, ldb, (int)mp, M, scal, tail, (double)n_total, noise, hdr,
+                                            d_out, cvec);
+  OAK_LAUNCHED();
+  if (d_alpha) {
+    // alpha = L^-T LB^-T c (utils.py:197-198)
+    OAK_CUBLAS(cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, M, d_LB, (int)ldb, cvec, 1));
+    OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_N, M, M, &one, U, (int)ld, cvec, 1, &zero, d_alpha, 1));
+    g_launches.fetch_add(2);
+  }
+  return 0;
+}
+
 extern "C" size_t oak_gpr_finish_work_bytes(int64_t n) {
   if (n < 1 || n > INT32_MAX) return 0;
   cusolverDnHandle_t cs;

@@ -40,6 +40,8 @@ constexpr size_t kSmemBytes = (size_t)kStages * kStageDoubles * sizeof(double);
 
 struct SyrkParams {
   const double* A;   // row-major [m][lda], k contiguous
+  const double* A_alt;  // operand used instead of A when *route != 0 (the whitened block L^-1 Kuf), or null
+  const int* route;     // device-side route flag of the SGPR statistics, or null
   double* partial;   // [units][64][64]
   int64_t lda;
   int m, k_steps;    // k_steps = number of 16-wide k stages (the caller zero-pads the last one)
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(syrk::kThreads, OAK_SYRK_MINB) syrk_lower_dmma
   const int lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;  // 2 x 2 warps, 32 x 32 each
   const int g = lane >> 2, q = lane & 3;    // fragment row / k-lane
+  const double* const Aop = (prm.route != nullptr && *prm.route != 0) ? prm.A_alt : prm.A;
 
   for (int u = blockIdx.x; u < prm.units; u += gridDim.x) {
     const int s = u / prm.tiles, t = u - s * prm.tiles;
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(syrk::kThreads, OAK_SYRK_MINB) syrk_lower_dmma
         const int row = idx / kChunks, chunk = idx % kChunks;  // row 0..127 (A rows 0..63, B rows 64..127)
         const int grow = (row < kTile) ? bi * kTile + row : bj * kTile + (row - kTile);
         const bool ok = grow < prm.m;
-        const double* src = prm.A + (int64_t)(ok ? grow : 0) * prm.lda + kbase + chunk * 2;
+        const double* src = Aop + (int64_t)(ok ? grow : 0) * prm.lda + kbase + chunk * 2;
         cp_async16_zfill(dst + row * kRowStride + chunk * 2, src, ok);
       }
       asm volatile("cp.async.commit_group;\n");
@@ -259,7 +262,7 @@ size_t syrk_dmma_work_bytes(int m) {
 // C(lower, column-major m x m) += A A^T, A row-major [m][lda] with k valid columns; columns
 // [k, roundup16(k)) of A must be readable (they are zeroed here).  `work` holds the partials.
 int syrk_lower_dmma(int m, int64_t k, double* A, int64_t lda, double* C, double* work, size_t work_bytes,
-                    int device, cudaStream_t stream) {
+                    int device, cudaStream_t stream, double* A_alt, const int* d_route) {
   using namespace syrk;
   if (m <= 0 || k <= 0) return 0;
   const int64_t k_pad = (k + kKT - 1) / kKT * kKT;
@@ -268,8 +271,13 @@ int syrk_lower_dmma(int m, int64_t k, double* A, int64_t lda, double* C, double*
   if (k_pad > k)
     OAK_CUDA(cudaMemset2DAsync(A + k, (size_t)lda * sizeof(double), 0, (size_t)(k_pad - k) * sizeof(double), (size_t)m,
                                stream));
+  if (k_pad > k && A_alt)
+    OAK_CUDA(cudaMemset2DAsync(A_alt + k, (size_t)lda * sizeof(double), 0, (size_t)(k_pad - k) * sizeof(double),
+                               (size_t)m, stream));
   SyrkParams prm;
   prm.A = A;
+  prm.A_alt = A_alt;
+  prm.route = A_alt ? d_route : nullptr;
   prm.partial = work;
   prm.lda = lda;
   prm.m = m;

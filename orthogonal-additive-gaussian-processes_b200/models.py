@@ -4,9 +4,9 @@ Stand-ins for the gpflow 2.2.1 model classes the reference instantiates
 (``oak/model_utils.py:149-159``): same attribute paths (``.data``, ``.kernel``,
 ``.likelihood.variance``, ``.inducing_variable.Z``) and methods (``log_marginal_likelihood``,
 ``elbo``, ``maximum_log_likelihood_objective``, ``training_loss``, ``predict_f``).  The Gram /
-Kuf tiles and the SGPR statistics run in ``liboak_b200.so``; the dense M^3 / N^3 tails go through
-cuSOLVER / cuBLAS inside the same library.  With ``torch.distributed`` initialised, each rank holds
-a shard of (X, y) and the packed statistics are combined by one all-reduce.
+Kuf tiles, the SGPR statistics and the M^3 tail (a one-launch bordered Cholesky) run in ``liboak_b200.so``.
+With ``distributed=True`` each rank holds a shard of (X, y) and the packed statistics are combined by one
+all-reduce.
 """
 from __future__ import annotations
 
@@ -48,7 +48,7 @@ class GPModel(Module):
     def log_prior_density(self) -> float:
         total = 0.0
         for p in collect_parameters(self):
-            if p.prior is not None:
+            if p.prior is not None and p.trainable:  # gpflow sums over trainable_parameters only
                 total += float(np.sum(p.prior.log_prob(p.numpy())))
         return total
 
@@ -104,6 +104,8 @@ class GPR(GPModel):
     def predict_f(self, Xnew, full_cov: bool = False) -> Tuple[object, object]:
         import torch
 
+        if full_cov:
+            raise NotImplementedError("marginal variances only (what the reference reads, model_utils.py:429-443)")
         host = _device.is_host(Xnew)
         Xd, _ = self._device_data()
         Xs = self._slice_for_kernel(Xd)
@@ -111,6 +113,7 @@ class GPR(GPModel):
         Kfac, _, alpha = self._factorise()
         spec = self.kernel._make_spec()
         try:
+            self.kernel._check_discrete(Xn, spec._keep)
             pn, px = _device.Points(spec, Xn), _device.Points(spec, Xs)
             Kns = _device.gram(spec, pn, px)  # (N*, N)
             kdiag = _device.gram_diag(spec, pn)
@@ -124,24 +127,44 @@ class GPR(GPModel):
 
 
 class SGPR(GPModel):
-    """Titsias' sparse GP regression bound (gpflow 2.2.1 ``SGPR``; model_utils.py:150-155)."""
+    """Titsias' sparse GP regression bound (gpflow 2.2.1 ``SGPR``; model_utils.py:150-155).
+
+    Every evaluation factors Kuu first (``oak_sgpr_factor_f64``) and picks, on the device, between the
+    un-whitened statistics Phi = Kuf Kuf^T (fast) and gpflow's operation order A = L^-1 Kuf, A A^T
+    (``whiten_stats``: None = from the condition estimate of Kuu, True / False = forced); one device-to-host
+    read per evaluation carries the bound and both Cholesky status codes.
+
+    ``distributed=True`` declares that every rank holds its own SHARD of (X, y): the packed statistics are then
+    summed over the ranks by one all-reduce and ``elbo`` / ``predict_f`` / ``sufficient_statistics`` become
+    collective calls.  It is never inferred from ``torch.distributed`` being initialised: ranks that each hold
+    the full data set (a generic DDP launch) would otherwise count it world-size times."""
 
     def __init__(self, data, kernel, inducing_variable, mean_function=None, noise_variance: float = 1.0,
-                 chunk: int = 262144, distributed: Optional[bool] = None):
+                 chunk: int = 262144, distributed: bool = False, whiten_stats: Optional[bool] = None,
+                 cond_threshold: float = 0.0):
         super().__init__(data, kernel, mean_function, noise_variance)
         if not isinstance(inducing_variable, InducingPoints):
             inducing_variable = InducingPoints(inducing_variable)
         self.inducing_variable = inducing_variable
         self.chunk = int(chunk)
-        # each rank holds a shard of (X, y) when torch.distributed is initialised
-        self.distributed = parallel.is_distributed() if distributed is None else bool(distributed)
+        self.distributed = bool(distributed)
+        if self.distributed and not parallel.is_distributed():
+            raise ValueError("distributed=True needs an initialised torch.distributed process group (world size > 1)")
+        self.whiten_stats = whiten_stats
+        self.cond_threshold = float(cond_threshold)
+        self.last_route = None      # route / condition estimate of the last evaluation (diagnostics)
+        self.last_cond_estimate = None
         self.last_timings = {}
 
     def _Z_device(self):
         return self._slice_for_kernel(_device.to_device(value_of(self.inducing_variable.Z)))
 
+    def _route(self) -> int:
+        return _device.ROUTE_AUTO if self.whiten_stats is None else int(bool(self.whiten_stats))
+
     def _statistics(self, want_alpha: bool):
-        """Returns (out[4], alpha, L-factor buffer, LB-factor buffer, n_total)."""
+        """Returns (tail, factor, n_total): ``tail.out`` = [elbo, sum log diag LB, tr AAT, c^T c, info, info, route,
+        cond]; nothing has been synchronised yet (``tail.host()`` does, and raises on a failed factorisation)."""
         Xd, Yd = self._device_data()
         Xs = self._slice_for_kernel(Xd)
         Zs = self._Z_device()
@@ -150,34 +173,40 @@ class SGPR(GPModel):
             self.kernel._check_discrete(Xs, spec._keep)
             self.kernel._check_discrete(Zs, spec._keep)
             pz, px = _device.Points(spec, Zs), _device.Points(spec, Xs)
-            stats = _device.sgpr_stats(spec, pz, px, Yd, chunk=self.chunk)
+            # Kuu(iv, kernel) + jitter I, L = chol, L^-1, route flag -- before the statistics, all on the device
+            fac = _device.sgpr_factor(spec, pz, DEFAULT_JITTER, route=self._route(), cond_threshold=self.cond_threshold)
+            stats = _device.sgpr_stats2(spec, pz, px, Yd, fac, chunk=self.chunk)
             n_total = int(Xs.shape[0])
             if self.distributed:
                 parallel.allreduce_sum_(stats)
                 n_total = parallel.allreduce_int(n_total)
-            Kuu = _device.gram(spec, pz)  # Kuu(iv, kernel); the jitter is added in the tail
         finally:
             spec.close()
-        out, alpha = _device.sgpr_finish(Kuu, stats, n_total, scalar_of(self.likelihood.variance),
-                                         DEFAULT_JITTER, want_alpha=want_alpha)
-        m = Kuu.shape[0]
-        return out, alpha, Kuu, stats[: m * m].view(m, m), n_total
+        tail = _device.sgpr_finish2(fac, stats, n_total, scalar_of(self.likelihood.variance), want_alpha=want_alpha)
+        return tail, fac, n_total
+
+    def _record(self, o):
+        self.last_route, self.last_cond_estimate = int(o[6]), float(o[7])
 
     def elbo(self) -> float:
-        return float(self._statistics(False)[0][0].item())
+        o = self._statistics(False)[0].host()
+        self._record(o)
+        return float(o[0])
 
     def maximum_log_likelihood_objective(self) -> float:
         return self.elbo()
 
     def sufficient_statistics(self):
         """alpha = L^-T LB^-T c, shape (M, 1) (oak/utils.py:195-198)."""
-        return self._statistics(True)[1].reshape(-1, 1)
+        tail = self._statistics(True)[0]
+        self._record(tail.host())
+        return tail.alpha.reshape(-1, 1)
 
     def predict_mean(self, Xnew):
         """Mean of ``predict_f`` only (what ``oak_model.predict`` uses, model_utils.py:429-443):
         Kus^T alpha through the fused Gram-matrix/vector tiles, no (M, N*) intermediate."""
         host = _device.is_host(Xnew)
-        alpha = self._statistics(True)[1]
+        alpha = self.sufficient_statistics()
         Xn = self._slice_for_kernel(_device.to_device(Xnew))
         Zs = self._Z_device()
         spec = self.kernel._make_spec()
@@ -191,22 +220,24 @@ class SGPR(GPModel):
     def predict_f(self, Xnew, full_cov: bool = False):
         import torch
 
+        if full_cov:
+            raise NotImplementedError("marginal variances only (what the reference reads, model_utils.py:429-443)")
         host = _device.is_host(Xnew)
-        out, alpha, Lbuf, LBbuf, _ = self._statistics(True)
+        tail, fac, _ = self._statistics(True)
+        self._record(tail.host())
         Xn = self._slice_for_kernel(_device.to_device(Xnew))
         Zs = self._Z_device()
         spec = self.kernel._make_spec()
         try:
+            self.kernel._check_discrete(Xn, spec._keep)
             pn, pz = _device.Points(spec, Xn), _device.Points(spec, Zs)
             Kus = _device.gram(spec, pz, pn)  # (M, N*)
             kdiag = _device.gram_diag(spec, pn)
         finally:
             spec.close()
-        mean = Kus.T @ alpha.reshape(-1, 1)
-        L = torch.triu(Lbuf).T
-        LB = torch.triu(LBbuf).T
-        tmp1 = torch.linalg.solve_triangular(L, Kus, upper=False)
-        tmp2 = torch.linalg.solve_triangular(LB, tmp1, upper=False)
+        mean = Kus.T @ tail.alpha.reshape(-1, 1)
+        tmp1 = torch.linalg.solve_triangular(fac.L(), Kus, upper=False)
+        tmp2 = torch.linalg.solve_triangular(tail.LB(), tmp1, upper=False)
         var = (kdiag + (tmp2 * tmp2).sum(0) - (tmp1 * tmp1).sum(0)).reshape(-1, 1)
         return _device.from_device(mean, host), _device.from_device(var, host)
 

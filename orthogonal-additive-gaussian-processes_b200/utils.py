@@ -52,16 +52,14 @@ def get_model_sufficient_statistics(m, get_L: bool = True):
         Qinv = Linv.T @ ((1.0 - s2)[:, None] * Linv)
         return alpha_h, torch.linalg.cholesky(torch.linalg.inv(Qinv)).cpu().numpy()
     if isinstance(m, SGPR):
-        out, alpha, Lbuf, LBbuf, _ = m._statistics(True)
-        alpha_h = alpha.reshape(-1, 1).cpu().numpy()
+        tail, fac, _ = m._statistics(True)
+        tail.host()  # raises when a factorisation failed
+        alpha_h = tail.alpha.reshape(-1, 1).cpu().numpy()
         if not get_L:
             return alpha_h
-        # effective L (utils.py:200-204): inv(L^-1 - LB^-1 L^-1); dense M x M library solves
-        L = torch.triu(Lbuf).T
-        LB = torch.triu(LBbuf).T
-        eye = torch.eye(L.shape[0], dtype=L.dtype, device=L.device)
-        LAi = torch.linalg.solve_triangular(L, eye, upper=False)
-        LBiLAi = torch.linalg.solve_triangular(LB, LAi, upper=False)
+        # effective L (utils.py:200-204): inv(L^-1 - LB^-1 L^-1); L^-1 comes with the factor
+        LAi = fac.Linv()
+        LBiLAi = torch.linalg.solve_triangular(tail.LB(), LAi, upper=False)
         return alpha_h, torch.linalg.inv(LAi - LBiLAi).cpu().numpy()
     if isinstance(m, GPR):
         Kfac, _, alpha = m._factorise()

@@ -8,7 +8,7 @@ from oak_b200.models import SGPR
 from oak_b200.workloads import build_kernel, config_C
 n = int(os.environ.get("AB_N", 125_000))
 cfg = config_C(n, 20, 1024, 3)
-model = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=65536)
+model = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=262144)
 model.likelihood.variance.assign(cfg["noise"])
 Xd, Yd = model._device_data()
 for _ in range(3): model.elbo()
@@ -22,14 +22,17 @@ t_spec, _ = T(lambda: kern._make_spec().close())
 spec = kern._make_spec()
 Zs = model._Z_device()
 t_zdev, _ = T(model._Z_device)
+t_chk, _ = T(lambda: (kern._check_discrete(Xd, spec._keep), kern._check_discrete(Zs, spec._keep)))
 t_pz, pz = T(lambda: _device.Points(spec, Zs))
 t_px, px = T(lambda: _device.Points(spec, Xd))
-t_stats, stats = T(lambda: _device.sgpr_stats(spec, pz, px, Yd, chunk=65536))
-t_kuu, Kuu = T(lambda: _device.gram(spec, pz))
-def fin():
-    return _device.sgpr_finish(Kuu.clone(), stats.clone(), n, 0.01, DEFAULT_JITTER, want_alpha=False)
-t_fin, out = T(fin)
-t_clone, _ = T(lambda: (Kuu.clone(), stats.clone()))
-t_item, _ = T(lambda: float(out[0][0].item()))
-print(f"N={n}: elbo total {t_total:.3f} ms | spec create+destroy {t_spec:.3f} | Z to device {t_zdev:.3f} | Points(Z) {t_pz:.3f} | "
-      f"Points(X) {t_px:.3f} | stats {t_stats:.3f} | Kuu gram {t_kuu:.3f} | finish {t_fin - t_clone:.3f} (+clone {t_clone:.3f}) | item {t_item:.3f}")
+t_fac, fac = T(lambda: _device.sgpr_factor(spec, pz, DEFAULT_JITTER))
+t_stats, stats = T(lambda: _device.sgpr_stats2(spec, pz, px, Yd, fac, chunk=262144))
+t_fin, tail = T(lambda: _device.sgpr_finish2(fac, stats, n, 0.01, want_alpha=False))
+t_item, _ = T(lambda: tail.host())
+print(f"N={n}: elbo total {t_total:.3f} ms | spec create+destroy {t_spec:.3f} | Z to device {t_zdev:.3f} | check_discrete {t_chk:.3f} | "
+      f"Points(Z) {t_pz:.3f} | Points(X) {t_px:.3f} | factor front {t_fac:.3f} | stats {t_stats:.3f} | finish {t_fin:.3f} | "
+      f"readback {t_item:.3f} | route {model.last_route} cond {model.last_cond_estimate:.3e}")
+for route in (0, 1):
+    f2 = _device.sgpr_factor(spec, pz, DEFAULT_JITTER, route=route)
+    t_s, _ = T(lambda: _device.sgpr_stats2(spec, pz, px, Yd, f2, chunk=262144), reps=5)
+    print(f"  stats phase, forced route {route}: {t_s:.3f} ms")
