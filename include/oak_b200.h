@@ -124,6 +124,14 @@ int oak_gram_f64(const oak_spec* spec, const void* d_points, int64_t n, const vo
 int oak_gram_lower_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
                        int64_t row_end, double* d_K, int64_t ldk, void* stream);
 
+/* oak_gram_lower_f64 plus the mirror image of the strip: d_Kt is a (row_end x (row_end - row_begin)) block,
+ * d_Kt[j*ldkt + (i-row_begin)] = K(i, j) for the entries of the off-diagonal tiles (tiles on the diagonal are
+ * written in full to d_K).  The strips of all ranks then hold the whole symmetric matrix between them -- the
+ * same product as the single-GPU oak_gram_f64 call -- still without a collective. */
+int oak_gram_lower_mirror_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                              int64_t row_end, double* d_K, int64_t ldk, double* d_Kt, int64_t ldkt,
+                              void* stream);
+
 /* Replaces OAKKernel.K_diag(X) (oak_kernel.py:267-278). d_out[n]. */
 int oak_gram_diag_f64(const oak_spec* spec, const void* d_points, int64_t n, double* d_out,
                       void* stream);

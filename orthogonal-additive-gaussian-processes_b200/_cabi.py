@@ -71,6 +71,7 @@ SIGNATURES = {
     "oak_prepare_points_f64": (C.c_int, [_vp, _dp, _i64, _i64, _vp, _vp]),
     "oak_gram_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _dp, _i64, _vp]),
     "oak_gram_lower_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _i64, _vp]),
+    "oak_gram_lower_mirror_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _dp, _i64, _dp, _i64, _vp]),
     "oak_gram_diag_f64": (C.c_int, [_vp, _vp, _i64, _dp, _vp]),
     "oak_gram_matvec_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _dp, _dp, _vp]),
     "oak_component_gram_f64": (C.c_int, [_vp, C.POINTER(_i32), _i32, _vp, _i64, _vp, _i64, _dp, _i64, _vp]),

@@ -139,6 +139,25 @@ def gram_lower(spec: Spec, px: Points, row_begin: int, row_end: int, out=None):
     return out
 
 
+def gram_lower_mirror(spec: Spec, px: Points, row_begin: int, row_end: int, out=None, out_t=None):
+    """``gram_lower`` plus the mirror image of the strip's off-diagonal tiles: returns (K[rows, :row_end],
+    Kt[:row_end, rows]) -- a rank's share of the full symmetric matrix."""
+    torch = _torch()
+    rows = row_end - row_begin
+    if out is None:
+        out = torch.empty((rows, row_end), dtype=torch.float64, device=px.buf.device)
+    if out_t is None:
+        out_t = torch.empty((row_end, rows), dtype=torch.float64, device=px.buf.device)
+    if rows > 0:
+        check(
+            _cabi.load().oak_gram_lower_mirror_f64(spec.handle, _p(px.buf), px.n, row_begin, row_end, _p(out),
+                                                   int(out.stride(0)), _p(out_t), int(out_t.stride(0)),
+                                                   C.c_void_p(stream_ptr())),
+            "oak_gram_lower_mirror_f64",
+        )
+    return out, out_t
+
+
 def gram_matvec(spec: Spec, px: Points, px2: Points, alpha, out=None):
     """out[i] = sum_j K(px_i, px2_j) alpha_j, fused (no N x N2 matrix)."""
     torch = _torch()

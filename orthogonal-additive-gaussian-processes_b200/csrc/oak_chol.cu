@@ -7,9 +7,9 @@
 //
 //   for each 64-column panel
 //     phase 1  every CTA that owns rows of the panel factors the 64 x 64 diagonal block redundantly in
-//              shared memory (right-looking, one barrier per pivot), inverts it (16 -> 32 -> 64 blocked
-//              triangular inverse) and solves its 16-row tiles of the panel as a small matrix product
-//              X = A21 inv(L11)^T; CTA 0 writes L11 back
+//              registers (right-looking on the bordered block [S ; I]: one barrier per pivot, L11 and
+//              inv(L11) come out together) and solves its 16-row tiles of the panel as a small matrix
+//              product X = A21 inv(L11)^T; CTA 0 writes L11 back
 //     grid barrier
 //     phase 2  trailing update C -= X X^T on the 64 x 64 tiles of the lower triangle (4 x 4 register
 //              micro-tiles, FP64 FMA), one tile per CTA at M = 1024
@@ -25,6 +25,8 @@
 // Column-major storage (leading dimension ld); only the lower triangle of the symmetric block is read
 // and written.  `gap` unused rows may separate the symmetric block from the border (alignment).
 #include <cooperative_groups.h>
+
+#include <type_traits>
 
 #include "oak_common.cuh"
 
@@ -50,6 +52,19 @@ struct CholParams {
   double* logdet;          // optional: sum_i log L_ii
 };
 
+#ifdef OAK_CHOL_TIMING  // development aid: per-panel phase boundaries (cycles) of CTA 0
+__device__ long long g_chol_t[64 * 8];
+__device__ long long g_chol_t2[256 * 4];  // per CTA, panel 1: phase-1 cycles, phase-2 cycles, tiles
+#define OAK_CHOL_T(slot)                                                                      \
+  do {                                                                                        \
+    if (blockIdx.x == 0 && tid == 0 && j0 / NB < 64) g_chol_t[(j0 / NB) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define OAK_CHOL_T(slot) \
+  do {                   \
+  } while (0)
+#endif
+
 __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const CholParams prm) {
   using namespace chol;
   cg::grid_group grid = cg::this_grid();
@@ -72,115 +87,98 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
     const int j1 = j0 + nb;
     const int r_end = prm.border_identity ? min(prm.rows, n + j1) : prm.rows;
     const int trsm_tiles = (r_end - j1 + TR - 1) / TR;
+    OAK_CHOL_T(0);
     if (blockIdx.x == 0 || (int)blockIdx.x < trsm_tiles) {
-      // ---- diagonal block -> shared memory (padded with the identity) ----------------------
-      for (int e = tid; e < NB * NB; e += kThreads) {
-        const int i = e & (NB - 1), k = e >> 6;
-        double v = (i == k) ? 1.0 : 0.0;
-        if (i < nb && k < nb && i >= k) v = A[(int64_t)(j0 + k) * ld + j0 + i];
-        S[k * LD + i] = v;
+      // ---- diagonal block: L11 and inv(L11) together, trailing matrix in registers -----------------
+      // Thread (i, kq) = (tid & 63, tid >> 6) owns row i, columns k = kq + 4u (u = 0..15) of the UNIFIED
+      // 64 x 64 matrix W: W(i, k) = S(i, k) for k <= i (the symmetric block being factored) and the border
+      // E(i, k) for k > i, E = I on entry (its unit diagonal is implicit).  Factoring [S ; E] right-looking
+      // leaves L11 below the diagonal and E L11^-T = inv(L11)^T above it, so the triangular inverse costs no
+      // separate pass.  Per pivot j: the owners of column j publish it through a double-buffered shared
+      // vector, ONE barrier, every thread forms its multiplier m_i and updates its registers:
+      //   W(i, k) -= m_i l_kj   for k > j and (k <= i  [S part, i > j]  or  i <= j  [E part]).
+      const int i = tid & (NB - 1), kq = tid >> 6;
+      double w[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int k = kq + 4 * u;
+        double v = 0.0;
+        if (k <= i) {
+          v = (i == k) ? 1.0 : 0.0;  // padding: identity
+          if (i < nb) v = A[(int64_t)(j0 + k) * ld + j0 + i];
+        }
+        w[u] = v;
       }
-      __syncthreads();
+      OAK_CHOL_T(1);
       int failj = -1;
-      {
-        const int i = tid & (NB - 1);
-        for (int j = 0; j < NB; ++j) {
-          const double ajj = S[j * LD + j];
+      double* const Cs = rd;  // 2 x NB doubles (rd | lg): the published column, double buffered
+      // Groups of four pivots; the register slots ROTATE so that the group's own columns always sit in slot 0
+      // and the loop body is the same code for every group (a fully unrolled 64-pivot body is ~100 KB of
+      // straight-line code executed once per panel: instruction-fetch bound, measured 22 us against 6).
+      // Two copies of the body: 16 live slots for the first eight groups, 8 for the rest.
+      auto pivot_group = [&](const int g, auto slots_tag) -> bool {
+        constexpr int kSlots = decltype(slots_tag)::value;
+#pragma unroll
+        for (int jq = 0; jq < 4; ++jq) {
+          const int j = 4 * g + jq;
+          double* const C = Cs + (jq & 1) * NB;
+          if (kq == jq) C[i] = w[0];
+          __syncthreads();
+          const double ajj = C[j];
           if (!(ajj > 0.0) || !(ajj < 1.0e300)) {  // uniform: every thread reads the same value
             failj = j;
-            break;
+            return false;
           }
-          const double ljj = sqrt(ajj);
           const double rs = rsqrt(ajj);
-          const double sij = S[j * LD + i];
-          if (tid < NB) Lc[j * LD + i] = (i > j) ? sij * rs : (i == j ? ljj : 0.0);
-          if (i > j) {
-            const double lij = sij * rs;
-            for (int k = j + 1 + (tid >> 6); k <= i; k += 4) {
-              const double lkj = S[j * LD + k] * rs;
-              S[k * LD + i] = fma(-lij, lkj, S[k * LD + i]);
+          const double mi = (i == j) ? rs : C[i] * rs;
+          if (kq == jq) {
+            if (i > j) {
+              Lc[j * LD + i] = mi;            // L(i, j)
+            } else if (i == j) {
+              Lc[j * LD + j] = ajj * rs;      // sqrt(a_jj) without a second long-latency chain in this warp
+              Inv[j * LD + j] = rs;
+            } else {
+              Inv[i * LD + j] = mi;           // inv(L11)(j, i) = (L11^-T)(i, j)
             }
           }
-          __syncthreads();
+          const double mrs = -mi * rs;
+          const int klim = (i <= j) ? NB - 1 : i;
+#pragma unroll
+          for (int u = 0; u < kSlots; ++u) {
+            const int k = kq + 4 * (g + u);
+            if (k > j && k <= klim) w[u] = fma(mrs, C[k], w[u]);
+          }
         }
+#pragma unroll
+        for (int u = 0; u + 1 < 16; ++u) w[u] = w[u + 1];
+        w[15] = 0.0;
+        return true;
+      };
+      {
+        bool ok = true;
+#pragma unroll 1
+        for (int g = 0; g < 8 && ok; ++g) ok = pivot_group(g, std::integral_constant<int, 16>{});
+#pragma unroll 1
+        for (int g = 8; g < 16 && ok; ++g) ok = pivot_group(g, std::integral_constant<int, 8>{});
       }
+      __syncthreads();
+      OAK_CHOL_T(2);
       if (failj >= 0) {
         if (blockIdx.x == 0 && tid == 0) *prm.info = j0 + failj + 1;
       } else {
         if (blockIdx.x == 0) {
           for (int e = tid; e < NB * NB; e += kThreads) {
-            const int i = e & (NB - 1), k = e >> 6;
-            if (i < nb && k < nb && i >= k) A[(int64_t)(j0 + k) * ld + j0 + i] = Lc[k * LD + i];
+            const int r = e & (NB - 1), k = e >> 6;
+            if (r < nb && k < nb && r >= k) A[(int64_t)(j0 + k) * ld + j0 + r] = Lc[k * LD + r];
           }
-          if (tid < NB) lg[tid] = log(Lc[tid * LD + tid]);  // padded pivots are 1 -> 0
-        }
-        // ---- inv(L11): 16 x 16 diagonal blocks by substitution, then 32, then 64 by products -
-        if (tid < NB) rd[tid] = 1.0 / Lc[tid * LD + tid];
-        for (int e = tid; e < kBlk; e += kThreads) Inv[e] = 0.0;
-        __syncthreads();
-        if (blockIdx.x == 0 && tid == 0) {
-          for (int i = 0; i < nb; ++i) logsum += lg[i];
-        }
-        if (tid < NB) {
-          const int c = tid, b0 = c & ~15, cl = c & 15;
-          double x[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            double s = (i == cl) ? 1.0 : 0.0;
-#pragma unroll
-            for (int k = 0; k < i; ++k) s = fma(-Lc[(b0 + k) * LD + b0 + i], x[k], s);
-            x[i] = (i >= cl) ? s * rd[b0 + i] : 0.0;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) Inv[c * LD + b0 + i] = x[i];
-        }
-        __syncthreads();
-        // 32-level: Inv21 = -Inv22 (L21 Inv11) for both 32-blocks; T1 staged in S
-        {
-          const int hb = tid >> 7, o = tid & 127;
-          const int R0 = 32 * hb + 16, C0 = 32 * hb;
-          const int r = o & 15;
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = (o >> 4) + 8 * u;
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) s = fma(Lc[(C0 + k) * LD + R0 + r], Inv[(C0 + c) * LD + C0 + k], s);
-            S[(C0 + c) * LD + R0 + r] = s;
-          }
+          if (tid < NB) S[tid] = log(Lc[tid * LD + tid]);  // padded pivots are 1 -> 0
           __syncthreads();
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int c = (o >> 4) + 8 * u;
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) s = fma(Inv[(R0 + k) * LD + R0 + r], S[(C0 + c) * LD + R0 + k], s);
-            Inv[(C0 + c) * LD + R0 + r] = -s;
+          if (tid == 0) {
+            for (int r = 0; r < nb; ++r) logsum += S[r];
           }
           __syncthreads();
         }
-        // 64-level
-        {
-          const int r = tid & 31;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = (tid >> 5) + 8 * u;
-            double s = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) s = fma(Lc[k * LD + 32 + r], Inv[c * LD + k], s);
-            S[c * LD + 32 + r] = s;
-          }
-          __syncthreads();
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = (tid >> 5) + 8 * u;
-            double s = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) s = fma(Inv[(32 + k) * LD + 32 + r], S[c * LD + 32 + k], s);
-            Inv[c * LD + 32 + r] = -s;
-          }
-          __syncthreads();
-        }
+        OAK_CHOL_T(3);
         // ---- panel solve: X = A21 inv(L11)^T on this CTA's 16-row tiles ----------------------
         for (int t = blockIdx.x; t < trsm_tiles; t += gridDim.x) {
           const int r0 = j1 + t * TR;
@@ -210,15 +208,30 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
         }
       }
     }
+    OAK_CHOL_T(4);
+#ifdef OAK_CHOL_TIMING
+    long long tb_ = clock64();
+    if (j0 == NB && tid == 0 && blockIdx.x < 256) g_chol_t2[blockIdx.x * 4 + 0] = tb_ - g_chol_t2[blockIdx.x * 4 + 3];
+#endif
     __threadfence();
     grid.sync();
+    OAK_CHOL_T(5);
+#ifdef OAK_CHOL_TIMING
+    tb_ = clock64();
+#endif
     if (*(volatile int*)prm.info != 0) break;  // uniform: written before the barrier
     if (j1 >= n) break;
     // ---- trailing update: C -= X X^T on the tiles that touch the lower triangle / the border ---
+    // FP64 tensor cores (DMMA m8n8k4): 8 warps as 4 x 2, warp tile 16 x 32; both operands are panel rows staged
+    // k-major with stride 68 (conflict-free fragment loads: lane (g, q) reads [4 ks + q][.. + g]).
     {
+      constexpr int LX = NB + 4;
+      double* const Xa = sm;
+      double* const Xb = sm + NB * LX;
       const int rt_count = (r_end - j1 + NB - 1) / NB, ct_count = (n - j1 + NB - 1) / NB;
       const int total = ct_count * rt_count - ct_count * (ct_count - 1) / 2;
-      const int tx = tid & 15, ty = tid >> 4;
+      const int lane = tid & 31, warp = tid >> 5;
+      const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
       for (int u = blockIdx.x; u < total; u += gridDim.x) {
         int ct = 0, rem = u;
         while (rem >= rt_count - ct) {
@@ -230,41 +243,57 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
         for (int e = tid; e < NB * NB; e += kThreads) {
           const int r = e & (NB - 1), k = e >> 6;
           const bool kk = k < nb;
-          S[k * LD + r] = (kk && rbase + r < r_end) ? A[(int64_t)(j0 + k) * ld + grow(rbase + r)] : 0.0;
-          Lc[k * LD + r] = (kk && cbase + r < n) ? A[(int64_t)(j0 + k) * ld + cbase + r] : 0.0;
+          Xa[k * LX + r] = (kk && rbase + r < r_end) ? A[(int64_t)(j0 + k) * ld + grow(rbase + r)] : 0.0;
+          Xb[k * LX + r] = (kk && cbase + r < n) ? A[(int64_t)(j0 + k) * ld + cbase + r] : 0.0;
         }
         __syncthreads();
-        double acc[4][4];
+        double acc[2][4][2];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+          for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const double* pa = Xa + q * LX + wm * 16 + g;
+        const double* pb = Xb + q * LX + wn * 32 + g;
 #pragma unroll 4
-        for (int k = 0; k < NB; ++k) {
-          double av[4], bv[4];
+        for (int ks = 0; ks < NB / 4; ++ks) {
+          double av[2], bv[4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) av[a] = S[k * LD + tx + 16 * a];
+          for (int a = 0; a < 2; ++a) av[a] = pa[ks * 4 * LX + a * 8];
 #pragma unroll
-          for (int b = 0; b < 4; ++b) bv[b] = Lc[k * LD + ty + 16 * b];
+          for (int b = 0; b < 4; ++b) bv[b] = pb[ks * 4 * LX + b * 8];
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            for (int b = 0; b < 4; ++b)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                           : "+d"(acc[a][b][0]), "+d"(acc[a][b][1])
+                           : "d"(av[a]), "d"(bv[b]));
         }
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = cbase + ty + 16 * b;
-          if (c >= n) continue;
+        for (int a = 0; a < 2; ++a) {
+          const int r = rbase + wm * 16 + a * 8 + g;
+          if (r >= r_end) continue;
+          const int64_t gr = grow(r);
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            const int r = rbase + tx + 16 * a;
-            if (r < r_end && r >= c) A[(int64_t)c * ld + grow(r)] -= acc[a][b];
-          }
+          for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = cbase + wn * 32 + b * 8 + 2 * q + e;
+              if (c < n && r >= c) A[(int64_t)c * ld + gr] -= acc[a][b][e];
+            }
         }
       }
     }
+    OAK_CHOL_T(6);
+#ifdef OAK_CHOL_TIMING
+    if (j0 == NB && tid == 0 && blockIdx.x < 256) g_chol_t2[blockIdx.x * 4 + 1] = clock64() - tb_;
+#endif
     __threadfence();
     grid.sync();
+    OAK_CHOL_T(7);
+#ifdef OAK_CHOL_TIMING
+    if (j0 == 0 && tid == 0 && blockIdx.x < 256) g_chol_t2[blockIdx.x * 4 + 3] = clock64();  // start of panel 1
+#endif
   }
   if (blockIdx.x == 0 && tid == 0 && prm.logdet) *prm.logdet = logsum;
 }
@@ -313,6 +342,15 @@ int chol_bordered(double* A, int64_t ld, int n, int rows, int gap, int border_id
 }  // namespace oak
 
 using namespace oak;
+
+#ifdef OAK_CHOL_TIMING
+extern "C" int oak_debug_chol_timing(long long* h_out) {
+  OAK_CUDA(cudaDeviceSynchronize());
+  OAK_CUDA(cudaMemcpyFromSymbol(h_out, g_chol_t, sizeof(long long) * 64 * 8));
+  OAK_CUDA(cudaMemcpyFromSymbol(h_out + 64 * 8, g_chol_t2, sizeof(long long) * 256 * 4));
+  return 0;
+}
+#endif
 
 // Cholesky factorisation with border rows of a column-major matrix (equivalently: the UPPER triangle of
 // the row-major view).  Replaces the tf.linalg.cholesky + tf.linalg.triangular_solve pairs of

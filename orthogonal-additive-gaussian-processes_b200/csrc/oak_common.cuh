@@ -112,7 +112,8 @@ int tile_rows_for_depth(int depth);
 // coordinates, see points_minmax); row/column ranges select the part to evaluate.
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
-                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream);
+                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt = nullptr,
+                int64_t ldkt = 0);
 // per-dimension min / max keys of the prepared coordinate: [D] min keys then [D] max keys
 inline const unsigned long long* points_minmax(const oak_spec* spec, const double2* pts, int64_t n_pad) {
   return reinterpret_cast<const unsigned long long*>(pts + (int64_t)spec->D * n_pad);

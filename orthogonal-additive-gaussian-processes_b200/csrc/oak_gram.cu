@@ -46,7 +46,10 @@ struct GramParams {
   int64_t row_begin, row_end, col_begin, n2;  // n2 = number of output columns
   int64_t tiles_n, num_tiles;
   int D, Dc, device;
-  int symmetric;        // 0 general, 1 lower-triangle tiles + mirrored stores, 2 lower trapezoid only
+  int symmetric;        // 0 general, 1 lower-triangle tiles + mirrored stores, 2 lower trapezoid only,
+                        // 3 lower trapezoid of a row strip + its mirror image into a second buffer (Kt)
+  double* Kt;           // mode 3: (n2 x rows) block, Kt[j * ldkt + (i - row_begin)] = K(i, j) of the off-diagonal tiles
+  int64_t ldkt;
   int64_t tile_row0;    // global TN-row-block index of row_begin (modes 1, 2)
   const unsigned long long* mm_row;  // [2 D] min / max keys of the prepared coordinates, or null
   const unsigned long long* mm_col;
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
 #pragma unroll
       for (int c = 0; c < RN; ++c) acc[r][c][0] = finish<P, ALGO>(acc[r][c], prm.sigma2);
 
-    const bool mirror = prm.symmetric == 1 && !diag;
+    const bool mirror = (prm.symmetric == 1 || prm.symmetric == 3) && !diag;
     const int64_t nrows = prm.row_end - prm.row_begin;
     const int64_t ldk = prm.ldk;
     const int64_t trow = row0 + ty * RM;  // first row / first column of this thread
@@ -456,13 +459,15 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
     }
     if (mirror && !prm.use_tma) {
       // direct mirrored stores (odd leading dimension / unaligned output)
-      double* const mp = prm.K + tcol * ldk + trow;  // row = column index, column = row index
+      // row = column index (< n2), column = row index relative to the strip (< nrows)
+      const int64_t ldm = prm.symmetric == 3 ? prm.ldkt : ldk;
+      double* const mp = (prm.symmetric == 3 ? prm.Kt : prm.K) + tcol * ldm + trow;
 #pragma unroll
       for (int c = 0; c < RN; ++c) {
-        if (tcol + TXD * c < nrows) {
+        if (tcol + TXD * c < prm.n2) {
 #pragma unroll
           for (int r = 0; r < RM; ++r)
-            if (trow + r < prm.n2) __stcs(mp + (int64_t)(TXD * c) * ldk + r, acc[r][c][0]);
+            if (trow + r < nrows) __stcs(mp + (int64_t)(TXD * c) * ldm + r, acc[r][c][0]);
         }
       }
     }
@@ -535,9 +540,14 @@ static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream)
   // 2-D TMA stores need a 16-byte aligned output with an even leading dimension
   static const int no_tma = env_int("OAK_GRAM_NOTMA", 0);
   prm.use_tma = 0;
-  if (prm.symmetric == 1 && !no_tma && (prm.ldk % 2 == 0) && (reinterpret_cast<uintptr_t>(prm.K) % 16 == 0) &&
-      (TM % 16 == 0) && kThreads / 32 >= TM / 16 && prm.n2 < (1ll << 31) && rows < (1ll << 31)) {
-    if (encode_output_map(&prm.tm_mir, prm.K, prm.n2, rows, prm.ldk, TN) == 0) prm.use_tma = 1;
+  if ((prm.symmetric == 1 || prm.symmetric == 3) && !no_tma && (TM % 16 == 0) && kThreads / 32 >= TM / 16 &&
+      prm.n2 < (1ll << 31) && rows < (1ll << 31)) {
+    // the mirror image: memory rows = columns of K, memory columns = rows of the strip
+    double* const mbase = prm.symmetric == 3 ? prm.Kt : prm.K;
+    const int64_t mld = prm.symmetric == 3 ? prm.ldkt : prm.ldk;
+    if (mld % 2 == 0 && reinterpret_cast<uintptr_t>(mbase) % 16 == 0 &&
+        encode_output_map(&prm.tm_mir, mbase, rows, prm.n2, mld, TN) == 0)
+      prm.use_tma = 1;
   }
   const size_t smem = L::bytes(prm.use_tma != 0);
   auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO, MINB>;
@@ -735,8 +745,10 @@ static int launch_matvec(GramParams prm, int algo, int sms, const double* alpha,
 
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
-                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream) {
+                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt, int64_t ldkt) {
   GramParams prm;
+  prm.Kt = Kt;
+  prm.ldkt = ldkt;
   for (int p = 0; p <= OAK_MAX_DEPTH; ++p) prm.sigma2[p] = spec->sigma2[p];
   prm.pts_row = prow;
   prm.pts_col = pcol;
@@ -839,6 +851,8 @@ extern "C" int oak_gram_matvec_f64(const oak_spec* spec, const void* d_points, i
   prm.Dc = spec->Dc;
   prm.device = spec->device;
   prm.symmetric = 0;
+  prm.Kt = nullptr;
+  prm.ldkt = 0;
   prm.tile_row0 = 0;
   prm.num_tiles = 0;
   prm.mm_row = prm.mm_col = nullptr;
@@ -869,4 +883,21 @@ extern "C" int oak_gram_lower_f64(const oak_spec* spec, const void* d_points, in
   return gram_launch(spec, (const double2*)d_points, padded(n), row_begin, row_end,
                      (const double2*)d_points, padded(n), 0, row_end, 2, d_K, ldk,
                      (cudaStream_t)stream_);
+}
+
+// The same lower trapezoid plus its mirror image: d_Kt is an (row_end x (row_end - row_begin)) block with
+// d_Kt[j * ldkt + (i - row_begin)] = K(i, j) for every entry of the off-diagonal tiles (the diagonal tiles are
+// written in full to d_K), so that the strips of all ranks together hold the whole symmetric matrix -- the
+// product of the single-GPU call -- without a collective.
+extern "C" int oak_gram_lower_mirror_f64(const oak_spec* spec, const void* d_points, int64_t n, int64_t row_begin,
+                                         int64_t row_end, double* d_K, int64_t ldk, double* d_Kt, int64_t ldkt,
+                                         void* stream_) {
+  OAK_REQUIRE(spec && d_points, "oak_gram_lower_mirror_f64: null argument");
+  OAK_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= n,
+              "oak_gram_lower_mirror_f64: row range outside [0, n]");
+  if (row_end == row_begin) return 0;
+  OAK_REQUIRE(d_K && d_Kt, "oak_gram_lower_mirror_f64: null output");
+  OAK_REQUIRE(ldk >= row_end && ldkt >= row_end - row_begin, "oak_gram_lower_mirror_f64: leading dimension too small");
+  return gram_launch(spec, (const double2*)d_points, padded(n), row_begin, row_end, (const double2*)d_points, padded(n),
+                     0, row_end, 3, d_K, ldk, (cudaStream_t)stream_, d_Kt, ldkt);
 }

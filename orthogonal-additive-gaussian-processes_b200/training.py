@@ -10,7 +10,8 @@ matrix is ever formed.
 
 Supported trainable parameters: RBF lengthscales under every measure (Gaussian -- the OAK default
 after the normalising flow --, empirical, uniform, mixture of Gaussians, or none), the order variances sigma^2_0..P
-(``share_var_across_orders=True``), the likelihood variance, the base variances s^2 of the RBF sub-kernels
+(``share_var_across_orders=True``; with ``False`` only sigma^2_0 exists and the sub-kernels' own variances carry
+the scale, oak_kernel.py:217-221), the likelihood variance, the base variances s^2 of the RBF sub-kernels
 where the reference keeps them trainable, and W / kappa of the categorical sub-kernels (through the
 cotangent of their B tables), and the inducing points Z of SGPR when ``zfixed=False``
 (``oak_gram_backward_rows_f64``; the columns of discrete sub-kernels carry no gradient, as under
@@ -57,10 +58,18 @@ def _transform_grad(p: Parameter) -> np.ndarray:
 
 
 def _prior_grad(p: Parameter) -> np.ndarray:
-    """d log prior / d constrained value (only the Gamma prior of the order variances exists)."""
+    """d log prior / d constrained value.  The reference only attaches Gamma(1, 0.2) to the order variances
+    (oak/model_utils.py:163-165); a prior object may also bring its own ``grad_log_prob``."""
+    from ._gpflow_shim import Gamma
+
     x = p.numpy()
     pr = p.prior
-    return (pr.concentration - 1.0) / x - pr.rate
+    if isinstance(pr, Gamma):
+        return (pr.concentration - 1.0) / x - pr.rate
+    if hasattr(pr, "grad_log_prob"):
+        return np.asarray(pr.grad_log_prob(x), dtype=np.float64)
+    raise NotImplementedError(f"gradient of the prior {type(pr).__name__} is not implemented (Gamma, or a prior with "
+                              "grad_log_prob)")
 
 
 def _lengthscale_parameter(sub):
@@ -135,8 +144,9 @@ def _check_trainables(model, spec_dims):
             raise NotImplementedError(
                 "gradient of a trainable parameter outside (RBF lengthscales, order / base variances, likelihood "
                 f"variance, categorical W / kappa, inducing points) is not implemented ({p!r}); set it non-trainable (freeze_unsupported)")
-    if not getattr(model.kernel, "share_var_across_orders", True):
-        raise NotImplementedError("backward tiles need share_var_across_orders=True")
+    # share_var_across_orders=False (Duvenaud-style, oak_kernel.py:217-221, 262-265): the spec carries
+    # sigma^2_n = 1 for n >= 1, only variances[0] exists as a Parameter and the base variances of the sub-kernels
+    # are the trainable scales -- all of them already have gradients (order slot 0, base-variance and table slots)
     for p, d in zip(ls, spec_dims):
         if p is not None and p.trainable and d.type != _cabi.DIM_RBF:
             raise NotImplementedError("a lengthscale on a non-RBF sub-kernel cannot be differentiated")
@@ -515,17 +525,31 @@ def optimise(model, method: str = "BFGS", maxiter: int = 1000, data=None, **opti
     params = trainable_parameters(model)
     u0 = np.concatenate([np.asarray(p.unconstrained_variable, dtype=np.float64).reshape(-1) for p in params])
 
+    state = {"finite": 0, "rejected": 0}
+
     def fun(u):
         _assign_unconstrained(params, u)
         try:
-            return training_loss_and_grad(model, data)
+            out = training_loss_and_grad(model, data)
         except (RuntimeError, _cabi.OakNativeError) as exc:
-            # a line-search trial point whose Kuu / K + noise I is not numerically positive definite:
-            # report a huge loss so that the step is shortened (gpflow's Scipy wrapper would abort here)
+            # a line-search TRIAL point whose Kuu / K + noise I is not numerically positive definite: report a
+            # huge loss so that the step is shortened.  At the initial point (no finite loss seen yet) this is an
+            # error of the model, not of the step: re-raise, as gpflow's Scipy wrapper would.
             if "positive" not in str(exc) and "Cholesky" not in str(exc):
                 raise
+            if state["finite"] == 0:
+                raise
+            state["rejected"] += 1
             return 1e25, np.zeros_like(u)
+        if np.isfinite(out[0]):
+            state["finite"] += 1
+        return out
 
     res = minimize(fun, u0, jac=True, method=method, options=dict(maxiter=maxiter, **options))
     _assign_unconstrained(params, res.x)
+    if state["rejected"]:
+        import warnings
+
+        warnings.warn(f"optimise: {state['rejected']} line-search trial point(s) rejected (matrix not positive definite)")
+    res.rejected_trial_points = state["rejected"]
     return res

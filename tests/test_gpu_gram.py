@@ -195,6 +195,43 @@ def test_lower_trapezoid_strips_cover_the_lower_triangle():
     spec.close()
 
 
+@pytest.mark.parametrize("odd_pitch", [False, True])
+def test_mirrored_strips_hold_the_whole_symmetric_matrix(odd_pitch):
+    """oak_gram_lower_mirror_f64: every rank's strip plus its mirror image; together, bit for bit, the matrix the
+    single-GPU symmetric call writes (the multi-GPU bench arm computes the same product as N = 1).  An odd
+    pitch of the mirror block takes the direct-store path instead of the TMA stores."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.parallel import balanced_symmetric_rows
+
+    n = 1100
+    cfg = _gauss_cfg(n, 6, 4, seed=14)
+    k = _product(cfg)
+    spec = k._make_spec()
+    px = _device.Points(spec, _device.to_device(cfg["X"]))
+    full = _device.gram(spec, px)
+    for G in (1, 2, 4):
+        got = torch.full_like(full, float("nan"))
+        for strips in balanced_symmetric_rows(n, G):
+            for b, e in strips:
+                if e <= b:
+                    continue
+                K = torch.full((e - b, e), float("nan"), dtype=torch.float64, device="cuda")
+                pitch = (e - b) + (1 if (e - b) % 2 == 0 else 0) if odd_pitch else (e - b + 1) // 2 * 2
+                Ktb = torch.full((e, pitch), float("nan"), dtype=torch.float64, device="cuda")
+                Kt = Ktb[:, : e - b]
+                _device.gram_lower_mirror(spec, px, b, e, out=K, out_t=Kt)
+                assert torch.isnan(Ktb[:, e - b:]).all()      # nothing outside the block
+                blk = got[b:e, :e]
+                got[b:e, :e] = torch.where(torch.isnan(K), blk, K)
+                blk = got[:e, b:e]
+                got[:e, b:e] = torch.where(torch.isnan(Kt), blk, Kt)
+        assert not torch.isnan(got).any()
+        assert torch.equal(got, full)
+    spec.close()
+
+
 def test_torch_inputs_stay_on_device():
     import torch
 

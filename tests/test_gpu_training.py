@@ -603,3 +603,61 @@ def test_training_with_trainable_inducing_points_improves_the_bound():
     res = optimise(m, maxiter=30)
     assert res.fun < loss0 - 1.0
     assert np.abs(m.inducing_variable.Z.numpy() - Z0).max() > 1e-3
+
+
+# ---- share_var_across_orders=False (Duvenaud-style prod(1 + k_i)) ------------------------------
+@pytest.mark.parametrize("sparse", [True, False])
+def test_share_var_false_model_has_gradients_and_trains(sparse):
+    """create_model_oak(share_var_across_orders=False): only variances[0] exists, the sub-kernels' own variances
+    (RBF base variance, binary variance) are trainable (oak_kernel.py:163-166, 217-221).  The gradient of the
+    training loss in the unconstrained variables is checked against central differences of the loss itself, then
+    BFGS must improve it (the reference trains this model: test_oak_model / model_utils.py:395-427)."""
+    from oak_b200.model_utils import create_model_oak
+    from oak_b200.training import _assign_unconstrained, optimise, trainable_parameters, training_loss_and_grad
+
+    rng = np.random.default_rng(21)
+    n = 260
+    X = rng.standard_normal((n, 3))
+    X[:, 2] = (rng.random(n) < 0.4).astype(float)
+    y = (np.sin(X[:, 0]) + 0.5 * X[:, 1] * X[:, 2] + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
+    y = (y - y.mean()) / y.std()
+    model = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=X[:30].copy() if sparse else None,
+                             optimise=False, share_var_across_orders=False, p0=[None, None, 0.6], p=[None, None, None])
+    assert len(model.kernel.variances) == 1
+    params = trainable_parameters(model)
+    # variances[0], 2 x (RBF variance, lengthscale), binary variance, likelihood variance
+    assert len(params) == 1 + 4 + 1 + 1
+    u0 = np.concatenate([np.asarray(p.unconstrained_variable, dtype=np.float64).reshape(-1) for p in params])
+    loss0, g = training_loss_and_grad(model)
+    assert np.isfinite(loss0) and g.shape == u0.shape and np.all(g != 0.0)
+    h = 1e-5
+    fd = np.zeros_like(u0)
+    for i in range(u0.size):
+        up, um = u0.copy(), u0.copy()
+        up[i] += h
+        um[i] -= h
+        _assign_unconstrained(params, up)
+        lp = model.training_loss()
+        _assign_unconstrained(params, um)
+        lm = model.training_loss()
+        fd[i] = (lp - lm) / (2 * h)
+    _assign_unconstrained(params, u0)
+    assert max_rel_err(g, fd) < 1e-5
+    res = optimise(model, method="BFGS", maxiter=8)
+    assert res.fun < loss0 - 1e-3
+
+
+def test_optimise_raises_when_the_initial_point_is_not_positive_definite():
+    """A Cholesky failure at the FIRST evaluation is the model's problem, not a line-search trial step: gpflow's
+    Scipy wrapper raises there, and so must optimise() instead of returning 'converged' with a zero gradient."""
+    from oak_b200._cabi import OakNativeError
+    from oak_b200.model_utils import create_model_oak
+    from oak_b200.training import optimise
+
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((120, 2))
+    y = rng.standard_normal((120, 1))
+    X[7, 0] = np.nan  # poisons Kuu / Kuf: the factorisation fails at the initial point
+    model = create_model_oak((X, y), max_interaction_depth=2, inducing_pts=X[:20].copy(), optimise=False)
+    with pytest.raises((RuntimeError, OakNativeError)):
+        optimise(model, method="BFGS", maxiter=3)
