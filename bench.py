@@ -5,16 +5,17 @@ Contract: ``python bench.py --gpus N --steps K --warmup W`` (under torchrun for 
 JSON line on rank 0.  A *step* is one pass of the hot path over the workload:
 
   headline   config B of BASELINE.json: K(X, X), N=65536, D=16, max_interaction_depth=4, FP64,
-             prepare + fused Gram kernel, inputs resident in HBM.  N=1: lower-triangle tiles +
-             mirrored stores (full matrix written).  N>1: folded row strips, each rank evaluates
-             the lower trapezoid of its strips (no collective) -> strong scaling of a fixed N.
-             value = unique entries N(N+1)/2 per evaluation / time (the work model of BASELINE.md).
-  e2e        the same metric through the host-buffer C-ABI call (oak_gram_host_f64): pinned NumPy
-             X in, H2D, prepare, row-blocked Gram, D2H of the rows into pinned host memory.
-  extra      config C: SGPR ELBO evals/s (N=1M, D=20, M=1024, depth 3), N axis sharded over ranks,
-             one all-reduce of M^2+M+2 doubles, M^3 tail timed separately; the training step (ELBO +
-             gradient through the backward tiles) with fixed and with trainable inducing points; one
-             evaluation of configs A, D, E; the widening rows (SVGP objective, flow objective pass).
+             prepare + fused Gram kernel, inputs resident in HBM; the FULL symmetric matrix is written on
+             every N: one GPU evaluates lower-triangle tiles + mirrored stores; N>1 ranks own folded row
+             strips and write the lower trapezoid of each strip and its mirror image (same product, no
+             collective) -> strong scaling of a fixed N.  value = unique entries N(N+1)/2 / time.
+             config_B_sweep: the same at N = 8k, 16k, 32k, 64k.
+  e2e        the same metric through the host-buffer C-ABI call (oak_gram_host_lower_f64): pinned NumPy
+             X in, H2D, prepare, row-blocked lower trapezoids, D2H of every unique entry into pinned host memory.
+  sgpr_elbo  config C: SGPR ELBO evals/s (N=1M, D=20, M=1024, depth 3), N axis sharded over ranks, L = chol(Kuu)
+             first, route chosen on the device, one all-reduce of M^2+M+2 doubles; statistics / factor front /
+             tail / all-reduce timed separately; the training step (ELBO + gradient through the backward tiles).
+  extra      one evaluation of configs A, D, E and an A-shaped Gram; the widening rows (SVGP, flow objective).
   roofline   FP64-pipe bound: algorithmic flop (306 slots x 2 per unique entry) / Gram-kernel time
              (CUDA events on the launch stream) / measured DFMA peak of the same run.
   cpu_baseline  the reference op sequence (oracle/cpu_baseline.py, torch-CPU FP64, all host cores)
@@ -46,7 +47,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=65536, help="Gram size (config B: 8k..64k)")
     ap.add_argument("--n-e2e", type=int, default=0, help="Gram size of the host-buffer leg (0 = auto)")
-    ap.add_argument("--n-cpu", type=int, default=4096, help="sample size of the CPU baseline")
+    ap.add_argument("--n-cpu", type=int, default=8192, help="sample size of the CPU baseline (BASELINE.md section 4)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the N = 8k / 16k / 32k points of config B")
     ap.add_argument("--elbo-n", type=int, default=1_000_000)
     ap.add_argument("--elbo-m", type=int, default=1024)
     ap.add_argument("--no-elbo", action="store_true")
@@ -185,53 +187,115 @@ def mem_available_gb():
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_gram_sample(n_cpu, reps, warm=0):
+def _host_threads():
+    """All host cores, whatever torchrun put into OMP_NUM_THREADS (it exports 1 to every rank)."""
+    import torch
+
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_gram_sample(n_cpu, reps, warm=0, keep=False):
     """Reference op sequence on the host cores: K(X, X) of config B at N=n_cpu. Returns
-    (unique entries/s, seconds per evaluation, threads)."""
+    (unique entries/s, seconds per evaluation, threads, K of the last evaluation or None)."""
     import torch
 
     from oak_b200.workloads import config_B
     from oracle import cpu_baseline
 
     cpu_baseline.tune_allocator()
+    threads = _host_threads()
     cfg = config_B(n_cpu)
     X = torch.as_tensor(cfg["X"])
     cpu_baseline.gram(cfg, X[:512])  # warm the thread pool / allocator
     for _ in range(warm):
         cpu_baseline.gram(cfg, X)
-    ts = []
+    ts, K = [], None
     for _ in range(reps):
         t0 = time.perf_counter()
         K = cpu_baseline.gram(cfg, X)
         ts.append(time.perf_counter() - t0)
-        del K
+        if not keep:
+            K = None
     ts.sort()
     t = ts[len(ts) // 2]
-    return n_cpu * (n_cpu + 1) / 2 / t, t, torch.get_num_threads()
+    return n_cpu * (n_cpu + 1) / 2 / t, t, threads, K
+
+
+def cpu_elbo_sample(n_slice, m, reps=1):
+    """gpflow SGPR.elbo with the unfused OAK kernel on a slice of config C (N=20000, M=1024)."""
+    import torch
+
+    from oak_b200.workloads import config_C
+    from oracle import cpu_baseline
+
+    _host_threads()
+    cfg = config_C(n_slice, 20, m, 3)
+    X, Y, Z = (torch.as_tensor(cfg[k]) for k in ("X", "y", "Z"))
+    ts, val = [], None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        val = cpu_baseline.sgpr_elbo(cfg, X, Y, Z, cfg["noise"])
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    return cfg, val, ts[len(ts) // 2]
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path (restated op sequence: TensorFlow / gpflow are not
+    installable here) on ALL host cores; under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-
     n = args.n_cpu
-    val, t_eval, threads = cpu_gram_sample(n, args.steps, warm=args.warmup)
+    val, t_eval, threads, _ = cpu_gram_sample(n, max(args.steps, 1), warm=max(args.warmup, 1))
+    _, _, t_elbo = cpu_elbo_sample(20000, args.elbo_m, reps=1)
     line = {
         "impl": "reference",
         "metric": "OAK Gram entries/sec (FP64)", "value": val, "unit": "unique entries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_eval * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"config B: OAK Gram K(X,X) D=16 depth=4 FP64; reference CPU op sequence on a "
-                               f"bounded sample N={n} (the unfused path needs ~(D+P+2) N^2 x 8 B)"},
+                               f"bounded sample N={n} (BASELINE.md section 4: the unfused path needs "
+                               f"~(D+P+2) N^2 x 8 B, N=16k+ does not fit)"},
         "cpu_baseline": {"value": val, "unit": "unique entries/s", "cores": threads, "kind": "port",
                          "sample": f"K(X,X) N={n}, D=16, depth=4, median of {args.steps} after {args.warmup} warm-ups; "
-                                   "TensorFlow/gpflow not installable -> oracle/cpu_baseline.py (torch-CPU FP64)"},
+                                   "TensorFlow/gpflow not installable -> oracle/cpu_baseline.py (torch-CPU FP64)",
+                         "elbo_evals_per_s_scaled_to_n1e6": 1.0 / (t_elbo * 1e6 / 20000),
+                         "elbo_sample": f"config C slice N=20000, M={args.elbo_m}: {t_elbo:.2f} s per evaluation, "
+                                        "scaled linearly in N"},
         "e2e": {"value": val, "unit": "unique entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that pinned host buffers are first-touched
+    on the GPU's NUMA node (8 ranks writing 1 GB each over PCIe into one node's memory is what held the 8-GPU
+    host-buffer leg at 11 GB/s per rank in round 1)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByUUID(ClockSampler._physical_id(local)) \
+            if ClockSampler._physical_id(local).startswith("GPU-") else pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -240,6 +304,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+
+    import ctypes as C
 
     import numpy as np
     import torch
@@ -256,7 +322,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _cabi.require_device()
-    import ctypes as C
+    warm = max(args.warmup, 3)
 
     def barrier():
         if world > 1:
@@ -272,115 +338,138 @@ def main():
 
     # ---- measured FP64 peak (roofline denominator) -------------------------------------------
     peak_slots = _device.measure_fp64_peak(1.0)
-
-    # ---- headline: config B -------------------------------------------------------------------
-    n = args.n
-    cfg = config_B(n)
-    kern = build_kernel(cfg)
-    kern.esp_algorithm = args.algo
-    spec = kern._make_spec()
-    Xd = _device.to_device(cfg["X"])
-    if world == 1:
-        out = torch.empty((n, n), dtype=torch.float64, device="cuda")
-        strips = [(0, n)]
-    else:
-        strips = [s for s in parallel.balanced_symmetric_rows(n, world)[rank] if s[1] > s[0]]
-        outs = [torch.empty((e - b, e), dtype=torch.float64, device="cuda") for b, e in strips]
-    kev = []  # (start, end) events bracketing the Gram kernel launches of each timed step
-
-    def step(record=False):
-        px = _device.Points(spec, Xd)  # per-point prologue (O(N D))
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        if world == 1:
-            _device.gram(spec, px, out=out)
-        else:
-            for (b, e), o in zip(strips, outs):
-                _device.gram_lower(spec, px, b, e, out=o)
-        if record:
-            e1.record()
-            kev.append((e0, e1))
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    launches0 = _cabi.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step(record=True)
-    ev1.record()
-    torch.cuda.synchronize()
-    launches = _cabi.launch_count() - launches0
-    clocks = sampler.stop()
-    barrier()
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    kern_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in kev) / len(kev))
-    unique = n * (n + 1) / 2
-    value = unique / (ms_step * 1e-3)
-    # per-rank algorithmic work of the dominant kernel (unique entries of this rank's strips)
-    my_unique = sum((e - b) * (b + e + 1) / 2 for b, e in strips)
-    my_unique = max_over_ranks(my_unique)
-    achieved_tflops = my_unique * SLOTS_B * 2 / (kern_ms * 1e-3) / 1e12
     peak_tflops = 2 * peak_slots / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("gram_kernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    ncu_file = {}
+    try:
+        ncu_file = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     hbm_peak = 6521.4
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    out_bytes = (n * n if world == 1 else sum((e - b) * e for b, e in strips)) * 8.0
+
+    # ---- config B: symmetric Gram, the same product on every N -----------------------------------
+    # N = 1: lower-triangle tiles + mirrored stores, the full matrix on one GPU.  N > 1: folded row strips; every
+    # rank evaluates the lower trapezoid of its strips AND writes their mirror image (oak_gram_lower_mirror_f64),
+    # so the ranks hold the full matrix between them: the same product, no collective.
+    def gram_leg(n, steps, sample_clocks=False):
+        cfg = config_B(n)
+        kern = build_kernel(cfg)
+        kern.esp_algorithm = args.algo
+        spec = kern._make_spec()
+        Xd = _device.to_device(cfg["X"])
+        if world == 1:
+            strips = [(0, n)]
+            outs = [torch.empty((n, n), dtype=torch.float64, device="cuda")]
+        else:
+            strips = [s for s in parallel.balanced_symmetric_rows(n, world)[rank] if s[1] > s[0]]
+            outs = [(torch.empty((e - b, e), dtype=torch.float64, device="cuda"),
+                     torch.empty((e, e - b), dtype=torch.float64, device="cuda")) for b, e in strips]
+        kev = []
+
+        def step(record=False):
+            px = _device.Points(spec, Xd)  # per-point prologue (O(N D))
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            if world == 1:
+                _device.gram(spec, px, out=outs[0])
+            else:
+                for (b, e), (o, ot) in zip(strips, outs):
+                    _device.gram_lower_mirror(spec, px, b, e, out=o, out_t=ot)
+            if record:
+                e1.record()
+                kev.append((e0, e1))
+
+        for _ in range(warm):
+            step()
+        sampler = ClockSampler(local) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        launches0 = _cabi.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            step(record=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        launches = _cabi.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        ms_step = max_over_ranks(ev0.elapsed_time(ev1) / steps)
+        kern_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in kev) / len(kev))
+        unique = n * (n + 1) / 2
+        my_unique = max_over_ranks(sum((e - b) * (b + e + 1) / 2 for b, e in strips))
+        achieved = my_unique * SLOTS_B * 2 / (kern_ms * 1e-3) / 1e12
+        out_bytes = max_over_ranks(float(n) * n * 8.0 if world == 1 else 16.0 * sum((e - b) * (b + e) / 2 for b, e in strips))
+        spec.close()
+        del outs
+        torch.cuda.empty_cache()
+        return {"n": n, "ms_per_step": ms_step, "kernel_ms": kern_ms, "value": unique / (ms_step * 1e-3),
+                "roofline_frac": achieved / peak_tflops, "achieved_tflops": achieved, "out_bytes": out_bytes,
+                "launches": int(launches), "clocks": clocks}
+
+    sweep = []
+    if not args.no_sweep:
+        for n_s in (8192, 16384, 32768):
+            if n_s < args.n:
+                r = gram_leg(n_s, 3)
+                sweep.append({k: r[k] for k in ("n", "ms_per_step", "value", "roofline_frac")})
+    head = gram_leg(args.n, args.steps, sample_clocks=True)
+    sweep.append({k: head[k] for k in ("n", "ms_per_step", "value", "roofline_frac")})
+    n = args.n
+    value, ms_step, kern_ms, clocks, launches = head["value"], head["ms_per_step"], head["kernel_ms"], head["clocks"], head["launches"]
     roofline = {
         "bound": "fp64",
         "bound_note": "FP64 (DFMA) pipe: neither of the template's roofs binds -- 8 B of HBM traffic per entry "
                       "against >= 242 FP64 instructions, no tensor-core work in this kernel; the hbm sub-object "
                       "carries the HBM line",
-        "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tflops / peak_tflops, "traffic": traffic,
+        "achieved": head["achieved_tflops"], "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": head["roofline_frac"], "traffic": ncu_file.get("gram_kernel_dram_bytes_per_launch"),
         "kernel": "oak::gram_kernel<4,4,4,NG>", "kernel_ms": kern_ms,
+        "fp64_pipe_active_pct_ncu": ncu_file.get("gram_kernel_fp64_pipe_active_pct"),
+        "fp64_pipe_note": "frac is the ALGORITHMIC roofline (work model 306 slots per entry; the kernel issues ~242 FP64 "
+                          "instructions per entry); the pipe utilisation behind it is ncu's "
+                          "sm__pipe_fp64_cycles_active of the committed capture (profiles/)",
         "peak_source": "measured in this run: oak_measure_fp64_peak (register-resident DFMA chains, burst); "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "work_model": f"{SLOTS_B:.0f} FP64 issue slots (x2 flop) per unique entry (BASELINE.md section 3)",
-        "hbm": {"achieved": out_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": out_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak,
-                "note": "8 B per written entry; the kernel is FP64-pipe bound, not HBM bound"},
+        "hbm": {"achieved": head["out_bytes"] / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": head["out_bytes"] / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                "note": "8 B per written entry (slowest rank); the kernel is FP64-pipe bound, not HBM bound"},
     }
 
-    # ---- e2e: host buffers through oak_gram_host_f64 -----------------------------------------
+    # ---- e2e: the symmetric Gram through HOST buffers (oak_gram_host_lower_f64) ---------------------
     e2e = None
     if not args.no_e2e:
+        ncpu_bound = bind_to_gpu_numa_node(local)
         n_e = args.n_e2e
         if n_e == 0:
-            avail = mem_available_gb()
-            n_e = 32768 if avail > 40 * max(1, 1) else 16384
+            # pinned result buffers on this host: the lower trapezoids of all ranks' strips, ~N^2/2 * 8 B in total
+            # (a full N x N matrix, 34.4 GB at 65536, on a single-GPU run: the reference-shaped output)
+            need_gb = 8.0 * args.n * args.n / 1e9 * (1.0 if world == 1 else 0.6) + 12.0
+            n_e = args.n if mem_available_gb() > need_gb else 32768
         cfg_e = config_B(n_e)
         kern_e = build_kernel(cfg_e)
         kern_e.esp_algorithm = args.algo
         spec_e = kern_e._make_spec()
-        rb, re_ = parallel.partition_rows(n_e, world)[rank]
-        rows = re_ - rb
+        strips_e = [(0, n_e)] if world == 1 else [s for s in parallel.balanced_symmetric_rows(n_e, world)[rank] if s[1] > s[0]]
         Xh = torch.as_tensor(np.ascontiguousarray(cfg_e["X"])).pin_memory()
-        Xrows = Xh[rb:re_].contiguous().pin_memory() if world > 1 else Xh
-        Kh = torch.empty((max(rows, 1), n_e), dtype=torch.float64).pin_memory()
         block = 2048
-        wb = lib.oak_gram_host_work_bytes(spec_e.handle, rows, n_e if world > 1 else 0, 16, block)
+        Kh = [torch.empty((e - b, e), dtype=torch.float64).pin_memory() for b, e in strips_e]
+        for k_ in Kh:
+            k_.zero_()  # first touch on this rank's NUMA node
+        wb = max(lib.oak_gram_host_lower_work_bytes(spec_e.handle, n_e, 16, e, block) for b, e in strips_e)
         work = torch.empty(wb // 8 + 1, dtype=torch.float64, device="cuda")
 
         def e2e_step():
-            rc = lib.oak_gram_host_f64(spec_e.handle, Xrows.data_ptr(), rows,
-                                       Xh.data_ptr() if world > 1 else None, n_e if world > 1 else 0, 16,
-                                       Kh.data_ptr(), n_e, block, work.data_ptr(),
-                                       C.c_void_p(_device.stream_ptr()))
-            assert rc == 0, _cabi.last_error()
+            for (b, e), k_ in zip(strips_e, Kh):
+                rc = lib.oak_gram_host_lower_f64(spec_e.handle, Xh.data_ptr(), n_e, 16, b, e, k_.data_ptr(), e, block, 0,
+                                                 work.data_ptr(), C.c_void_p(_device.stream_ptr()))
+                assert rc == 0, _cabi.last_error()
 
         e2e_steps = max(1, min(args.steps, 3))
         e2e_step()
@@ -395,18 +484,25 @@ def main():
         wall = (time.perf_counter() - t0) / e2e_steps
         ms_e = max_over_ranks(max(a.elapsed_time(b_) / e2e_steps, wall * 1e3))
         barrier()
+        d2h = 0
+        for b, e in strips_e:
+            for r0 in range(b, e, block):
+                r1 = min(r0 + block, e)
+                d2h += (r1 - r0) * r1 * 8
         e2e = {
             "value": n_e * (n_e + 1) / 2 / (ms_e * 1e-3), "unit": "unique entries/s",
-            "h2d_bytes_per_step": int(Xrows.numel() * 8 + (Xh.numel() * 8 if world > 1 else 0)),
-            "d2h_bytes_per_step": int(rows * n_e * 8), "ms_per_step": ms_e,
-            "workload": f"oak_gram_host_f64: K(X,X) N={n_e} D=16 depth=4, pinned host X in, all {n_e}^2 entries "
-                        f"copied back to pinned host memory in {block}-row blocks overlapped with compute"
-                        + (f", rows partitioned over {world} ranks" if world > 1 else ""),
+            "h2d_bytes_per_step": int(Xh.numel() * 8 * len(strips_e)), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": ms_e, "d2h_gb_per_s_this_rank": d2h / (ms_e * 1e-3) / 1e9,
+            "cpus_bound_to_gpu_numa_node": ncpu_bound,
+            "workload": f"oak_gram_host_lower_f64: K(X,X) N={n_e} D=16 depth=4, pinned host X in; the lower trapezoid of "
+                        f"every {block}-row block (all unique entries) copied back to pinned host memory, overlapped "
+                        "with compute; the upper triangle is the mirror image (mirror=1 fills it on the host, not timed)"
+                        + (f"; folded row strips over {world} ranks" if world > 1 else ""),
         }
         del Kh, work, Xh
         spec_e.close()
 
-    # ---- extra: SGPR ELBO evals/s (config C) ---------------------------------------------------
+    # ---- SGPR ELBO evals/s (config C): the second half of BASELINE.json's metric ---------------------
     elbo = None
     if not args.no_elbo:
         cfg_c = config_C(args.elbo_n, 20, args.elbo_m, 3)
@@ -417,16 +513,17 @@ def main():
                      distributed=(world > 1))
         model.likelihood.variance.assign(cfg_c["noise"])
         model._device_data()
-        model.elbo()
+        for _ in range(2):
+            model.elbo()
         barrier()
         a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k_e = max(2, min(args.steps, 5))
+        k_e = max(3, min(args.steps, 5))
         a.record()
         vals = [model.elbo() for _ in range(k_e)]
         b2.record()
         torch.cuda.synchronize()
         ms_elbo = max_over_ranks(a.elapsed_time(b2) / k_e)
-        # stats phase alone (tile generation + DSYRK + DGEMV), no tail, no collective
+        # phases on their own: statistics (tiles + DMMA contraction), the factor-first front, the tail
         sp = kc._make_spec()
         Xs, Ys = model._device_data()
         pz = _device.Points(sp, model._Z_device())
@@ -434,36 +531,36 @@ def main():
         fac = _device.sgpr_factor(sp, pz, 1e-6)
         _device.sgpr_stats2(sp, pz, pxs, Ys, fac)
         torch.cuda.synchronize()
-        a.record()
-        for _ in range(k_e):
-            _device.sgpr_stats2(sp, pz, pxs, Ys, fac)
-        b2.record()
-        torch.cuda.synchronize()
-        ms_stats = max_over_ranks(a.elapsed_time(b2) / k_e)
-        # the factor-first front (Kuu tiles, bordered Cholesky -> L and L^-1, condition estimate, route flag)
-        a.record()
-        for _ in range(k_e):
-            _device.sgpr_factor(sp, pz, 1e-6, buf=fac.buf)
-        b2.record()
-        torch.cuda.synchronize()
-        ms_factor = max_over_ranks(a.elapsed_time(b2) / k_e)
-        # the tail after the all-reduce (whitening, bordered Cholesky of B, bound)
-        st = _device.sgpr_stats2(sp, pz, pxs, Ys, fac)
-        a.record()
-        for _ in range(k_e):
-            _device.sgpr_finish2(fac, st, args.elbo_n, cfg_c["noise"], want_alpha=False)
-        b2.record()
-        torch.cuda.synchronize()
-        ms_finish = max_over_ranks(a.elapsed_time(b2) / k_e)
+
+        def timed_dev(fn):
+            a.record()
+            for _ in range(k_e):
+                r = fn()
+            b2.record()
+            torch.cuda.synchronize()
+            return max_over_ranks(a.elapsed_time(b2) / k_e), r
+
+        ms_stats, st = timed_dev(lambda: _device.sgpr_stats2(sp, pz, pxs, Ys, fac))
+        ms_factor, _ = timed_dev(lambda: _device.sgpr_factor(sp, pz, 1e-6, buf=fac.buf))
+        ms_finish, _ = timed_dev(lambda: _device.sgpr_finish2(fac, st, args.elbo_n, cfg_c["noise"], want_alpha=False))
+        ms_allreduce = None
+        if world > 1:
+            ms_allreduce, _ = timed_dev(lambda: parallel.allreduce_sum_(st))
+        fac_w = _device.sgpr_factor(sp, pz, 1e-6, route=_device.ROUTE_WHITENED)
+        _device.sgpr_stats2(sp, pz, pxs, Ys, fac_w)
+        ms_stats_w, _ = timed_dev(lambda: _device.sgpr_stats2(sp, pz, pxs, Ys, fac_w))
         sp.close()
+        del fac_w
         kuf_entries = float(args.elbo_m) * (e - b)
         elbo = {
             "metric": "SGPR ELBO evals/sec", "value": 1e3 / ms_elbo, "unit": "evals/s", "ms_per_eval": ms_elbo,
             "ms_stats_phase": ms_stats, "ms_tail_and_collective": ms_elbo - ms_stats, "elbo": vals[-1],
-            "ms_factor_front": ms_factor, "ms_finish_tail": ms_finish, "route": model.last_route,
-            "cond_estimate_kuu": model.last_cond_estimate,
+            "ms_factor_front": ms_factor, "ms_finish_tail": ms_finish, "ms_allreduce": ms_allreduce,
+            "route": model.last_route, "cond_estimate_kuu": model.last_cond_estimate,
+            "ms_stats_phase_whitened_route": ms_stats_w,
             "workload": f"config C: N={args.elbo_n}, D=20, M={args.elbo_m}, depth 3; N axis sharded over {world} "
-                        f"rank(s); all-reduce of {args.elbo_m ** 2 + args.elbo_m + 2} doubles",
+                        f"rank(s); all-reduce of {args.elbo_m ** 2 + args.elbo_m + 2} doubles; L = chol(Kuu) first, route "
+                        "chosen on the device (0 = Phi statistics, 1 = gpflow's whitened order)",
             "roofline_stats_phase": {
                 "bound": "fp64", "unit": "TFLOP/s", "peak": peak_tflops,
                 "achieved": kuf_entries * SLOTS_C * 2 / (ms_stats * 1e-3) / 1e12,
@@ -503,8 +600,10 @@ def main():
                 "ms_per_eval": ms_gz, "grad_norm_Z": float(np.abs(model._inducing_grad).max())}
         except Exception as exc:  # the headline must not depend on the widening row
             elbo["training_step"] = {"error": repr(exc)}
+        del model
+        torch.cuda.empty_cache()
 
-    # ---- the other BASELINE.json configurations (A, D, E): one timed evaluation each, N=1 only --------
+    # ---- the other BASELINE.json configurations (A, D, E) and an A-shaped Gram, N=1 only ---------------
     others = None
     if world == 1 and not args.no_elbo:
         try:
@@ -529,6 +628,18 @@ def main():
             others["A_gpr_lml_n1030_d8_depth8"] = {"ms": ms, "lml": lml}
             ms, _ = timed(lambda: compute_sobol_oak(ga, 1.0, 0.0), reps=1)
             others["A_sobol_255_components"] = {"ms": ms}
+            # config A's kernel (D=8, full depth 8) at a size where the tile kernel is the whole cost
+            na = 32768
+            cal = config_A(na)
+            sa = build_kernel(cal)._make_spec()
+            pxa = _device.Points(sa, _device.to_device(cal["X"]))
+            outa = torch.empty((na, na), dtype=torch.float64, device="cuda")
+            ms, _ = timed(lambda: _device.gram(sa, pxa, out=outa))
+            others["A_shaped_gram_n32768_d8_depth8"] = {
+                "ms": ms, "unique_entries_per_s": na * (na + 1) / 2 / (ms * 1e-3),
+                "roofline_frac_244_slots": na * (na + 1) / 2 * 244 / (ms * 1e-3) / peak_slots}
+            sa.close()
+            del outa
             cd = config_D()
             kd_ = build_kernel(cd)
             sd = kd_._make_spec()
@@ -580,34 +691,49 @@ def main():
         except Exception as exc:
             widening = {"error": repr(exc)}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only) ------------------------------------------------
+    # ---- CPU baseline beside it (rank 0, N=1 only): timing AND parity on the same inputs ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, t_eval, threads = cpu_gram_sample(args.n_cpu, 3)
+        v, t_eval, threads, Kc = cpu_gram_sample(args.n_cpu, 3, warm=1, keep=True)
+        cfg_p = config_B(args.n_cpu)
+        Kg = build_kernel(cfg_p).K(_device.to_device(cfg_p["X"])).cpu()
+        gram_err = float(((Kg - Kc).abs() / Kc.abs().clamp_min(1e-12)).max())
+        del Kg, Kc
+        cfg_s, elbo_cpu, t_elbo = cpu_elbo_sample(20000, args.elbo_m)
+        ms_ = SGPR((cfg_s["X"], cfg_s["y"]), kernel=build_kernel(cfg_s), inducing_variable=cfg_s["Z"])
+        ms_.likelihood.variance.assign(cfg_s["noise"])
+        elbo_gpu = ms_.elbo()
         cpu = {"value": v, "unit": "unique entries/s", "cores": threads, "kind": "port",
                "sample": f"K(X,X) N={args.n_cpu}, D=16, depth=4 (reference op sequence, oracle/cpu_baseline.py, "
-                         f"torch-CPU FP64), median of 3: {t_eval:.2f} s per evaluation"}
+                         f"torch-CPU FP64), median of 3: {t_eval:.2f} s per evaluation",
+               "parity_max_elementwise_rel_err_gram": gram_err,
+               "elbo": {"evals_per_s_scaled_to_n1e6": 1.0 / (t_elbo * args.elbo_n / 20000),
+                        "sample": f"config C slice N=20000, M={args.elbo_m}: {t_elbo:.2f} s per evaluation, scaled "
+                                  f"linearly to N={args.elbo_n}",
+                        "parity_rel_err_elbo": abs(elbo_gpu - elbo_cpu) / abs(elbo_cpu)}}
 
     if rank == 0:
         line = {
             "metric": "OAK Gram entries/sec (FP64)", "value": value, "unit": "unique entries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"config B: OAK Gram K(X,X), N={n}, D=16, max_interaction_depth=4, Gaussian measure, "
-                            "FP64; step = prepare + fused Gram kernel, X resident in HBM; "
-                            + ("lower-triangle tiles + mirrored stores, full N x N matrix written"
-                               if world == 1 else f"folded row strips over {world} ranks, lower trapezoids, no collective"),
-                "l2": f"output of {out_bytes / 1e9:.1f} GB per step >> 126 MB L2 (streaming stores); inputs 16 MB",
+                            "FP64; step = prepare + fused Gram kernel, X resident in HBM; the full symmetric N x N matrix "
+                            "is written: " + ("lower-triangle tiles + mirrored stores on one GPU" if world == 1 else
+                                              f"folded row strips over {world} ranks, each rank its lower trapezoids and "
+                                              "their mirror images (same product as N=1), no collective"),
+                "l2": f"output of {head['out_bytes'] / 1e9:.1f} GB per step and rank >> 126 MB L2 (streaming stores); inputs 16 MB",
                 "esp": "newton_girard" if args.algo == 0 else "direct_recurrence",
             },
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu,
-            "extra": {"sgpr_elbo": elbo, "other_configs": others, "widening": widening,
-                      "fp64_peak_slots_per_s": peak_slots},
+            "elbo_evals_per_s": None if elbo is None else elbo["value"],
+            "sgpr_elbo": elbo,
+            "config_B_sweep": sweep,
+            "extra": {"other_configs": others, "widening": widening, "fp64_peak_slots_per_s": peak_slots},
         }
         print(json.dumps(line))
-    spec.close()
     if world > 1:
         dist.destroy_process_group()
 

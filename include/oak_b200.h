@@ -176,6 +176,17 @@ int oak_gram_host_f64(const oak_spec* spec, const double* h_X, int64_t n, const 
                       int64_t n2, int64_t ldx, double* h_K, int64_t ldk, int64_t block_rows,
                       void* d_work, void* stream);
 
+/* Symmetric K(X, X) through host buffers, lower trapezoid only: rows [row_begin, row_end) are produced in
+ * blocks of block_rows and only columns [0, end of the block) of each block are copied back -- half the PCIe
+ * bytes of oak_gram_host_f64 for the whole matrix.  h_K[(i - row_begin)*ldk + j] for j <= i (and the rest of the
+ * 64 x 64 tiles on the diagonal); entries further right are left untouched unless mirror != 0 (full row range
+ * only), which fills the strict upper triangle on the host from the lower one.  h_X: all n points (n x ldx). */
+size_t oak_gram_host_lower_work_bytes(const oak_spec* spec, int64_t n, int64_t ldx, int64_t row_end,
+                                      int64_t block_rows);
+int oak_gram_host_lower_f64(const oak_spec* spec, const double* h_X, int64_t n, int64_t ldx, int64_t row_begin,
+                            int64_t row_end, double* h_K, int64_t ldk, int64_t block_rows, int mirror,
+                            void* d_work, void* stream);
+
 /* ---- SGPR statistics --------------------------------------------------------------- */
 /* Layout of the packed statistics vector (doubles): Phi[M*M] | Kuf_y[M] | sum_kdiag | yty.
  * This is the single buffer all-reduced (sum) across ranks. */

@@ -78,6 +78,8 @@ SIGNATURES = {
     "oak_component_predict_f64": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i64, _vp, _i64, _dp, _dp, _vp]),
     "oak_gram_host_work_bytes": (_sz, [_vp, _i64, _i64, _i64, _i64]),
     "oak_gram_host_f64": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "oak_gram_host_lower_work_bytes": (_sz, [_vp, _i64, _i64, _i64, _i64]),
+    "oak_gram_host_lower_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "oak_gram_backward_work_bytes": (_sz, [_vp, _i64]),
     "oak_backward_grad_count": (_sz, [_vp]),
     "oak_spec_table_layout": (C.c_int, [_vp, _i32, C.POINTER(_i32), C.POINTER(_i32)]),

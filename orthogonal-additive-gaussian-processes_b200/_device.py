@@ -94,13 +94,17 @@ class Points:
 
 
 def validate_discrete(Xd, columns: Sequence[int], counts: Sequence[int]):
-    """``tf.gather`` on CPU raises for out-of-range indices; do the same before the table gather."""
-    for col, cnt in zip(columns, counts):
-        if Xd.shape[0] == 0:
-            continue
-        v = Xd[:, col].trunc()
-        lo, hi = float(v.min()), float(v.max())
-        if lo < 0 or hi > cnt - 1:
+    """``tf.gather`` on CPU raises for out-of-range indices; do the same before the table gather.  One fused
+    min / max over all discrete columns and ONE read-back (models remember that their resident training data
+    passed, see ``GPModel._check_training_discrete``)."""
+    if Xd.shape[0] == 0 or not len(columns):
+        return
+    torch = _torch()
+    v = Xd[:, list(columns)].trunc()
+    lohi = torch.stack((v.amin(0), v.amax(0))).cpu().numpy()
+    for j, (col, cnt) in enumerate(zip(columns, counts)):
+        lo, hi = float(lohi[0, j]), float(lohi[1, j])
+        if not (lo >= 0 and hi <= cnt - 1):  # NaN fails too
             raise ValueError(f"column {col}: category index outside [0, {cnt - 1}] (got [{lo}, {hi}])")
 
 

@@ -101,6 +101,8 @@ struct oak_spec {
   std::vector<double> h_blob;          // host copy (backward pass: closed-form d var_s / dl of MOG measures)
   std::vector<size_t> blob_off0, blob_off1, blob_off2;  // [D] offsets of v0 / v1 / v2 per kernel-order dim
   const double* d_exptab = nullptr;    // 2^(j/256)
+  void* arena = nullptr;               // pooled device + pinned staging block holding every d_* array above
+  void* arena_stream = nullptr;        // stream the spec was created on (orders the reuse of the arena)
 };
 
 namespace oak {

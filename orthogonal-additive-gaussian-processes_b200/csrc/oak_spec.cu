@@ -159,15 +159,67 @@ extern "C" int oak_device_count(void) {
   return n;
 }
 
+// ---- parameter arena pool -----------------------------------------------------------------------------
+// A spec is rebuilt for every objective evaluation (the hyper-parameters are gpflow Parameters read at call
+// time).  Seven cudaMalloc + pageable copies + seven cudaFree per evaluation cost ~0.17 ms, and every cudaFree
+// synchronises the device in the middle of the evaluation.  Instead: one device block + one pinned staging
+// block per spec, recycled through a per-device free list; one asynchronous copy; nothing is freed.
+// Reuse is ordered by events: the copy must have consumed the staging block, and the kernels of the previous
+// owner (on the stream it was created on) must have finished before the new copy lands.
+namespace oak {
+struct SpecArena {
+  char* dev = nullptr;
+  char* host = nullptr;
+  size_t cap = 0;
+  int device = 0;
+  cudaEvent_t copied = nullptr;    // the H2D copy of the last owner has completed
+  cudaEvent_t released = nullptr;  // recorded on the owner's stream when the spec was destroyed
+  bool has_released = false;
+};
+static std::mutex g_arena_mu;
+static std::vector<SpecArena*> g_arena_free;
+
+static SpecArena* arena_acquire(size_t need, int device, cudaStream_t stream) {
+  SpecArena* a = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_arena_mu);
+    for (size_t i = 0; i < g_arena_free.size(); ++i)
+      if (g_arena_free[i]->device == device && g_arena_free[i]->cap >= need) {
+        a = g_arena_free[i];
+        g_arena_free.erase(g_arena_free.begin() + i);
+        break;
+      }
+  }
+  if (!a) {
+    a = new SpecArena();
+    a->device = device;
+    a->cap = (need + 65535) / 65536 * 65536;
+    if (cudaMalloc(&a->dev, a->cap) != cudaSuccess || cudaMallocHost(&a->host, a->cap) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a->copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&a->released, cudaEventDisableTiming) != cudaSuccess) {
+      if (a->dev) cudaFree(a->dev);
+      if (a->host) cudaFreeHost(a->host);
+      delete a;
+      return nullptr;
+    }
+    return a;
+  }
+  cudaEventSynchronize(a->copied);  // staging block free again (normally long done)
+  if (a->has_released) cudaStreamWaitEvent(stream, a->released, 0);
+  return a;
+}
+
+static void arena_release(SpecArena* a, cudaStream_t stream) {
+  if (!a) return;
+  a->has_released = cudaEventRecord(a->released, stream) == cudaSuccess;
+  std::lock_guard<std::mutex> lock(g_arena_mu);
+  g_arena_free.push_back(a);
+}
+}  // namespace oak
+
 extern "C" int oak_spec_destroy(oak_spec* spec) {
   if (!spec) return 0;
-  cudaFree(spec->d_dims);
-  cudaFree(spec->d_inv_sqrt_v);
-  cudaFree(spec->d_neg_log_s2);
-  cudaFree(spec->d_gram_aux);
-  cudaFree(spec->d_tables);
-  cudaFree(spec->d_blob);
-  cudaFree(spec->d_sobolG);
+  arena_release((SpecArena*)spec->arena, (cudaStream_t)spec->arena_stream);
   delete spec;
   return 0;
 }
@@ -323,12 +375,30 @@ extern "C" int oak_spec_create(const oak_kernel_desc* desc, void* stream_, oak_s
   s->blob_off0 = off0;
   s->blob_off1 = off1;
   s->blob_off2 = off2;
-  if (!blob.empty()) {
-    if (cudaMalloc(&s->d_blob, blob.size() * sizeof(double)) != cudaSuccess) return fail("cudaMalloc");
-    if (cudaMemcpyAsync(s->d_blob, blob.data(), blob.size() * sizeof(double),
-                        cudaMemcpyHostToDevice, stream) != cudaSuccess)
-      return fail("cudaMemcpyAsync");
-  }
+  // Gram-tile flavour: the exponent of the RBF dims in units of ln2/256 (0 when s^2 == 1)
+  std::vector<double> gaux(nls);
+  for (int k = 0; k < s->Dc; ++k) gaux[k] = (s->h_dims[k].s2 == 1.0) ? 0.0 : nls[k] * kXScale2;
+  // one arena: blob | dims | inv_sqrt_v | neg_log_s2 | gram_aux | tables | sobolG, each 256-byte aligned
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_blob = 0;
+  const size_t o_dims = o_blob + up(blob.size() * sizeof(double));
+  const size_t o_isv = o_dims + up(D * sizeof(DimDev));
+  const size_t o_nls = o_isv + up(D * sizeof(double));
+  const size_t o_gaux = o_nls + up(D * sizeof(double));
+  const size_t o_tab = o_gaux + up(D * sizeof(double));
+  const size_t o_sob = o_tab + up((size_t)s->tables_len * sizeof(double));
+  const size_t total = o_sob + up(s->h_sobolG.size() * sizeof(double)) + 256;
+  SpecArena* arena = arena_acquire(total, s->device, stream);
+  if (!arena) return fail("arena allocation");
+  s->arena = arena;
+  s->arena_stream = stream;
+  s->d_blob = blob.empty() ? nullptr : (double*)(arena->dev + o_blob);
+  s->d_dims = (DimDev*)(arena->dev + o_dims);
+  s->d_inv_sqrt_v = (double*)(arena->dev + o_isv);
+  s->d_neg_log_s2 = (double*)(arena->dev + o_nls);
+  s->d_gram_aux = (double*)(arena->dev + o_gaux);
+  s->d_tables = s->tables_len > 0 ? (double*)(arena->dev + o_tab) : nullptr;
+  s->d_sobolG = s->h_sobolG.empty() ? nullptr : (double*)(arena->dev + o_sob);
   for (int k = 0; k < D; ++k) {
     DimDev& dd = s->h_dims[k];
     if (dd.type == OAK_DIM_RBF &&
@@ -338,39 +408,17 @@ extern "C" int oak_spec_create(const oak_kernel_desc* desc, void* stream_, oak_s
       dd.v2 = dd.measure == OAK_MEASURE_MOG ? s->d_blob + off2[k] : nullptr;
     }
   }
-  if (cudaMalloc(&s->d_dims, D * sizeof(DimDev)) != cudaSuccess) return fail("cudaMalloc");
-  if (cudaMalloc(&s->d_inv_sqrt_v, D * sizeof(double)) != cudaSuccess) return fail("cudaMalloc");
-  if (cudaMalloc(&s->d_neg_log_s2, D * sizeof(double)) != cudaSuccess) return fail("cudaMalloc");
-  if (cudaMemcpyAsync(s->d_dims, s->h_dims.data(), D * sizeof(DimDev), cudaMemcpyHostToDevice,
-                      stream) != cudaSuccess)
+  if (!blob.empty()) std::memcpy(arena->host + o_blob, blob.data(), blob.size() * sizeof(double));
+  std::memcpy(arena->host + o_dims, s->h_dims.data(), D * sizeof(DimDev));
+  std::memcpy(arena->host + o_isv, isv.data(), D * sizeof(double));
+  std::memcpy(arena->host + o_nls, nls.data(), D * sizeof(double));
+  std::memcpy(arena->host + o_gaux, gaux.data(), D * sizeof(double));
+  if (s->tables_len > 0) std::memcpy(arena->host + o_tab, s->h_tables.data(), (size_t)s->tables_len * sizeof(double));
+  if (!s->h_sobolG.empty())
+    std::memcpy(arena->host + o_sob, s->h_sobolG.data(), s->h_sobolG.size() * sizeof(double));
+  if (cudaMemcpyAsync(arena->dev, arena->host, total - 256, cudaMemcpyHostToDevice, stream) != cudaSuccess)
     return fail("cudaMemcpyAsync");
-  if (cudaMemcpyAsync(s->d_inv_sqrt_v, isv.data(), D * sizeof(double), cudaMemcpyHostToDevice,
-                      stream) != cudaSuccess)
-    return fail("cudaMemcpyAsync");
-  if (cudaMemcpyAsync(s->d_neg_log_s2, nls.data(), D * sizeof(double), cudaMemcpyHostToDevice,
-                      stream) != cudaSuccess)
-    return fail("cudaMemcpyAsync");
-  // Gram-tile flavour: the exponent of the RBF dims in units of ln2/256 (0 when s^2 == 1)
-  std::vector<double> gaux(nls);
-  for (int k = 0; k < s->Dc; ++k) gaux[k] = (s->h_dims[k].s2 == 1.0) ? 0.0 : nls[k] * kXScale2;
-  if (cudaMalloc(&s->d_gram_aux, D * sizeof(double)) != cudaSuccess) return fail("cudaMalloc");
-  if (cudaMemcpyAsync(s->d_gram_aux, gaux.data(), D * sizeof(double), cudaMemcpyHostToDevice,
-                      stream) != cudaSuccess)
-    return fail("cudaMemcpyAsync");
-  if (s->tables_len > 0) {
-    if (cudaMalloc(&s->d_tables, s->tables_len * sizeof(double)) != cudaSuccess)
-      return fail("cudaMalloc");
-    if (cudaMemcpyAsync(s->d_tables, s->h_tables.data(), s->tables_len * sizeof(double),
-                        cudaMemcpyHostToDevice, stream) != cudaSuccess)
-      return fail("cudaMemcpyAsync");
-  }
-  if (!s->h_sobolG.empty()) {
-    if (cudaMalloc(&s->d_sobolG, s->h_sobolG.size() * sizeof(double)) != cudaSuccess)
-      return fail("cudaMalloc");
-    if (cudaMemcpyAsync(s->d_sobolG, s->h_sobolG.data(), s->h_sobolG.size() * sizeof(double),
-                        cudaMemcpyHostToDevice, stream) != cudaSuccess)
-      return fail("cudaMemcpyAsync");
-  }
+  if (cudaEventRecord(arena->copied, stream) != cudaSuccess) return fail("cudaEventRecord");
   s->d_exptab = exp_table_device();
   if (!s->d_exptab) return fail("exp table upload");
 

@@ -44,6 +44,14 @@ class GPModel(Module):
     def _slice_for_kernel(self, Xd):
         return self.kernel.slice(Xd, None)[0].contiguous()
 
+    def _check_training_discrete(self, Xs, dims):
+        """Range check of the discrete columns of the RESIDENT training inputs: once per (data, kernel layout),
+        not on every objective evaluation (it costs a device read-back)."""
+        key = (Xs.data_ptr(), tuple(Xs.shape), tuple((d.column, d.count) for d in dims if d.type != 0))
+        if getattr(self, "_discrete_checked", None) != key:
+            self.kernel._check_discrete(Xs, dims)
+            self._discrete_checked = key
+
     # ---- gpflow-style objective API --------------------------------------------------------
     def log_prior_density(self) -> float:
         total = 0.0
@@ -157,7 +165,13 @@ class SGPR(GPModel):
         self.last_timings = {}
 
     def _Z_device(self):
-        return self._slice_for_kernel(_device.to_device(value_of(self.inducing_variable.Z)))
+        """Inducing points on the device; the upload is skipped while the host values are unchanged (they are
+        fixed by default, model_utils.py:100-101)."""
+        z = np.asarray(value_of(self.inducing_variable.Z), dtype=np.float64)
+        cached = getattr(self, "_z_cache", None)
+        if cached is None or cached[0].shape != z.shape or not np.array_equal(cached[0], z):
+            self._z_cache = (z.copy(), self._slice_for_kernel(_device.to_device(z)))
+        return self._z_cache[1]
 
     def _route(self) -> int:
         return _device.ROUTE_AUTO if self.whiten_stats is None else int(bool(self.whiten_stats))
@@ -170,7 +184,7 @@ class SGPR(GPModel):
         Zs = self._Z_device()
         spec = self.kernel._make_spec()
         try:
-            self.kernel._check_discrete(Xs, spec._keep)
+            self._check_training_discrete(Xs, spec._keep)
             self.kernel._check_discrete(Zs, spec._keep)
             pz, px = _device.Points(spec, Zs), _device.Points(spec, Xs)
             # Kuu(iv, kernel) + jitter I, L = chol, L^-1, route flag -- before the statistics, all on the device

@@ -289,6 +289,46 @@ def test_gram_host_pipeline_matches_device():
     spec.close()
 
 
+def test_gram_host_lower_pipeline_halves_the_copies_and_can_mirror():
+    """oak_gram_host_lower_f64: the symmetric Gram through host buffers, lower trapezoid row blocks only; with
+    mirror=1 the host fills the upper triangle and the result is the full matrix; a row sub-range is a rank's share."""
+    import ctypes as C
+
+    import torch
+
+    from oak_b200 import _cabi, _device
+
+    n = 700
+    cfg = _gauss_cfg(n, 5, 3, seed=12)
+    k, ref = _product(cfg), build_oracle(cfg)
+    X = np.ascontiguousarray(cfg["X"])
+    Kref = ref.K(X)
+    spec = k._make_spec()
+    lib = _cabi.load()
+    wb = lib.oak_gram_host_lower_work_bytes(spec.handle, n, 5, n, 128)
+    work = torch.empty(wb // 8 + 1, dtype=torch.float64, device="cuda")
+    for mirror in (0, 1):
+        out = torch.full((n, n), float("nan"), dtype=torch.float64).pin_memory()
+        rc = lib.oak_gram_host_lower_f64(spec.handle, X.ctypes.data, n, 5, 0, n, out.data_ptr(), n, 128, mirror,
+                                         work.data_ptr(), C.c_void_p(_device.stream_ptr()))
+        assert rc == 0, _cabi.last_error()
+        got = out.numpy()
+        assert max_rel_err(np.tril(got), np.tril(Kref)) < RTOL
+        if mirror:
+            assert max_rel_err(got, Kref) < RTOL and np.array_equal(got, got.T)
+        else:
+            assert np.isnan(got[0, n - 1])       # far right of the first block: never copied
+    b, e = 256, 640                              # a rank's row range
+    out = torch.full((e - b, e), float("nan"), dtype=torch.float64).pin_memory()
+    rc = lib.oak_gram_host_lower_f64(spec.handle, X.ctypes.data, n, 5, b, e, out.data_ptr(), e, 128, 0,
+                                     work.data_ptr(), C.c_void_p(_device.stream_ptr()))
+    assert rc == 0, _cabi.last_error()
+    got = out.numpy()
+    mask = np.tril(np.ones((n, n), dtype=bool))[b:e, :e]
+    assert np.abs(got[mask] - Kref[b:e, :e][mask]).max() / np.abs(Kref).max() < RTOL
+    spec.close()
+
+
 def test_fast_and_general_exp_bodies_agree_per_stage():
     """The clamp-free exp body is taken per 16-dim stage when every dim of the stage qualifies
     (s^2 == 1, bounded |a_i - b_j|).  D = 40: stage 0 has a tiny lengthscale (general body), stage 1

@@ -207,8 +207,11 @@ def test_bench_reference_arm_prints_one_contract_line():
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the arm must use all host cores regardless
+    env1 = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--n-cpu", "512"], capture_output=True, text=True, timeout=300)
+                          "--warmup", "0", "--n-cpu", "512", "--elbo-m", "64"], capture_output=True, text=True,
+                         timeout=600, env=env1)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -217,6 +220,8 @@ def test_bench_reference_arm_prints_one_contract_line():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["elbo_evals_per_s_scaled_to_n1e6"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     # ranks other than 0 stay silent under torchrun
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
