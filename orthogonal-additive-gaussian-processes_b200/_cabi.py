@@ -55,6 +55,12 @@ class KernelDesc(C.Structure):
     ]
 
 
+# the same layout for bulk packing
+_DIM_DTYPE = np.dtype([("type", "<i4"), ("column", "<i4"), ("measure", "<i4"), ("count", "<i4"), ("rank", "<i4"),
+                       ("reserved", "<i4"), ("lengthscale", "<f8"), ("variance", "<f8"), ("m0", "<f8"), ("m1", "<f8"),
+                       ("v0", "<u8"), ("v1", "<u8"), ("v2", "<u8")], align=True)
+assert _DIM_DTYPE.itemsize == C.sizeof(DimDesc)
+
 _i64, _i32, _vp, _dp, _sz = C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/oak_b200.h one to one
@@ -208,12 +214,13 @@ class Spec:
             raise OakNativeError(f"max_interaction_depth {depth} > OAK_MAX_DEPTH {OAK_MAX_DEPTH}")
         self._keep = list(dims)
         self.num_dims, self.depth = len(dims), int(depth)
-        arr = (DimDesc * len(dims))()
-        for i, d in enumerate(dims):
-            arr[i].type, arr[i].column, arr[i].measure = d.type, d.column, d.measure
-            arr[i].count, arr[i].rank = d.count, d.rank
-            arr[i].lengthscale, arr[i].variance, arr[i].m0, arr[i].m1 = d.lengthscale, d.variance, d.m0, d.m1
-            arr[i].v0, arr[i].v1, arr[i].v2 = _dptr(d.v0), _dptr(d.v1), _dptr(d.v2)
+        # oak_dim_desc records packed through one structured NumPy array (per-field ctypes stores cost ~6 us a dim)
+        recs = np.zeros(len(dims), dtype=_DIM_DTYPE)
+        ptr = lambda a: 0 if a is None else a.ctypes.data
+        recs[:] = [(d.type, d.column, d.measure, d.count, d.rank, 0, d.lengthscale, d.variance, d.m0, d.m1,
+                    ptr(d.v0), ptr(d.v1), ptr(d.v2)) for d in dims]
+        self._recs = recs
+        arr = recs.ctypes.data_as(C.POINTER(DimDesc))
         var = np.ascontiguousarray(np.asarray(variances, dtype=np.float64).reshape(-1))
         need = depth + 1 if share_var else 1
         if var.shape[0] < need:

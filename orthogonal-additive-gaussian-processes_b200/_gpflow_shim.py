@@ -74,14 +74,29 @@ class Parameter:
         self.trainable = trainable
         self.prior = prior
         self.name = name
-        self._u = np.asarray(self.transform.inverse(np.asarray(value, dtype=np.float64)), dtype=np.float64)
+        self._set_u(self.transform.inverse(np.asarray(value, dtype=np.float64)))
+
+    def _set_u(self, u):
+        self._u = np.asarray(u, dtype=np.float64)
+        self._v = None       # constrained value, computed on demand (a spec is packed on every evaluation)
+        self._scalar = None
 
     # gpflow API subset
     def numpy(self):
-        return np.asarray(self.transform.forward(self._u), dtype=np.float64)
+        if self._v is None:
+            self._v = np.array(self.transform.forward(self._u), dtype=np.float64)
+        return self._v.copy()
+
+    def scalar(self) -> float:
+        """float(squeeze(value)), cached until the next assignment."""
+        if self._scalar is None:
+            if self._v is None:
+                self._v = np.array(self.transform.forward(self._u), dtype=np.float64)
+            self._scalar = float(np.squeeze(self._v))
+        return self._scalar
 
     def assign(self, value):
-        self._u = np.asarray(self.transform.inverse(np.asarray(value, dtype=np.float64)), dtype=np.float64)
+        self._set_u(self.transform.inverse(np.asarray(value, dtype=np.float64)))
         return self
 
     @property
@@ -90,7 +105,7 @@ class Parameter:
 
     @unconstrained_variable.setter
     def unconstrained_variable(self, u):
-        self._u = np.asarray(u, dtype=np.float64)
+        self._set_u(u)
 
     @property
     def shape(self):
@@ -146,6 +161,8 @@ def value_of(p) -> np.ndarray:
 
 
 def scalar_of(p) -> float:
+    if isinstance(p, Parameter):
+        return p.scalar()
     return float(np.squeeze(value_of(p)))
 
 
