@@ -115,7 +115,9 @@ int tile_rows_for_depth(int depth);
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt = nullptr,
-                int64_t ldkt = 0);
+                int64_t ldkt = 0, const double* ydot_y = nullptr, double* ydot_part = nullptr);
+// the folded K y of the general-mode tiles (depth <= 4): ydot_part holds ceil(cols / 64) x rows partial sums
+inline bool gram_can_fold_ky(const oak_spec* spec) { return spec->depth <= 4; }
 // per-dimension min / max keys of the prepared coordinate: [D] min keys then [D] max keys
 inline const unsigned long long* points_minmax(const oak_spec* spec, const double2* pts, int64_t n_pad) {
   return reinterpret_cast<const unsigned long long*>(pts + (int64_t)spec->D * n_pad);
@@ -124,6 +126,11 @@ inline const unsigned long long* points_minmax(const oak_spec* spec, const doubl
 size_t syrk_dmma_work_bytes(int m);
 int syrk_lower_dmma(int m, int64_t k, double* A, int64_t lda, double* C, double* work, size_t work_bytes,
                     int device, cudaStream_t stream, double* A_alt = nullptr, const int* d_route = nullptr);
+// second-generation contraction (oak_syrk2.cu): 128 x 128 tiles, weighted stream-K, A y folded in
+size_t syrk2_work_bytes(int m, int device);
+int syrk2_lower_dmma(int m, int64_t k, double* A, int64_t lda, double* C, const double* y, double* kufy, double* work,
+                     size_t work_bytes, int device, cudaStream_t stream, double* A_alt = nullptr,
+                     const int* d_route = nullptr);
 // C = T B (+ u v^T) on the FP64 tensor cores (oak_pgemm.cu); d_gate: optional device flag, 0 = no-op
 int panel_gemm_dmma(const double* T, int64_t ldt, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int Kd,
                     int64_t n, int lower, const double* u, const double* v, const int* d_gate, int* d_counter,

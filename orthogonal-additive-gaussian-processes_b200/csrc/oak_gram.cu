@@ -50,6 +50,8 @@ struct GramParams {
                         // 3 lower trapezoid of a row strip + its mirror image into a second buffer (Kt)
   double* Kt;           // mode 3: (n2 x rows) block, Kt[j * ldkt + (i - row_begin)] = K(i, j) of the off-diagonal tiles
   int64_t ldkt;
+  const double* ydot_y;  // YDOT kernels (SGPR Kuf tiles): y of the columns of this call, y[j - col_begin]
+  double* ydot_part;     // [column tile][rows] partial sums  sum_{j in tile} K(i, j) y_j  (general mode only)
   int64_t tile_row0;    // global TN-row-block index of row_begin (modes 1, 2)
   const unsigned long long* mm_row;  // [2 D] min / max keys of the prepared coordinates, or null
   const unsigned long long* mm_col;
@@ -159,7 +161,7 @@ __device__ __forceinline__ double finish(const double (&a)[P], const double* __r
   return r;
 }
 
-template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB>
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT = false>
 __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_constant__ GramParams prm) {
   using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int TM = L::TM, TN = L::TN;
@@ -442,6 +444,25 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
       pend_stage = stage;
       mirror_buf ^= 1;
     }
+    if constexpr (YDOT) {
+      // Kuf y folded into the tile epilogue (north_star: warp-shuffle reduction): every thread dots its RM x RN
+      // entries with the y values of its columns, the TXD threads of a row group are folded by shuffles, and
+      // lane tx == 0 writes the tile's row sums -- one slot per (column tile, row), summed in a fixed order later.
+      static_assert(TXD == 16, "row groups are half warps");
+      double yv[RN];
+#pragma unroll
+      for (int c = 0; c < RN; ++c) yv[c] = (tcol + TXD * c < prm.n2) ? __ldg(prm.ydot_y + tcol + TXD * c) : 0.0;
+      double* const part = prm.ydot_part + (col0 / TN) * nrows;
+#pragma unroll
+      for (int r = 0; r < RM; ++r) {
+        double v = acc[r][0][0] * yv[0];
+#pragma unroll
+        for (int c = 1; c < RN; ++c) v = fma(acc[r][c][0], yv[c], v);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (tx == 0 && trow + r < nrows) part[trow + r] = v;
+      }
+    }
     double* const kp = prm.K + trow * ldk + tcol;
     const bool interior = row0 + TM <= nrows && col0 + TN <= prm.n2;
     // the tile itself: straight from registers (a warp store covers two 128-byte row segments)
@@ -521,7 +542,7 @@ static int encode_output_map(CUtensorMap* tm, double* K, int64_t cols, int64_t r
   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
-template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB>
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT = false>
 static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream) {
   using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int kThreads = TXD * TYD;
@@ -550,7 +571,7 @@ static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream)
       prm.use_tma = 1;
   }
   const size_t smem = L::bytes(prm.use_tma != 0);
-  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO, MINB>;
+  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO, MINB, YDOT>;
   static int cached_per_sm[64][2] = {{0}};  // per instantiation, device and shared-memory footprint
   const int fp = prm.use_tma ? 1 : 0;
   int per_sm = (device >= 0 && device < 64) ? cached_per_sm[device][fp] : 0;
@@ -584,6 +605,11 @@ static int launch_algo(const GramParams& prm, int algo, int sms, cudaStream_t st
 //   4: 256 threads (32x8), 4x2 micro-tile, 32x64 tile, 2 CTAs / SM
 template <int P>
 static int launch_small_depth(const GramParams& prm, int algo, int sms, cudaStream_t stream) {
+  if (prm.ydot_y != nullptr) {  // the SGPR Kuf tiles with the folded Kuf y (general mode)
+    if (algo == OAK_ESP_DIRECT)
+      return launch_gram<P, 16, 16, 4, 4, OAK_ESP_DIRECT, 1, true>(prm, sms, prm.device, stream);
+    return launch_gram<P, 16, 16, 4, 4, OAK_ESP_NEWTON_GIRARD, 1, true>(prm, sms, prm.device, stream);
+  }
 #ifdef OAK_GRAM_EXPERIMENTS  // the losing geometries of profiles/r01_ab_gram_variants_*.txt; not built by default
   static const int variant = env_int("OAK_GRAM_VARIANT", 0);
   if (variant == 1) return launch_algo<P, 32, 16, 4, 2, 1>(prm, algo, sms, stream);
@@ -745,10 +771,19 @@ static int launch_matvec(GramParams prm, int algo, int sms, const double* alpha,
 
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
-                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt, int64_t ldkt) {
+                int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt, int64_t ldkt,
+                const double* ydot_y, double* ydot_part) {
   GramParams prm;
   prm.Kt = Kt;
   prm.ldkt = ldkt;
+  prm.ydot_y = nullptr;
+  prm.ydot_part = nullptr;
+  if (ydot_y != nullptr) {
+    OAK_REQUIRE(mode == 0 && spec->depth <= 4 && ydot_part != nullptr,
+                "gram: the folded K y needs the general mode and max_interaction_depth <= 4");
+    prm.ydot_y = ydot_y;
+    prm.ydot_part = ydot_part;
+  }
   for (int p = 0; p <= OAK_MAX_DEPTH; ++p) prm.sigma2[p] = spec->sigma2[p];
   prm.pts_row = prow;
   prm.pts_col = pcol;
@@ -853,6 +888,8 @@ extern "C" int oak_gram_matvec_f64(const oak_spec* spec, const void* d_points, i
   prm.symmetric = 0;
   prm.Kt = nullptr;
   prm.ldkt = 0;
+  prm.ydot_y = nullptr;
+  prm.ydot_part = nullptr;
   prm.tile_row0 = 0;
   prm.num_tiles = 0;
   prm.mm_row = prm.mm_col = nullptr;

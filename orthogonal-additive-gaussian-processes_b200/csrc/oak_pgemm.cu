@@ -19,7 +19,10 @@
 namespace oak {
 
 namespace pgemm {
-constexpr int BM = 128, BN = 128, KT = 16, kStages = 3, kThreads = 256;
+#ifndef OAK_PGEMM_STAGES
+#define OAK_PGEMM_STAGES 3
+#endif
+constexpr int BM = 128, BN = 128, KT = 16, kStages = OAK_PGEMM_STAGES, kThreads = 256;
 constexpr int SA = 24;            // doubles per staged T row (16 + 8: conflict-free LDS.128)
 constexpr int SB = BN + 2;        // doubles per staged B row (conflict-free LDS.64)
 constexpr int kADoubles = BM * SA, kBDoubles = KT * SB;

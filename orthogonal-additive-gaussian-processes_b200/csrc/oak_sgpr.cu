@@ -584,11 +584,15 @@ __global__ void __launch_bounds__(256) route_kernel(double* hdr, const double* c
 
 // B (lower, column-major ld = ldb) = src / noise + I, border row = v / noise, dvec = diag(src) / noise
 __global__ void __launch_bounds__(256) assemble_B_kernel(const double* __restrict__ psi, const double* __restrict__ s2,
-                                                         const int* __restrict__ route, const double* __restrict__ v,
-                                                         int m, int border_row, int64_t ldb, double inv_noise,
-                                                         double* __restrict__ LB, double* __restrict__ dvec) {
+                                                         const int* __restrict__ route, const double* __restrict__ v_white,
+                                                         const double* __restrict__ v_raw, int m, int border_row,
+                                                         int64_t ldb, double inv_noise, double* __restrict__ LB,
+                                                         double* __restrict__ dvec) {
   const int j = blockIdx.x;
-  const double* src = (*route != 0 ? psi : s2) + (int64_t)j * m;
+  const bool whitened = *route != 0;
+  const double* src = (whitened ? psi : s2) + (int64_t)j * m;
+  const double* v = v_white;  // Kuf y is accumulated un-whitened on both routes; v_white = L^-1 Kuf y
+  (void)v_raw;
   double* col = LB + (int64_t)j * ldb;
   for (int i = j + threadIdx.x; i < m; i += 256) {
     const double val = src[i] * inv_noise;
@@ -692,13 +696,43 @@ extern "C" int oak_sgpr_factor_f64(const oak_spec* spec, const void* d_pointsZ, 
   return 0;
 }
 
+constexpr int kKySegments = 64;
+
+// Kuf y from the per-tile row sums the Gram tiles leave (oak_gram.cu, YDOT): two fixed-order levels
+__global__ void __launch_bounds__(256) ky_reduce_kernel(const double* __restrict__ part, int tiles, int m,
+                                                        double* __restrict__ part2) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  const int per = (tiles + kKySegments - 1) / kKySegments;
+  const int t0 = blockIdx.y * per, t1 = min(tiles, t0 + per);
+  double acc = 0.0;
+  for (int t = t0; t < t1; ++t) acc += part[(int64_t)t * m + i];
+  part2[(int64_t)blockIdx.y * m + i] = acc;
+}
+__global__ void __launch_bounds__(256) ky_final_kernel(const double* __restrict__ part2, int m, double* __restrict__ kufy) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  double acc = 0.0;
+  for (int s = 0; s < kKySegments; ++s) acc += part2[(int64_t)s * m + i];
+  kufy[i] += acc;
+}
+
+static size_t stats2_piece_bytes(int64_t m) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  const size_t a = syrk2_work_bytes((int)m, dev), b = syrk_dmma_work_bytes((int)m);
+  return a > b ? a : b;
+}
+
 extern "C" size_t oak_sgpr_stats2_work_bytes(int64_t m, int64_t chunk) {
   if (m < 0 || chunk < 0) return 0;
-  return (size_t)(2 * m * chunk + chunk) * sizeof(double) + syrk_dmma_work_bytes((int)m);
+  const int64_t me = (m + 1) / 2 * 2;
+  return (size_t)(2 * m * chunk + chunk + (chunk / 64 + kKySegments) * me) * sizeof(double) + stats2_piece_bytes(m);
 }
 
 // Phi (route 0) or Psi = sum (L^-1 Kuf)(L^-1 Kuf)^T (route 1) | Kuf y | sum K_diag | y^T y for the local points,
-// accumulated into d_stats; the route is read on the device from the header of d_fac.
+// accumulated into d_stats; the route is read on the device from the header of d_fac.  Kuf y comes out of the
+// Gram-tile epilogue (warp-shuffle row sums per tile, summed in a fixed order) when the depth allows it.
 // d_kuf_store (nullable): keeps every chunk's Kuf block as in oak_sgpr_stats_keep_f64.
 extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
                                    const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
@@ -721,28 +755,55 @@ extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, 
   double* kuf_scratch = (double*)d_work;
   double* abuf = kuf_scratch + m * chunk;
   double* kdiag = abuf + m * chunk;
-  double* partials = kdiag + chunk;
-  const size_t partial_bytes = syrk_dmma_work_bytes((int)m);
+  const int64_t me = (m + 1) / 2 * 2;                   // keeps the partial tiles behind 16-byte aligned
+  double* ypart = kdiag + chunk;                       // [chunk / 64][m] per-tile row sums of Kuf y
+  double* ypart2 = ypart + (chunk / 64) * me;          // [kKySegments][m]
+  double* partials = ypart2 + kKySegments * me;
+  const size_t partial_bytes = stats2_piece_bytes(m);
+  const bool fold_ky = gram_can_fold_ky(spec) && !(getenv("OAK_NO_FOLD_KY") && atoi(getenv("OAK_NO_FOLD_KY")));
   double* phi = d_stats;
   double* kufy = d_stats + m * m;
   double* tail = kufy + m;
   const double2* pz = (const double2*)d_pointsZ;
   const double2* px = (const double2*)d_pointsX;
   const int64_t m_pad = padded(m), n_pad = padded(n_local);
-  const double one = 1.0;
   for (int64_t c0 = 0; c0 < n_local; c0 += chunk) {
     const int64_t nc = (n_local - c0 < chunk) ? (n_local - c0) : chunk;
     double* kuf = d_kuf_store ? d_kuf_store + (c0 / chunk) * m * chunk : kuf_scratch;
-    if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream)) return rc;
+    // Kuf chunk = K(Z, X[c0:c0+nc]) (gpflow Kuf, oak/utils.py:184); with depth <= 4 the tile epilogue also leaves
+    // the per-tile row sums of Kuf y (no second pass over the 2 GB block)
+    const bool fold = fold_ky;
+    if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream, nullptr, 0,
+                             fold ? d_y + c0 : nullptr, fold ? ypart : nullptr))
+      return rc;
     // route 1: A_r = L^-1 Kuf_r (utils.py:189), a no-op launch otherwise
     if (int rc = panel_gemm_dmma(d_fac + mp, ld, kuf, chunk, abuf, chunk, (int)m, (int)m, nc, 1, nullptr, nullptr,
                                  d_route, d_counter, spec->device, stream))
       return rc;
-    if (int rc = syrk_lower_dmma((int)m, nc, kuf, chunk, phi, partials, partial_bytes, spec->device, stream, abuf,
-                                 d_route))
+    // Phi += Kuf Kuf^T (route 0) / Psi += A A^T (route 1).  OAK_SYRK_GEN=2 selects the 128 x 128 variant
+    // (oak_syrk2.cu), measured slower on B200 (DMMA pipe 78 % against 88 %: one 8-warp CTA per SM idles the pipe
+    // at every stage barrier; profiles/r02i_*), kept for A/B runs.
+    static const int syrk_gen = getenv("OAK_SYRK_GEN") ? atoi(getenv("OAK_SYRK_GEN")) : 1;
+    if (syrk_gen == 2) {
+      if (int rc = syrk2_lower_dmma((int)m, nc, kuf, chunk, phi, nullptr, nullptr, partials, partial_bytes,
+                                    spec->device, stream, abuf, d_route))
+        return rc;
+    } else if (int rc = syrk_lower_dmma((int)m, nc, kuf, chunk, phi, partials, partial_bytes, spec->device, stream,
+                                        abuf, d_route)) {
       return rc;
-    OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, (int)nc, (int)m, &one, kuf, (int)chunk, d_y + c0, 1, &one, kufy, 1));
-    g_launches.fetch_add(1);
+    }
+    // Kuf_y += Kuf y: always of the UN-whitened block (the tail applies L^-1 once)
+    if (fold) {
+      const int tiles_c = (int)((nc + 63) / 64);
+      ky_reduce_kernel<<<dim3((unsigned)((m + 255) / 256), kKySegments), 256, 0, stream>>>(ypart, tiles_c, (int)m, ypart2);
+      OAK_LAUNCHED();
+      ky_final_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(ypart2, (int)m, kufy);
+      OAK_LAUNCHED();
+    } else {
+      const double one = 1.0;
+      OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, (int)nc, (int)m, &one, kuf, (int)chunk, d_y + c0, 1, &one, kufy, 1));
+      g_launches.fetch_add(1);
+    }
     if (int rc = gram_diag_launch(spec, px + c0, nc, n_pad, kdiag, stream)) return rc;
     reduce_accumulate_kernel<<<1, 1024, 0, stream>>>(kdiag, nullptr, nc, tail + 0);
     OAK_LAUNCHED();
@@ -801,7 +862,7 @@ extern "C" int oak_sgpr_finish2_f64(double* d_fac, double* d_stats, int64_t m, i
   OAK_CUBLAS(cublasDgemv(cb, CUBLAS_OP_T, M, M, &one, U, (int)ld, kufy, 1, &zero, vtmp, 1));
   g_launches.fetch_add(3);
   // B = AAT + I (utils.py:190-191) with the border row Aerr / sigma; LB = chol(B) leaves c in the border
-  assemble_B_kernel<<<(unsigned)m, 256, 0, stream>>>(phi, S2, hi, vtmp, M, (int)mp, ldb, 1.0 / noise, d_LB, dvec);
+  assemble_B_kernel<<<(unsigned)m, 256, 0, stream>>>(phi, S2, hi, vtmp, kufy, M, (int)mp, ldb, 1.0 / noise, d_LB, dvec);
   OAK_LAUNCHED();
   if (int rc = chol_bordered(d_LB, ldb, M, M + 1, (int)(mp - m), 0, hi + 3, scal, dev, stream)) return rc;
   sgpr_bound2_kernel<<<1, 256, 0, stream>>>(dvec, d_LB, ldb, (int)mp, M, scal, tail, (double)n_total, noise, hdr,
