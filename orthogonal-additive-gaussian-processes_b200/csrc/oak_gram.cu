@@ -40,6 +40,7 @@ struct GramParams {
   const double2* pts_col;
   const double* dim_aux;  // [D] RBF: -ln s^2 ; discrete: bits(table offset)
   const double* tables;
+  int tables_len;       // doubles in the discrete-table blob (staged in shared memory when <= kTableStage)
   const double* exptab;
   double* K;
   int64_t n_row_pad, n_col_pad, ldk;
@@ -61,6 +62,7 @@ struct GramParams {
 };
 
 constexpr int kFastWords = 8;  // clamp-free exp flags for the first 256 continuous dims
+constexpr int kTableStage = 2048;  // doubles of shared memory for the discrete B tables (16 KB)
 
 template <int TXD, int TYD, int RM, int RN>
 struct SmemLayout {
@@ -72,7 +74,8 @@ struct SmemLayout {
   // 1024-byte aligned.
   static constexpr int kOutBytes = TM * TN * (int)sizeof(double);
   static constexpr size_t base_bytes = sizeof(double) * kTabDoubles + 2 * sizeof(double2) * kStageDouble2 +
-                                       2 * sizeof(double) * kDimChunk + sizeof(unsigned) * kFastWords;
+                                       2 * sizeof(double) * kDimChunk + sizeof(unsigned) * kFastWords +
+                                       sizeof(double) * kTableStage;
   static constexpr size_t bytes(bool tma) { return base_bytes + (tma ? 1024 + 2 * (size_t)kOutBytes : 0); }
 };
 
@@ -174,6 +177,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
   double2* sStage = reinterpret_cast<double2*>(sTab + L::kTabDoubles);
   double* sAux = reinterpret_cast<double*>(sStage + 2 * L::kStageDouble2);
   unsigned* sFast = reinterpret_cast<unsigned*>(sAux + 2 * kDimChunk);
+  double* sTables = reinterpret_cast<double*>(sFast + kFastWords);
   // output staging (TMA path only), 1024-byte aligned shared-window addresses
   const unsigned out_mir = ((unsigned)__cvta_generic_to_shared(smem_raw + L::base_bytes) + 1023u) & ~1023u;
   int mirror_buf = 0;
@@ -193,6 +197,12 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
   }
   const unsigned char* tab_bytes = smem_raw;
   const unsigned lane_bits = (unsigned)(tx & (kExpRepl - 1)) * 8u;
+  // discrete B tables: a few dozen doubles gathered 16 times per thread, dimension and tile -- from shared memory
+  // when the blob fits (global / L1 gathers held the mixed-input configuration at 0.76 of its roofline)
+  const bool tables_in_smem = prm.tables_len > 0 && prm.tables_len <= kTableStage;
+  if (tables_in_smem)
+    for (int i = tid; i < prm.tables_len; i += kThreads) sTables[i] = prm.tables[i];
+  const double* const table_base = tables_in_smem ? sTables : prm.tables;
 
   const int D = prm.D, Dc = prm.Dc;
   const int num_chunks = (D + kDimChunk - 1) / kDimChunk;
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
       for (int dl = nc; dl < nd; ++dl) {  // discrete dims: table gather
         const double2* rowp = sRow + dl * (TM + TN);
         const double2* colp = rowp + TM;
-        const double* tbl = prm.tables + (int)__double_as_longlong(aux[dl]);
+        const double* tbl = table_base + (int)__double_as_longlong(aux[dl]);
         int ro[RM], co[RN];
 #pragma unroll
         for (int r = 0; r < RM; ++r) ro[r] = __double2hiint(rowp[ty * RM + r].x);
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
 #pragma unroll
         for (int r = 0; r < RM; ++r)
 #pragma unroll
-          for (int c = 0; c < RN; ++c) accumulate<P, ALGO>(acc[r][c], __ldg(tbl + ro[r] + co[c]));
+          for (int c = 0; c < RN; ++c) accumulate<P, ALGO>(acc[r][c], tbl[ro[r] + co[c]]);
       }
       buf ^= 1;
     }
@@ -791,6 +801,7 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
   prm.n_col_pad = n_col_pad;
   prm.dim_aux = spec->d_gram_aux;
   prm.tables = spec->d_tables;
+  prm.tables_len = spec->tables_len;
   prm.exptab = spec->d_exptab;
   prm.K = K;
   prm.ldk = ldk;
@@ -875,6 +886,7 @@ extern "C" int oak_gram_matvec_f64(const oak_spec* spec, const void* d_points, i
   prm.n_col_pad = padded(n2);
   prm.dim_aux = spec->d_gram_aux;
   prm.tables = spec->d_tables;
+  prm.tables_len = spec->tables_len;
   prm.exptab = spec->d_exptab;
   prm.K = nullptr;
   prm.ldk = 0;

@@ -6,8 +6,9 @@
 //     A = L^-1 Kuf / sigma before A A^T (oak/utils.py:186-190);
 //   * the cotangent of the training step: W = 2 G_Phi Kuf + g_b y^T (training.py), formerly a cuBLAS
 //     DGEMM (cutlass_80 d884gemm) plus a rank-1 update.
-// CTA tile 128 x 128 (8 warps as 4 x 2, warp tile 32 x 64: 64 accumulators per lane), 16-wide k stages in a
-// 3-stage cp.async pipeline.  The A fragment ("8 rows x 4 k") is read as 16-byte pairs of consecutive k, the
+// CTA tile 64 x 128 (4 warps as 2 x 2, warp tile 32 x 64: 64 accumulators per lane; two CTAs per SM so that one
+// CTA's stage barrier is covered by the other -- the 128 x 128 / one-CTA-per-SM build, OAK_PGEMM_BM=128, idles the
+// FP64 tensor pipe at every barrier), 16-wide k stages in a 3-stage cp.async pipeline.  The A fragment ("8 rows x 4 k") is read as 16-byte pairs of consecutive k, the
 // B fragment ("4 k x 8 columns") as 8-byte words from the k-major staged panel; the k values of a stage are
 // dealt to the four k-lanes as kappa(q, s) = 8 (s >> 1) + 2 q + (s & 1) for both operands, which makes both
 // access patterns bank-conflict free (row strides 24 and 130 doubles).  Tiles are handed out by an atomic
@@ -22,7 +23,12 @@ namespace pgemm {
 #ifndef OAK_PGEMM_STAGES
 #define OAK_PGEMM_STAGES 3
 #endif
-constexpr int BM = 128, BN = 128, KT = 16, kStages = OAK_PGEMM_STAGES, kThreads = 256;
+#ifndef OAK_PGEMM_BM
+#define OAK_PGEMM_BM 64  // 64: 4 warps (2 x 2), two CTAs per SM; 128: 8 warps (4 x 2), one CTA per SM
+#endif
+constexpr int BM = OAK_PGEMM_BM, BN = 128, KT = 16, kStages = OAK_PGEMM_STAGES, kThreads = 2 * BM;
+constexpr int kMinBlocks = BM == 64 ? 2 : 1;
+static_assert(BM == 64 || BM == 128, "OAK_PGEMM_BM must be 64 or 128");
 constexpr int SA = 24;            // doubles per staged T row (16 + 8: conflict-free LDS.128)
 constexpr int SB = BN + 2;        // doubles per staged B row (conflict-free LDS.64)
 constexpr int kADoubles = BM * SA, kBDoubles = KT * SB;
@@ -56,7 +62,7 @@ __device__ __forceinline__ void pg_dmma(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(pgemm::kThreads, 1) panel_gemm_dmma_kernel(const PGemmParams prm) {
+__global__ void __launch_bounds__(pgemm::kThreads, pgemm::kMinBlocks) panel_gemm_dmma_kernel(const PGemmParams prm) {
   using namespace pgemm;
   if (prm.gate != nullptr && *prm.gate == 0) return;
   extern __shared__ __align__(16) double smem[];
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(pgemm::kThreads, 1) panel_gemm_dmma_kernel(con
       double* dB = dA + kADoubles;
       const int kbase = step * KT;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < (BM * (KT / 2)) / kThreads; ++i) {
         const int idx = tid + i * kThreads;
         const int row = idx >> 3, ch = idx & 7;
         const bool ok = (m0 + row < prm.M) && (kbase + 2 * ch < prm.Kd);
@@ -93,7 +99,7 @@ __global__ void __launch_bounds__(pgemm::kThreads, 1) panel_gemm_dmma_kernel(con
         pg_cp16(dA + row * SA + 2 * ch, src, ok);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < (KT * (BN / 2)) / kThreads; ++i) {
         const int idx = tid + i * kThreads;
         const int kr = idx >> 6, ch = idx & 63;
         const bool ok = (kbase + kr < prm.Kd) && (n0 + 2 * ch < prm.n_read);
@@ -208,7 +214,8 @@ int panel_gemm_dmma(const double* T, int64_t ldt, const double* B, int64_t ldb, 
   prm.gate = d_gate;
   prm.counter = d_counter;
   OAK_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
-  const int64_t grid = prm.units < sms ? prm.units : sms;
+  const int64_t resident = (int64_t)sms * kMinBlocks;
+  const int64_t grid = prm.units < resident ? prm.units : resident;
   panel_gemm_dmma_kernel<<<(unsigned)grid, kThreads, kSmemBytes, stream>>>(prm);
   OAK_LAUNCHED();
   return 0;

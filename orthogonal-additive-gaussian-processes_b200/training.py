@@ -224,9 +224,20 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         z_train = zpar is not None and zpar.trainable
         gZ = torch.zeros((m, spec.num_dims), dtype=torch.float64, device=Kuu.device) if z_train else None
 
+        yvec = Yd.reshape(-1)
+        gb_vec = g_b.reshape(-1).contiguous()
+        if m % 2:  # the DMMA panel product wants an even pitch of its left factor
+            G2p = torch.zeros((m, m + 1), dtype=torch.float64, device=Kuu.device)
+            G2p[:, :m] = G2
+            G2 = G2p[:, :m]
+
         def rows_chunk(Kc, c0, c1):
-            # W = 2 G_phi Kuf + g_b y^T for one chunk (M x nc), rows = inducing points
-            Wc = torch.addmm(g_b @ Yd[c0:c1].reshape(1, -1), G2, Kc)
+            # W = 2 G_phi Kuf + g_b y^T for one chunk (M x nc), rows = inducing points: one pass of the in-house
+            # DMMA panel product (csrc/oak_pgemm.cu) with the rank-1 term in its epilogue
+            if Kc.stride(0) % 2 == 0 and Kc.data_ptr() % 16 == 0 and (c0 % 2 == 0):
+                Wc = _device.panel_gemm(G2, Kc, u=gb_vec, v=yvec[c0:c1])
+            else:
+                Wc = torch.addmm(g_b @ Yd[c0:c1].reshape(1, -1), G2, Kc)
             pxc = _device.Points(spec, Xs[c0:c1])
             if z_train:
                 _device.gram_backward_rows(spec, pz, Wc, px2=pxc, grad=grad, grad_rows=gZ)

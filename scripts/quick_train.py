@@ -8,7 +8,7 @@ from oak_b200.training import freeze_unsupported, sgpr_elbo_and_grad
 from oak_b200.workloads import build_kernel, config_C
 n = int(os.environ.get("AB_N", 1_000_000))
 cfg = config_C(n, 20, 1024, 3)
-model = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=65536)
+model = SGPR((cfg["X"], cfg["y"]), kernel=build_kernel(cfg), inducing_variable=cfg["Z"], chunk=262144)
 model.likelihood.variance.assign(cfg["noise"])
 freeze_unsupported(model)
 model._device_data()

@@ -313,7 +313,12 @@ def main():
                            use_normalising_flow=False, sparse=True, num_inducing=12)
     oak.fit(Xp, Yp, optimise=False)
     sob = oak.get_sobol()
-    save("g10_oak_model_pipeline", cfg_from_kernel(oak.m.kernel), X=Xp, Y=Yp, X_test=Xt,
+    # alpha and the un-normalised indices of the same model: lets the CUDA Sobol tiles be held to 1e-9 with the
+    # reference's own alpha (the indices computed from the product's alpha carry cond(Kuu))
+    alpha10 = np.asarray(ref_utils.get_model_sufficient_statistics(oak.m, get_L=False))
+    _, sob_raw = ref_utils.compute_sobol_oak(oak.m, 1, 0, share_var_across_orders=True)
+    save("g10_oak_model_pipeline", cfg_from_kernel(oak.m.kernel), X=Xp, Y=Yp, X_test=Xt, alpha=alpha10,
+         sobol_raw=np.asarray(sob_raw, dtype=np.float64),
          X_scaled=np.asarray(oak.X_scaled), Y_scaled=np.asarray(oak.Y_scaled),
          Z=np.asarray(oak.m.inducing_variable.Z.numpy()), noise=np.array(float(oak.m.likelihood.variance.numpy())),
          y_pred=np.asarray(oak.predict(Xt)), y_pred_clip=np.asarray(oak.predict(Xt, clip=True)),

@@ -38,9 +38,16 @@ def max_rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
-def max_elem_rel_err(a, b, floor=1e-12):
-    """max element-wise relative error, entries below `floor` (absolute) compared absolutely."""
+def max_elem_rel_err(a, b, floor=None):
+    """max ELEMENT-WISE relative error |a - b| / max(|b|, floor).  Entries of a constrained-kernel Gram pass through
+    zero (k~ changes sign), so entries smaller than `floor` are compared at that absolute scale; the default floor
+    is 1e-3 of the largest reference entry -- three orders tighter than the norm-wise ``max_rel_err``."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    if floor is None:
+        floor = 1e-3 * max(float(np.max(np.abs(b))), 1e-300)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor)))
 
 

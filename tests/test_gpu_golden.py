@@ -5,7 +5,7 @@ import json
 import numpy as np
 import pytest
 
-from helpers import RTOL, load_golden, max_rel_err
+from helpers import max_elem_rel_err, RTOL, load_golden, max_rel_err
 
 pytestmark = pytest.mark.gpu
 KERNEL_CASES = ["g1_gaussian_d5_p3", "g2_mixed_p2", "g3_no_share_var", "g4_unconstrained", "g9_full_depth_d8_p8"]
@@ -21,9 +21,10 @@ def test_cuda_kernel_matches_reference_golden(name, algo):
     k = build_kernel(cfg)
     k.esp_algorithm = algo
     X, X2 = g["X"], g["X2"]
-    assert max_rel_err(k.K(X), g["K"]) < RTOL
-    assert max_rel_err(k(X, X2), g["K_cross"]) < RTOL
-    assert max_rel_err(k(X, full_cov=False), g["K_diag"]) < RTOL
+    # element-wise, not norm-wise: every entry within 1e-9 of the reference's own output
+    assert max_elem_rel_err(k.K(X), g["K"]) < RTOL
+    assert max_elem_rel_err(k(X, X2), g["K_cross"]) < RTOL
+    assert max_elem_rel_err(k(X, full_cov=False), g["K_diag"]) < RTOL
     subsets = json.loads(str(g["subsets_json"]))
     for slot, ci in enumerate(g["component_index"]):
         comp = KernelComponenent(k, subsets[int(ci)], share_var_across_orders=cfg["share_var"])
@@ -90,8 +91,11 @@ def test_cuda_sobol_quadforms_with_reference_alpha():
     # (expanded squared distance) sits 1.2e-7 away from an np.longdouble evaluation of the same
     # formulas (1.43422282 vs 1.43422264; see DESIGN.md "conditioning").  The CUDA tiles use the
     # direct (x-y)^2 form and land between the two, so this case is held to 1e-6, not 1e-9.
+    # g10: the reference's own oak_model pipeline (binary + categorical + two continuous inputs, k-means inducing
+    # points); with ITS alpha the un-normalised indices are held to 1e-9
     for name, key_a, key_s, key_x, tol in (("g6_models_sobol", "sgpr_alpha", "sgpr_sobol", "Z", RTOL),
-                                           ("g7_empirical_sobol", "alpha", "sobol", "Z", 1e-6)):
+                                           ("g7_empirical_sobol", "alpha", "sobol", "Z", 1e-6),
+                                           ("g10_oak_model_pipeline", "alpha", "sobol_raw", "Z", RTOL)):
         cfg, g = load_golden(name)
         k = build_kernel(cfg)
         spec = k._make_spec()
