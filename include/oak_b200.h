@@ -187,6 +187,20 @@ int oak_gram_host_lower_f64(const oak_spec* spec, const double* h_X, int64_t n, 
                             int64_t row_end, double* h_K, int64_t ldk, int64_t block_rows, int mirror,
                             void* d_work, void* stream);
 
+/* ---- input pipeline on the device ------------------------------------------ */
+/* np.unique(X[:, col], return_counts=True) of a row-major (n x ldx) device matrix: sorted distinct values and
+ * their multiplicities (sort + run-length on order-preserving 64-bit keys: values are the input bit patterns,
+ * counts exact).  Replaces the per-column host calls that build the empirical-measure locations / weights
+ * (oak/model_utils.py:334-344) and the category frequencies p (oak/model_utils.py:736-739).
+ * d_vals[n], d_counts[n]: the first *d_num entries are written. */
+size_t oak_column_unique_work_bytes(int64_t n);
+int oak_column_unique_f64(const double* d_X, int64_t n, int64_t ldx, int64_t col, double* d_vals,
+                          int64_t* d_counts, int32_t* d_num, void* d_work, void* stream);
+/* d_out[0] = mean of column col (p0 = 1 - mean of a binary feature, oak/model_utils.py:731); fixed summation
+ * order, exact for 0/1 columns.  d_work: ceil(n / 4096) + 1 doubles. */
+int oak_column_mean_f64(const double* d_X, int64_t n, int64_t ldx, int64_t col, double* d_out, void* d_work,
+                        void* stream);
+
 /* ---- SGPR statistics --------------------------------------------------------------- */
 /* Layout of the packed statistics vector (doubles): Phi[M*M] | Kuf_y[M] | sum_kdiag | yty.
  * This is the single buffer all-reduced (sum) across ranks. */

@@ -106,6 +106,9 @@ SIGNATURES = {
     "oak_gram_backward_rows_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _dp, _i64, _vp, _vp]),
     "oak_gram_backward_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _dp, _i64, _dp, _vp, _vp]),
     "oak_gram_diag_backward_f64": (C.c_int, [_vp, _vp, _vp, _i64, _dp, C.c_double, _dp, _vp, _vp]),
+    "oak_column_unique_work_bytes": (_sz, [_i64]),
+    "oak_column_unique_f64": (C.c_int, [_dp, _i64, _i64, _i64, _dp, _vp, _vp, _vp, _vp]),
+    "oak_column_mean_f64": (C.c_int, [_dp, _i64, _i64, _i64, _dp, _vp, _vp]),
     "oak_sgpr_stats_count": (_sz, [_i64]),
     "oak_sgpr_stats_work_bytes": (_sz, [_i64, _i64]),
     "oak_sgpr_stats_f64": (C.c_int, [_vp, _vp, _i64, _vp, _dp, _i64, _i64, _dp, _vp, _vp]),

@@ -374,6 +374,41 @@ def flow_objective(x, offset: float, use_log: bool, theta, work=None):
     return out.cpu().numpy()
 
 
+def cuda_available() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available() and _cabi.load().oak_device_count() > 0
+    except Exception:
+        return False
+
+
+def column_unique(Xd, col: int):
+    """``np.unique(X[:, col], return_counts=True)`` of a device matrix: (values, counts) as NumPy arrays."""
+    torch = _torch()
+    lib = _cabi.load()
+    assert Xd.ndim == 2 and Xd.dtype == torch.float64 and Xd.stride(1) == 1
+    n = int(Xd.shape[0])
+    vals = torch.empty(max(n, 1), dtype=torch.float64, device=Xd.device)
+    counts = torch.empty(max(n, 1), dtype=torch.int64, device=Xd.device)
+    num = torch.zeros(1, dtype=torch.int32, device=Xd.device)
+    work = torch.empty(max(int(lib.oak_column_unique_work_bytes(n)) // 8 + 1, 1), dtype=torch.float64, device=Xd.device)
+    check(lib.oak_column_unique_f64(_p(Xd), n, int(Xd.stride(0)), int(col), _p(vals), _p(counts), _p(num), _p(work),
+                                    C.c_void_p(stream_ptr())), "oak_column_unique_f64")
+    u = int(num.item())
+    return vals[:u].cpu().numpy(), counts[:u].cpu().numpy()
+
+
+def column_mean(Xd, col: int) -> float:
+    torch = _torch()
+    n = int(Xd.shape[0])
+    out = torch.empty(1, dtype=torch.float64, device=Xd.device)
+    work = torch.empty(n // 4096 + 2, dtype=torch.float64, device=Xd.device)
+    check(_cabi.load().oak_column_mean_f64(_p(Xd), n, int(Xd.stride(0)), int(col), _p(out), _p(work),
+                                           C.c_void_p(stream_ptr())), "oak_column_mean_f64")
+    return float(out.item())
+
+
 # ---- whitened SVGP / Bernoulli pieces ------------------------------------------------------------
 _GH_CACHE = {}
 

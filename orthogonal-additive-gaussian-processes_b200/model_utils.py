@@ -153,10 +153,38 @@ def estimate_one_dim_gmm(K: int, X: np.ndarray) -> MOGMeasure:
     return MOGMeasure(weights=gm.weights_, means=gm.means_.reshape(-1), variances=gm.covariances_)
 
 
+class _ColumnStats:
+    """Per-column statistics of the input pipeline (distinct values + counts, means).  With a CUDA device the matrix
+    is moved to HBM once and every column is summarised there (csrc/oak_unique.cu: sort + run-length on
+    order-preserving keys, bit-identical to NumPy); without one -- the CPU-only unit tests of this host logic -- the
+    reference's own NumPy calls run.  This is one-off preprocessing, not the hot path."""
+
+    def __init__(self, X):
+        from . import _device
+
+        self.X = np.asarray(X, dtype=np.float64)
+        self.Xd = _device.to_device(self.X) if _device.cuda_available() else None
+
+    def unique(self, j):
+        if self.Xd is not None:
+            from . import _device
+
+            return _device.column_unique(self.Xd, j)
+        return np.unique(self.X[:, j], return_counts=True)
+
+    def mean(self, j):
+        if self.Xd is not None:
+            from . import _device
+
+            return _device.column_mean(self.Xd, j)
+        return self.X[:, j].mean()
+
+
 def _calculate_features(X, categorical_feature, binary_feature):
     """Feature typing and discrete measures (model_utils.py:703-750): p0 = 1 - mean, p = frequencies."""
     if binary_feature is None and categorical_feature is None:
         return list(range(X.shape[1])), [], [], None, None
+    stats = _ColumnStats(X)
     if binary_feature is not None and categorical_feature is not None:
         overlap = set(binary_feature).intersection(categorical_feature)
         if len(overlap) > 0:
@@ -164,12 +192,12 @@ def _calculate_features(X, categorical_feature, binary_feature):
     binary_index, categorical_index, continuous_index, p0, p = [], [], [], [], []
     for j in range(X.shape[1]):
         if binary_feature is not None and j in binary_feature:
-            p0.append(1 - X[:, j].mean())
+            p0.append(1 - stats.mean(j))
             p.append(None)
             binary_index.append(j)
         elif categorical_feature is not None and j in categorical_feature:
             p0.append(None)
-            vals, counts = np.unique(X[:, j], return_counts=True)
+            vals, counts = stats.unique(j)
             p.append((counts / len(X[:, j])).reshape(-1, 1))
             assert np.abs(p[-1].sum() - 1) < 1e-6
             categorical_index.append(j)
@@ -285,8 +313,9 @@ class oak_model:
 
         # empirical locations / weights from the scaled data (:334-344)
         if self.empirical_measure is not None:
+            stats = _ColumnStats(self.X_scaled)
             for ii in self.empirical_measure:
-                loc, cnt = np.unique(self.X_scaled[:, ii], return_counts=True)
+                loc, cnt = stats.unique(ii)
                 self.empirical_weights[ii] = (cnt / cnt.sum()).reshape(-1, 1)
                 self.empirical_locations[ii] = loc.reshape(-1, 1)
 

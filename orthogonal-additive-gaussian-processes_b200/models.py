@@ -267,7 +267,7 @@ class SVGP(Module):
 
     def __init__(self, kernel, likelihood, inducing_variable, *, mean_function=None, num_latent_gps: int = 1,
                  q_diag: bool = False, q_mu=None, q_sqrt=None, whiten: bool = True, num_data: Optional[int] = None,
-                 chunk: int = 65536):
+                 chunk: int = 65536, distributed: bool = False):
         if not (whiten and q_diag):
             raise NotImplementedError("only whiten=True, q_diag=True (the reference's configuration) is built")
         if num_latent_gps != 1 or mean_function is not None:
@@ -288,6 +288,11 @@ class SVGP(Module):
         self.num_data = num_data
         self.mean_function = lambda X: 0.0
         self.chunk = int(chunk)
+        # distributed=True: every rank passes its own SHARD of (X, Y) to elbo / training_loss; the data sums of the
+        # bound and of its gradient are combined by one all-reduce (declared by the caller, never inferred)
+        self.distributed = bool(distributed)
+        if self.distributed and not parallel.is_distributed():
+            raise ValueError("distributed=True needs an initialised torch.distributed process group (world size > 1)")
         self.data = None  # the reference assigns oak.m.data before the Sobol step (:145)
 
     _slice_for_kernel = GPModel._slice_for_kernel

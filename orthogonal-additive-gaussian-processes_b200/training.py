@@ -352,7 +352,10 @@ def svgp_elbo_and_grad(model, data, want_grad: bool = True):
         m, n = pz.n, int(Xs.shape[0])
         if y.numel() != n:
             raise ValueError("one label per input row")
-        scale = 1.0 if model.num_data is None else float(model.num_data) / n
+        # N axis sharded over ranks (like the SGPR statistics): the minibatch scale refers to the global batch
+        sharded = bool(getattr(model, "distributed", False))
+        n_global = parallel.allreduce_int(n) if sharded else n
+        scale = 1.0 if model.num_data is None else float(model.num_data) / n_global
         dev = Xs.device
         q_mu = _device.to_device(model.q_mu.numpy(), ndim=1).reshape(-1)
         q_sqrt = _device.to_device(model.q_sqrt.numpy(), ndim=1).reshape(-1)
@@ -391,6 +394,26 @@ def svgp_elbo_and_grad(model, data, want_grad: bool = True):
             else:
                 _device.gram_backward(spec, pz, Wc, px2=pxc, grad=grad)
             _device.gram_diag_backward(spec, pxc, w=gv, grad=grad)
+        if sharded:
+            # one all-reduce of every data sum: variational expectation | d/dq_mu | d/dq_sqrt | A-bar A^T | kernel
+            # gradients | row-point gradients (the KL term and the Kuu chain are replicated)
+            parts = [ve_sum.reshape(1)]
+            if want_grad:
+                parts += [g_qmu, g_qsqrt, G_AA.reshape(-1), grad] + ([gZ.reshape(-1)] if z_train else [])
+            packed = torch.cat(parts)
+            parallel.allreduce_sum_(packed)
+            off = 0
+
+            def take(t):
+                nonlocal off
+                t.copy_(packed[off: off + t.numel()].view_as(t))
+                off += t.numel()
+
+            ve_sum = packed[0].clone()
+            off = 1
+            if want_grad:
+                for t in [g_qmu, g_qsqrt, G_AA, grad] + ([gZ] if z_train else []):
+                    take(t)
         kl = 0.5 * float((q_mu * q_mu).sum() - m - torch.log(q_sqrt * q_sqrt).sum() + (q_sqrt * q_sqrt).sum())
         elbo = scale * float(ve_sum) - kl
         if not want_grad:

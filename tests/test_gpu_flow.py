@@ -114,3 +114,52 @@ def test_device_flow_matches_the_references_normalizer_golden():
             assert max_rel_err(y, g[f"{tag}_y_{step}"]) < 1e-13
             J = _device.flow_objective(xd, offset, log, th)[0]
             assert abs(J - float(g[f"{tag}_J_{step}"])) < 1e-12 * max(1.0, abs(J))
+
+
+# ---- the rest of the input pipeline on the device: distinct values + counts, column means -------
+@pytest.mark.parametrize("n", [1, 7, 1000, 2048, 2049, 50_000, 300_001])
+def test_column_unique_matches_numpy_bit_for_bit(n):
+    """oak_column_unique_f64 == np.unique(col, return_counts=True): the empirical-measure locations / weights
+    (oak/model_utils.py:334-344) and the category frequencies (:736-739)."""
+    from oak_b200 import _device
+
+    rng = np.random.default_rng(n)
+    X = np.zeros((n, 3))
+    X[:, 0] = np.round(8 * rng.standard_normal(n)) / 8            # config D's empirical-measure column: few levels
+    X[:, 0] = (X[:, 0] - X[:, 0].mean()) / (X[:, 0].std() if n > 1 else 1.0)
+    X[:, 1] = rng.integers(0, 6, n).astype(float)                  # categorical levels
+    X[:, 2] = rng.standard_normal(n)                               # all distinct
+    if n > 5:
+        X[3, 2], X[4, 2] = -0.0, 0.0                               # one value for np.unique
+    Xd = _device.to_device(X)
+    for col in range(3):
+        vals, counts = _device.column_unique(Xd, col)
+        ref_v, ref_c = np.unique(X[:, col], return_counts=True)
+        assert vals.shape == ref_v.shape and np.array_equal(np.abs(vals), np.abs(ref_v)) and np.array_equal(vals == 0, ref_v == 0)
+        assert np.array_equal(counts, ref_c)
+        assert np.array_equal(counts / counts.sum(), ref_c / ref_c.sum())     # the weights, bit for bit
+    b = (rng.random(n) < 0.3).astype(float)
+    assert _device.column_mean(_device.to_device(b.reshape(-1, 1)), 0) == b.mean()   # exact for 0/1 columns
+
+
+def test_feature_typing_and_empirical_measures_come_from_the_device():
+    """_calculate_features (p0, p) and the empirical locations / weights of oak_model.fit equal the NumPy results."""
+    from oak_b200 import model_utils as mu
+
+    rng = np.random.default_rng(3)
+    n = 4000
+    X = np.zeros((n, 4))
+    X[:, 0] = (rng.random(n) < 0.35).astype(float)
+    X[:, 1] = rng.integers(0, 5, n).astype(float)
+    X[:, 2] = rng.standard_normal(n)
+    X[:, 3] = np.round(4 * rng.standard_normal(n)) / 4
+    cont, binary, cat, p0, p = mu._calculate_features(X, categorical_feature=[1], binary_feature=[0])
+    assert (cont, binary, cat) == ([2, 3], [0], [1])
+    assert p0[0] == 1 - X[:, 0].mean() and p0[1] is None
+    _, cnt = np.unique(X[:, 1], return_counts=True)
+    assert np.array_equal(p[1], (cnt / n).reshape(-1, 1))
+    stats = mu._ColumnStats(X)
+    assert stats.Xd is not None                                    # the device path is the one that ran
+    loc, c3 = stats.unique(3)
+    ref_loc, ref_c = np.unique(X[:, 3], return_counts=True)
+    assert np.array_equal(loc, ref_loc) and np.array_equal(c3, ref_c)
