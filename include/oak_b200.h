@@ -257,6 +257,18 @@ size_t oak_sgpr_stats2_work_bytes(int64_t m, int64_t chunk);
 int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
                         const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
                         double* d_stats, void* d_work, double* d_kuf_store, void* stream);
+/* oak_sgpr_factor_f64 followed by oak_sgpr_stats2_f64 as one call that takes the factorisation off the
+ * critical path (it is replicated on every rank): the Kuu tiles run on `stream`, then [L ; L^-T], the
+ * condition estimate and the route flag run on an internal side stream on `overlap_ctas` CTAs while the first
+ * chunk's Kuf tiles (oak/utils.py:184 -- they need neither) keep the other SMs busy; `stream` joins the side
+ * stream before the first kernel that reads the flag, so on return everything is ordered on `stream`.
+ * overlap_ctas: 0 = serial (exactly the two calls above), > 0 = that many CTAs for the factorisation,
+ * < 0 = automatic (8 when the first chunk is long enough to cover it, else serial; OAK_SGPR_OVERLAP overrides).
+ * Results are bit-identical for every value of overlap_ctas. */
+int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, int route,
+                              double cond_threshold, double* d_fac, const void* d_pointsX, const double* d_y,
+                              int64_t n_local, int64_t chunk, double* d_stats, void* d_work, double* d_kuf_store,
+                              int overlap_ctas, void* stream);
 /* Tail of SGPR.elbo (oak/utils.py:190-198) from the (all-reduced) statistics: B = I + A A^T, LB = chol(B),
  * c = LB^-1 A err / sigma, the bound, alpha = L^-T LB^-T c.  d_LB: oak_sgpr_lb_ld(m) * m doubles, column-major
  * with that leading dimension: rows [0, m) = LB (lower triangle), row roundup8(m) = c^T.

@@ -584,6 +584,41 @@ def sgpr_stats2(spec: Spec, pz: Points, px: Points, y, fac: KuuFactor, chunk: in
     return stats
 
 
+def sgpr_factor_stats(spec: Spec, pz: Points, px: Points, y, jitter: float, route: int = ROUTE_AUTO,
+                      cond_threshold: float = 0.0, chunk: int = 262144, stats=None, keep_kuf: bool = False,
+                      kuf_store=None, overlap_ctas: int = -1, buf=None):
+    """``sgpr_factor`` + ``sgpr_stats2`` in one call (``oak_sgpr_factor_stats_f64``): the factorisation of Kuu runs
+    on a side stream next to the first chunk's Kuf tiles.  Returns (factor, stats) or, with ``keep_kuf``,
+    (factor, stats, blocks, chunk, store)."""
+    torch = _torch()
+    lib = _cabi.load()
+    m = pz.n
+    dev = pz.buf.device
+    cnt = int(lib.oak_sgpr_factor_count(m))
+    if buf is None or buf.numel() != cnt:
+        buf = torch.empty(cnt, dtype=torch.float64, device=dev)
+    if stats is None:
+        stats = torch.zeros(int(lib.oak_sgpr_stats_count(m)), dtype=torch.float64, device=dev)
+    chunk = int(max(64, min(chunk, max(px.n, 64))))
+    chunk = (chunk + 63) // 64 * 64
+    work = torch.empty(max(int(lib.oak_sgpr_stats2_work_bytes(m, chunk)) // 8, 1), dtype=torch.float64, device=dev)
+    yv = y.reshape(-1).contiguous()
+    store = None
+    nchunks = max((px.n + chunk - 1) // chunk, 1)
+    if keep_kuf:
+        store = kuf_store
+        if store is None or tuple(store.shape) != (nchunks, m, chunk) or store.device != dev:
+            store = torch.empty((nchunks, m, chunk), dtype=torch.float64, device=dev)
+    check(lib.oak_sgpr_factor_stats_f64(spec.handle, _p(pz.buf), m, float(jitter), int(route), float(cond_threshold),
+                                        _p(buf), _p(px.buf), _p(yv), px.n, chunk, _p(stats), _p(work), _p(store),
+                                        int(overlap_ctas), C.c_void_p(stream_ptr())), "oak_sgpr_factor_stats_f64")
+    fac = KuuFactor(buf, m)
+    if keep_kuf:
+        blocks = [store[c, :, : min(chunk, px.n - c * chunk)] for c in range(nchunks) if px.n - c * chunk > 0]
+        return fac, stats, blocks, chunk, store
+    return fac, stats
+
+
 class SgprTail:
     """Result of ``sgpr_finish2``: ``out`` (8 doubles on the device), ``alpha`` and the factor of B."""
 

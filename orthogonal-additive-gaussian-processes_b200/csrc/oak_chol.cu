@@ -7,12 +7,14 @@
 //
 //   for each 64-column panel
 //     phase 1  every CTA that owns rows of the panel factors the 64 x 64 diagonal block redundantly in
-//              registers (right-looking on the bordered block [S ; I]: one barrier per pivot, L11 and
+//              registers (right-looking on the bordered block [S ; I], FOUR pivots per pair of barriers: the
+//              4 x 4 diagonal block is factored redundantly by every thread, the rank-4 update follows; L11 and
 //              inv(L11) come out together) and solves its 16-row tiles of the panel as a small matrix
 //              product X = A21 inv(L11)^T; CTA 0 writes L11 back
 //     grid barrier
-//     phase 2  trailing update C -= X X^T on the 64 x 64 tiles of the lower triangle (4 x 4 register
-//              micro-tiles, FP64 FMA), one tile per CTA at M = 1024
+//     phase 2  trailing update C -= X X^T on the 64 x 64 tiles of the lower triangle (DMMA m8n8k4), one tile
+//              per CTA at M = 1024; operand loads and the read-modify-write of C are batched (all loads of a
+//              thread in flight together: element-wise loops were chains of 16 dependent L2 round trips)
 //     grid barrier
 //
 // Border rows: rows [n, rows) below the symmetric block take part in the panel solves and in the
@@ -40,7 +42,7 @@ constexpr int LD = NB + 1;          // shared-memory leading dimension (conflict
 constexpr int kThreads = 256;
 constexpr int TR = 16;              // rows per panel-solve tile
 constexpr int kBlk = NB * LD;       // doubles per staged 64 x 64 block
-constexpr size_t kSmemBytes = (3 * (size_t)kBlk + 2 * NB) * sizeof(double);  // S | Lc | Inv | rd | lg
+constexpr size_t kSmemBytes = (3 * (size_t)kBlk + 8 * NB) * sizeof(double);  // S | Lc | Inv | group columns | multipliers
 }  // namespace chol
 
 struct CholParams {
@@ -73,7 +75,6 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
   double* Lc = sm + kBlk;
   double* Inv = sm + 2 * kBlk;
   double* rd = sm + 3 * kBlk;
-  double* lg = rd + NB;
   const int tid = threadIdx.x;
   const int n = prm.n;
   const int64_t ld = prm.ld;
@@ -111,42 +112,93 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
       }
       OAK_CHOL_T(1);
       int failj = -1;
-      double* const Cs = rd;  // 2 x NB doubles (rd | lg): the published column, double buffered
-      // Groups of four pivots; the register slots ROTATE so that the group's own columns always sit in slot 0
-      // and the loop body is the same code for every group (a fully unrolled 64-pivot body is ~100 KB of
-      // straight-line code executed once per panel: instruction-fetch bound, measured 22 us against 6).
+      double* const Cs = rd;           // [4][NB]: the four columns of the group as published
+      double* const Ms = rd + 4 * NB;  // [NB][4]: the four multipliers of every row
+      // Groups of FOUR pivots per pair of barriers (one barrier per pivot before: the 64 dependent
+      // publish -> barrier -> rsqrt -> update rounds were 47 % of the factorisation).  The owners publish the
+      // group's four columns; every thread factors the 4 x 4 diagonal block redundantly (four dependent rsqrt
+      // chains -- the irreducible part) and forms the four multipliers of its own row,
+      //   m_q = (W(i, j+q) - sum_{q' < q} m_q' l_{q q'}) / l_qq,
+      // with the rule of the unified matrix deciding which terms exist: pivot column q' reaches column k of row i
+      // iff (i > j+q' and k <= i) [S part] or i <= j+q' [E part].  The multipliers are published, second barrier,
+      // and every thread applies the rank-4 update to its registers.  The register slots ROTATE so that the
+      // group's own columns always sit in slot 0 and the loop body is the same code for every group (a fully
+      // unrolled body is ~100 KB of straight-line code executed once per panel: instruction-fetch bound).
       // Two copies of the body: 16 live slots for the first eight groups, 8 for the rest.
       auto pivot_group = [&](const int g, auto slots_tag) -> bool {
         constexpr int kSlots = decltype(slots_tag)::value;
-#pragma unroll
-        for (int jq = 0; jq < 4; ++jq) {
-          const int j = 4 * g + jq;
-          double* const C = Cs + (jq & 1) * NB;
-          if (kq == jq) C[i] = w[0];
-          __syncthreads();
-          const double ajj = C[j];
-          if (!(ajj > 0.0) || !(ajj < 1.0e300)) {  // uniform: every thread reads the same value
-            failj = j;
-            return false;
+        const int j = 4 * g;
+        Cs[kq * NB + i] = w[0];
+        __syncthreads();
+        // diagonal block, lower part: a_pq = W(j+p, j+q)
+        const double a00 = Cs[j], a10 = Cs[j + 1], a20 = Cs[j + 2], a30 = Cs[j + 3];
+        double a11 = Cs[NB + j + 1];
+        const double a21 = Cs[NB + j + 2], a31 = Cs[NB + j + 3];
+        double a22 = Cs[2 * NB + j + 2];
+        const double a32 = Cs[2 * NB + j + 3];
+        double a33 = Cs[3 * NB + j + 3];
+        const double c0 = Cs[i], c1 = Cs[NB + i], c2 = Cs[2 * NB + i], c3 = Cs[3 * NB + i];
+        auto bad = [](double v) { return !(v > 0.0) || !(v < 1.0e300); };  // uniform: same value in every thread
+        if (bad(a00)) { failj = j; return false; }
+        const double r0 = rsqrt(a00);
+        const double l10 = a10 * r0, l20 = a20 * r0, l30 = a30 * r0;
+        a11 = fma(-l10, l10, a11);
+        if (bad(a11)) { failj = j + 1; return false; }
+        const double r1 = rsqrt(a11);
+        const double l21 = fma(-l20, l10, a21) * r1, l31 = fma(-l30, l10, a31) * r1;
+        a22 = fma(-l21, l21, fma(-l20, l20, a22));
+        if (bad(a22)) { failj = j + 2; return false; }
+        const double r2 = rsqrt(a22);
+        const double l32 = fma(-l31, l21, fma(-l30, l20, a32)) * r2;
+        a33 = fma(-l32, l32, fma(-l31, l31, fma(-l30, l30, a33)));
+        if (bad(a33)) { failj = j + 3; return false; }
+        const double r3 = rsqrt(a33);
+        // this row's multipliers; rule(q', q): does pivot q' reach column j+q of row i
+        const int p = i - j;  // < 0: E row above the block, 0..3: inside it, > 3: S row below it
+        auto reach = [&](int qp, int q) { return (p > qp && q <= p) || p <= qp; };
+        const double m0 = (p == 0) ? r0 : c0 * r0;
+        double t1 = c1;
+        if (reach(0, 1)) t1 = fma(-m0, l10, t1);
+        const double m1 = (p == 1) ? r1 : t1 * r1;
+        double t2 = c2;
+        if (reach(0, 2)) t2 = fma(-m0, l20, t2);
+        if (reach(1, 2)) t2 = fma(-m1, l21, t2);
+        const double m2 = (p == 2) ? r2 : t2 * r2;
+        double t3 = c3;
+        if (reach(0, 3)) t3 = fma(-m0, l30, t3);
+        if (reach(1, 3)) t3 = fma(-m1, l31, t3);
+        if (reach(2, 3)) t3 = fma(-m2, l32, t3);
+        const double m3 = (p == 3) ? r3 : t3 * r3;
+        {
+          // thread (i, kq) files pivot j + kq: L(i, j+kq) below the diagonal, inv(L11)(j+kq, i) above it
+          const double mq = kq == 0 ? m0 : kq == 1 ? m1 : kq == 2 ? m2 : m3;
+          const int jj = j + kq;
+          if (i > jj) {
+            Lc[jj * LD + i] = mq;
+          } else if (i == jj) {
+            const double ad = kq == 0 ? a00 : kq == 1 ? a11 : kq == 2 ? a22 : a33;
+            Lc[jj * LD + jj] = ad * mq;  // sqrt(a_jj) = a_jj * rsqrt(a_jj)
+            Inv[jj * LD + jj] = mq;
+          } else {
+            Inv[i * LD + jj] = mq;       // inv(L11)(jj, i) = (L11^-T)(i, jj)
           }
-          const double rs = rsqrt(ajj);
-          const double mi = (i == j) ? rs : C[i] * rs;
-          if (kq == jq) {
-            if (i > j) {
-              Lc[j * LD + i] = mi;            // L(i, j)
-            } else if (i == j) {
-              Lc[j * LD + j] = ajj * rs;      // sqrt(a_jj) without a second long-latency chain in this warp
-              Inv[j * LD + j] = rs;
-            } else {
-              Inv[i * LD + j] = mi;           // inv(L11)(j, i) = (L11^-T)(i, j)
-            }
-          }
-          const double mrs = -mi * rs;
-          const int klim = (i <= j) ? NB - 1 : i;
+          Ms[i * 4 + kq] = mq;
+        }
+        __syncthreads();
+        // rank-4 update of the columns right of the block (k >= j + 4): pivot q acts on this row unless the row
+        // lies inside the block below pivot q's own row (its S part ends at column i < k)
+        const double u0 = (p >= 1 && p <= 3) ? 0.0 : -m0;
+        const double u1 = (p >= 2 && p <= 3) ? 0.0 : -m1;
+        const double u2 = (p == 3) ? 0.0 : -m2;
+        const double u3 = -m3;
+        const int klim = (p > 3) ? i : NB - 1;
 #pragma unroll
-          for (int u = 0; u < kSlots; ++u) {
-            const int k = kq + 4 * (g + u);
-            if (k > j && k <= klim) w[u] = fma(mrs, C[k], w[u]);
+        for (int u = 1; u < kSlots; ++u) {
+          const int k = kq + 4 * (g + u);
+          if (k <= klim) {
+            const double2 ma = *reinterpret_cast<const double2*>(Ms + 4 * k);
+            const double2 mb = *reinterpret_cast<const double2*>(Ms + 4 * k + 2);
+            w[u] = fma(u3, mb.y, fma(u2, mb.x, fma(u1, ma.y, fma(u0, ma.x, w[u]))));
           }
         }
 #pragma unroll
@@ -182,11 +234,17 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
         // ---- panel solve: X = A21 inv(L11)^T on this CTA's 16-row tiles ----------------------
         for (int t = blockIdx.x; t < trsm_tiles; t += gridDim.x) {
           const int r0 = j1 + t * TR;
-          for (int e = tid; e < NB * TR; e += kThreads) {
-            const int r = e & (TR - 1), k = e >> 4;
-            const int row = r0 + r;
-            S[k * LD + r] = (row < r_end && k < nb) ? A[(int64_t)(j0 + k) * ld + grow(row)] : 0.0;
-          }
+          // (all global loads of a tile are issued before the first use: one L2 round trip, not one per element)
+          constexpr int kPer = NB * TR / kThreads;
+          const int lr = tid & (TR - 1), lk = tid >> 4;  // element e = tid + it * kThreads: row lr, column lk + 16 it
+          const int row = r0 + lr;
+          double* const gp = A + (int64_t)(j0 + lk) * ld + grow(row);
+          double vin[kPer];
+#pragma unroll
+          for (int it = 0; it < kPer; ++it)
+            vin[it] = (row < r_end && lk + 16 * it < nb) ? gp[(int64_t)(16 * it) * ld] : 0.0;
+#pragma unroll
+          for (int it = 0; it < kPer; ++it) S[(lk + 16 * it) * LD + lr] = vin[it];
           __syncthreads();
           const int c = tid & (NB - 1), rq = tid >> 6;
           double x[4] = {0.0, 0.0, 0.0, 0.0};
@@ -199,11 +257,9 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
 #pragma unroll
           for (int u = 0; u < 4; ++u) S[c * LD + rq + 4 * u] = x[u];
           __syncthreads();
-          for (int e = tid; e < NB * TR; e += kThreads) {
-            const int r = e & (TR - 1), k = e >> 4;
-            const int row = r0 + r;
-            if (row < r_end && k < nb) A[(int64_t)(j0 + k) * ld + grow(row)] = S[k * LD + r];
-          }
+#pragma unroll
+          for (int it = 0; it < kPer; ++it)
+            if (row < r_end && lk + 16 * it < nb) gp[(int64_t)(16 * it) * ld] = S[(lk + 16 * it) * LD + lr];
           __syncthreads();
         }
       }
@@ -240,11 +296,25 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
         }
         const int rbase = j1 + NB * (ct + rem), cbase = j1 + NB * ct;
         __syncthreads();
-        for (int e = tid; e < NB * NB; e += kThreads) {
-          const int r = e & (NB - 1), k = e >> 6;
-          const bool kk = k < nb;
-          Xa[k * LX + r] = (kk && rbase + r < r_end) ? A[(int64_t)(j0 + k) * ld + grow(rbase + r)] : 0.0;
-          Xb[k * LX + r] = (kk && cbase + r < n) ? A[(int64_t)(j0 + k) * ld + cbase + r] : 0.0;
+        {
+          // both operand blocks: 2 x 16 independent loads per thread in flight, then the shared-memory stores
+          // (element-by-element the loop was a chain of 16 L2 round trips: 4-6 us of the 6-11 us per tile)
+          const int lr = tid & (NB - 1), lk = tid >> 6;  // element (row lr, column lk + 4 it)
+          const bool ra = rbase + lr < r_end, rb = cbase + lr < n;
+          const double* const pa_g = A + (int64_t)(j0 + lk) * ld + grow(rbase + lr);
+          const double* const pb_g = A + (int64_t)(j0 + lk) * ld + cbase + lr;
+          double va[NB / 4], vb[NB / 4];
+#pragma unroll
+          for (int it = 0; it < NB / 4; ++it) {
+            const bool kk = lk + 4 * it < nb;
+            va[it] = (kk && ra) ? pa_g[(int64_t)(4 * it) * ld] : 0.0;
+            vb[it] = (kk && rb) ? pb_g[(int64_t)(4 * it) * ld] : 0.0;
+          }
+#pragma unroll
+          for (int it = 0; it < NB / 4; ++it) {
+            Xa[(lk + 4 * it) * LX + lr] = va[it];
+            Xb[(lk + 4 * it) * LX + lr] = vb[it];
+          }
         }
         __syncthreads();
         double acc[2][4][2];
@@ -269,18 +339,34 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
                            : "+d"(acc[a][b][0]), "+d"(acc[a][b][1])
                            : "d"(av[a]), "d"(bv[b]));
         }
+        {
+          // C -= acc: the 16 loads first, then the 16 stores (a load -> subtract -> store chain per element is
+          // sixteen dependent L2 round trips)
+          double cv[2][4][2];
+          double* cp[2][4];
+          bool ok[2][4][2];
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-          const int r = rbase + wm * 16 + a * 8 + g;
-          if (r >= r_end) continue;
-          const int64_t gr = grow(r);
+          for (int a = 0; a < 2; ++a) {
+            const int r = rbase + wm * 16 + a * 8 + g;
+            const int64_t gr = grow(r);
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
+            for (int b = 0; b < 4; ++b) {
+              const int c = cbase + wn * 32 + b * 8 + 2 * q;
+              cp[a][b] = A + (int64_t)c * ld + gr;
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int c = cbase + wn * 32 + b * 8 + 2 * q + e;
-              if (c < n && r >= c) A[(int64_t)c * ld + gr] -= acc[a][b][e];
+              for (int e = 0; e < 2; ++e) {
+                ok[a][b][e] = r < r_end && c + e < n && r >= c + e;
+                cv[a][b][e] = ok[a][b][e] ? cp[a][b][(int64_t)e * ld] : 0.0;
+              }
             }
+          }
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+                if (ok[a][b][e]) cp[a][b][(int64_t)e * ld] = cv[a][b][e] - acc[a][b][e];
         }
       }
     }
@@ -301,7 +387,7 @@ __global__ void __launch_bounds__(chol::kThreads, 1) chol_bordered_kernel(const 
 // Launcher shared with oak_sgpr.cu.  Column-major A (ld), symmetric block n x n (lower triangle), border
 // rows [n, rows) stored `gap` rows further down.
 int chol_bordered(double* A, int64_t ld, int n, int rows, int gap, int border_identity, int* d_info,
-                  double* d_logdet, int device, cudaStream_t stream) {
+                  double* d_logdet, int device, cudaStream_t stream, int max_ctas) {
   using namespace chol;
   if (n <= 0) return 0;
   OAK_REQUIRE(rows >= n && gap >= 0 && ld >= (int64_t)rows + gap, "chol_bordered: bad shape");
@@ -330,7 +416,8 @@ int chol_bordered(double* A, int64_t ld, int n, int rows, int gap, int border_id
     if (t1 > want) want = t1;
     if (t2 > want) want = t2;
   }
-  const int grid = want < sms ? want : sms;
+  int grid = want < sms ? want : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   CholParams prm{A, ld, n, rows, gap, border_identity, d_info, d_logdet};
   void* args[] = {&prm};
   OAK_CUDA(cudaLaunchCooperativeKernel((const void*)chol_bordered_kernel, dim3(grid), dim3(kThreads), args,

@@ -115,7 +115,8 @@ int tile_rows_for_depth(int depth);
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt = nullptr,
-                int64_t ldkt = 0, const double* ydot_y = nullptr, double* ydot_part = nullptr);
+                int64_t ldkt = 0, const double* ydot_y = nullptr, double* ydot_part = nullptr, int sm_reserve = 0);
+// sm_reserve: the persistent grid leaves that many SMs free (for a small kernel running next to the tiles)
 // the folded K y of the general-mode tiles (depth <= 4): ydot_part holds ceil(cols / 64) x rows partial sums
 inline bool gram_can_fold_ky(const oak_spec* spec) { return spec->depth <= 4; }
 // per-dimension min / max keys of the prepared coordinate: [D] min keys then [D] max keys
@@ -136,8 +137,9 @@ int panel_gemm_dmma(const double* T, int64_t ldt, const double* B, int64_t ldb, 
                     int64_t n, int lower, const double* u, const double* v, const int* d_gate, int* d_counter,
                     int device, cudaStream_t stream);
 // blocked Cholesky with border rows, one cooperative launch (oak_chol.cu)
+// max_ctas > 0 caps the grid (the factorisation then shares the GPU with another kernel)
 int chol_bordered(double* A, int64_t ld, int n, int rows, int gap, int border_identity, int* d_info,
-                  double* d_logdet, int device, cudaStream_t stream);
+                  double* d_logdet, int device, cudaStream_t stream, int max_ctas = 0);
 int gram_diag_launch(const oak_spec* spec, const double2* pts, int64_t n, int64_t n_pad,
                      double* out, cudaStream_t stream);
 

@@ -782,7 +782,7 @@ static int launch_matvec(GramParams prm, int algo, int sms, const double* alpha,
 int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, int64_t row_begin,
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt, int64_t ldkt,
-                const double* ydot_y, double* ydot_part) {
+                const double* ydot_y, double* ydot_part, int sm_reserve) {
   GramParams prm;
   prm.Kt = Kt;
   prm.ldkt = ldkt;
@@ -824,7 +824,8 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
   prm.tile_row0 = 0;
   prm.tiles_n = 0;
   prm.num_tiles = 0;
-  const int sms = sm_count(spec->device);
+  int sms = sm_count(spec->device);
+  if (sm_reserve > 0) sms = sms - sm_reserve > 1 ? sms - sm_reserve : 1;
   const int algo = spec->algo;
   switch (depth) {
     case 0:

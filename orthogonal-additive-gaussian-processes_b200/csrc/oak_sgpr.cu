@@ -62,6 +62,34 @@ static int handles(cublasHandle_t* cb, cusolverDnHandle_t* cs, cudaStream_t stre
   return 0;
 }
 
+// Side stream of the overlapped front (oak_sgpr_factor_stats_f64): its own cuBLAS handle (a handle's
+// workspace belongs to one stream at a time), a non-blocking stream (no implicit ordering against the legacy
+// default stream the caller may be using) and the two events of the fork / join.
+struct SideLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cublasHandle_t cublas = nullptr;
+};
+static SideLane g_side[64];
+
+static int side_lane(SideLane** out) {
+  int dev = 0;
+  OAK_CUDA(cudaGetDevice(&dev));
+  OAK_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  std::lock_guard<std::mutex> lock(g_handle_mu);
+  SideLane& l = g_side[dev];
+  if (!l.stream) {
+    OAK_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    OAK_CUDA(cudaEventCreateWithFlags(&l.fork, cudaEventDisableTiming));
+    OAK_CUDA(cudaEventCreateWithFlags(&l.join, cudaEventDisableTiming));
+    OAK_CUBLAS(cublasCreate(&l.cublas));
+    OAK_CUBLAS(cublasSetPointerMode(l.cublas, CUBLAS_POINTER_MODE_HOST));
+    OAK_CUBLAS(cublasSetStream(l.cublas, l.stream));
+  }
+  *out = &l;
+  return 0;
+}
+
 // out[0] += sum_i a[i] * (b ? b[i] : 1), fixed summation order (one block).
 __global__ void __launch_bounds__(1024) reduce_accumulate_kernel(const double* __restrict__ a,
                                                                  const double* __restrict__ b,
@@ -659,26 +687,32 @@ extern "C" size_t oak_sgpr_factor_count(int64_t m) {
 extern "C" int64_t oak_sgpr_factor_ld(int64_t m) { return m < 1 ? 0 : fac_ld(m); }
 extern "C" int64_t oak_sgpr_lb_ld(int64_t m) { return m < 1 ? 0 : lb_ld(m); }
 
-extern "C" int oak_sgpr_factor_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, int route,
-                                   double cond_threshold, double* d_fac, void* stream_) {
-  OAK_REQUIRE(spec && d_pointsZ && d_fac, "oak_sgpr_factor_f64: null argument");
-  OAK_REQUIRE(m >= 1 && m <= INT32_MAX / 8, "oak_sgpr_factor_f64: bad M");
-  OAK_REQUIRE(reinterpret_cast<uintptr_t>(d_fac) % 16 == 0, "oak_sgpr_factor_f64: d_fac must be 16-byte aligned");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  cublasHandle_t cb;
-  if (int rc = handles(&cb, nullptr, stream)) return rc;
+// Kuu(iv, kernel) (oak/utils.py:185) + jitter I with the identity border, column 1-norms, start vector
+static int factor_pre(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, double* d_fac,
+                      cudaStream_t stream) {
+  const int64_t mp = fac_mp(m), ld = fac_ld(m);
+  double* hdr = d_fac + ld * m;
+  double* scratch = hdr + kHdrDoubles;  // colsum | wa | wb | wc
+  const double2* pz = (const double2*)d_pointsZ;
+  // row-major with pitch LD == column-major (symmetric)
+  if (int rc = gram_launch(spec, pz, padded(m), 0, m, pz, padded(m), 0, m, 1, d_fac, ld, stream)) return rc;
+  fac_init_kernel<<<(unsigned)m, 256, 0, stream>>>(d_fac, (int)m, (int)mp, ld, jitter, scratch, scratch + mp);
+  OAK_LAUNCHED();
+  return 0;
+}
+
+// [L ; L^-T], the condition estimate and the route flag; `cb` must be bound to `stream`.  max_ctas > 0: the
+// factorisation runs on that many CTAs (next to the first chunk's Gram tiles, see oak_sgpr_factor_stats_f64).
+static int factor_chol(const oak_spec* spec, int64_t m, int route, double cond_threshold, double* d_fac,
+                       cublasHandle_t cb, cudaStream_t stream, int max_ctas) {
   const int64_t mp = fac_mp(m), ld = fac_ld(m);
   const int M = (int)m;
   double* hdr = d_fac + ld * m;
-  double* scratch = hdr + kHdrDoubles;  // colsum | wa | wb | wc
+  double* scratch = hdr + kHdrDoubles;
   double *colsum = scratch, *wa = scratch + mp, *wb = scratch + 2 * mp, *wc = scratch + 3 * mp;
-  const double2* pz = (const double2*)d_pointsZ;
-  // Kuu(iv, kernel) (oak/utils.py:185): row-major with pitch LD == column-major (symmetric)
-  if (int rc = gram_launch(spec, pz, padded(m), 0, m, pz, padded(m), 0, m, 1, d_fac, ld, stream)) return rc;
-  fac_init_kernel<<<(unsigned)m, 256, 0, stream>>>(d_fac, M, (int)mp, ld, jitter, colsum, wa);
-  OAK_LAUNCHED();
-  // [L ; L^-T]: L = chol(Kuu + jitter I) (utils.py:188) with the identity as border rows
-  if (int rc = chol_bordered(d_fac, ld, M, 2 * M, (int)(mp - m), 1, hdr_ints(hdr) + 1, hdr + 5, spec->device, stream))
+  // L = chol(Kuu + jitter I) (utils.py:188) with the identity as border rows
+  if (int rc = chol_bordered(d_fac, ld, M, 2 * M, (int)(mp - m), 1, hdr_ints(hdr) + 1, hdr + 5, spec->device, stream,
+                             max_ctas))
     return rc;
   // lambda_max(Kuu^-1) = ||L^-T||_2^2: three power iterations on U U^T, U = L^-T
   const double* U = d_fac + mp;
@@ -694,6 +728,18 @@ extern "C" int oak_sgpr_factor_f64(const oak_spec* spec, const void* d_pointsZ, 
   route_kernel<<<1, 256, 0, stream>>>(hdr, colsum, wa, wc, M, route, cond_threshold > 0.0 ? cond_threshold : 3.0e5);
   OAK_LAUNCHED();
   return 0;
+}
+
+extern "C" int oak_sgpr_factor_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, int route,
+                                   double cond_threshold, double* d_fac, void* stream_) {
+  OAK_REQUIRE(spec && d_pointsZ && d_fac, "oak_sgpr_factor_f64: null argument");
+  OAK_REQUIRE(m >= 1 && m <= INT32_MAX / 8, "oak_sgpr_factor_f64: bad M");
+  OAK_REQUIRE(reinterpret_cast<uintptr_t>(d_fac) % 16 == 0, "oak_sgpr_factor_f64: d_fac must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  cublasHandle_t cb;
+  if (int rc = handles(&cb, nullptr, stream)) return rc;
+  if (int rc = factor_pre(spec, d_pointsZ, m, jitter, d_fac, stream)) return rc;
+  return factor_chol(spec, m, route, cond_threshold, d_fac, cb, stream, 0);
 }
 
 constexpr int kKySegments = 64;
@@ -734,9 +780,13 @@ extern "C" size_t oak_sgpr_stats2_work_bytes(int64_t m, int64_t chunk) {
 // accumulated into d_stats; the route is read on the device from the header of d_fac.  Kuf y comes out of the
 // Gram-tile epilogue (warp-shuffle row sums per tile, summed in a fixed order) when the depth allows it.
 // d_kuf_store (nullable): keeps every chunk's Kuf block as in oak_sgpr_stats_keep_f64.
-extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
-                                   const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
-                                   double* d_stats, void* d_work, double* d_kuf_store, void* stream_) {
+// sm_reserve / route_ready: the overlapped front -- the first chunk's Gram tiles (which do not depend on the
+// factorisation) leave sm_reserve SMs to it, and the stream waits for route_ready before the first kernel that
+// reads the route flag.
+static int sgpr_stats2_impl(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
+                            const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
+                            double* d_stats, void* d_work, double* d_kuf_store, void* stream_, int sm_reserve,
+                            cudaEvent_t route_ready) {
   OAK_REQUIRE(spec && d_pointsZ && d_fac && d_stats && d_work, "oak_sgpr_stats2_f64: null argument");
   OAK_REQUIRE(m >= 1, "oak_sgpr_stats2_f64: need at least one inducing point");
   OAK_REQUIRE(n_local >= 0, "oak_sgpr_stats2_f64: negative n");
@@ -774,8 +824,9 @@ extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, 
     // the per-tile row sums of Kuf y (no second pass over the 2 GB block)
     const bool fold = fold_ky;
     if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream, nullptr, 0,
-                             fold ? d_y + c0 : nullptr, fold ? ypart : nullptr))
+                             fold ? d_y + c0 : nullptr, fold ? ypart : nullptr, c0 == 0 ? sm_reserve : 0))
       return rc;
+    if (c0 == 0 && route_ready) OAK_CUDA(cudaStreamWaitEvent(stream, route_ready, 0));
     // route 1: A_r = L^-1 Kuf_r (utils.py:189), a no-op launch otherwise
     if (int rc = panel_gemm_dmma(d_fac + mp, ld, kuf, chunk, abuf, chunk, (int)m, (int)m, nc, 1, nullptr, nullptr,
                                  d_route, d_counter, spec->device, stream))
@@ -819,6 +870,53 @@ extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, 
     OAK_LAUNCHED();
   }
   return 0;
+}
+
+extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
+                                   const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
+                                   double* d_stats, void* d_work, double* d_kuf_store, void* stream_) {
+  return sgpr_stats2_impl(spec, d_pointsZ, m, d_fac, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store,
+                          stream_, 0, nullptr);
+}
+
+// oak_sgpr_factor_f64 + oak_sgpr_stats2_f64 as ONE call that hides the factorisation: the Kuu tiles run first on
+// `stream`; [L ; L^-T], the condition estimate and the route flag then run on an internal side stream on
+// `overlap_ctas` CTAs while the first chunk's Kuf tiles -- which need neither -- occupy the other SMs, and `stream`
+// joins the side stream before the first kernel that reads the flag.  The bordered Cholesky is latency bound
+// (1024 dependent pivots: 0.57 ms on a whole GPU it cannot fill), the tiles are throughput bound, so lending the
+// factorisation 8 of 148 SMs costs the tiles 5 % of ONE chunk instead of 0.57 ms on the critical path of every
+// evaluation -- which is replicated on every rank (it is what held the 8-GPU ELBO below linear scaling).
+// overlap_ctas: 0 = serial (exactly the two calls), > 0 = that many CTAs, < 0 = automatic (8 when the first chunk
+// is long enough to cover the slower factorisation, else serial).  On return all work is ordered on `stream`.
+extern "C" int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter,
+                                         int route, double cond_threshold, double* d_fac, const void* d_pointsX,
+                                         const double* d_y, int64_t n_local, int64_t chunk, double* d_stats,
+                                         void* d_work, double* d_kuf_store, int overlap_ctas, void* stream_) {
+  OAK_REQUIRE(spec && d_pointsZ && d_fac, "oak_sgpr_factor_stats_f64: null argument");
+  OAK_REQUIRE(m >= 1 && m <= INT32_MAX / 8, "oak_sgpr_factor_stats_f64: bad M");
+  OAK_REQUIRE(reinterpret_cast<uintptr_t>(d_fac) % 16 == 0, "oak_sgpr_factor_stats_f64: d_fac must be 16-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  static const int env_overlap = getenv("OAK_SGPR_OVERLAP") ? atoi(getenv("OAK_SGPR_OVERLAP")) : -1;
+  if (overlap_ctas < 0) {
+    // the factorisation on 8 CTAs takes ~3x its whole-GPU time; the tiles of the first chunk must outlast it:
+    // m * nc Gram entries at ~5e10 entries/s against ~1.6 us * m (1.6 ms at M = 1024)
+    const int64_t nc = n_local < chunk ? n_local : chunk;
+    overlap_ctas = env_overlap >= 0 ? env_overlap : (nc >= 100000 && m >= 256 ? 8 : 0);
+  }
+  if (overlap_ctas == 0 || n_local <= 0) {
+    if (int rc = oak_sgpr_factor_f64(spec, d_pointsZ, m, jitter, route, cond_threshold, d_fac, stream_)) return rc;
+    return sgpr_stats2_impl(spec, d_pointsZ, m, d_fac, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store,
+                            stream_, 0, nullptr);
+  }
+  SideLane* lane = nullptr;
+  if (int rc = side_lane(&lane)) return rc;
+  if (int rc = factor_pre(spec, d_pointsZ, m, jitter, d_fac, stream)) return rc;
+  OAK_CUDA(cudaEventRecord(lane->fork, stream));
+  OAK_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
+  if (int rc = factor_chol(spec, m, route, cond_threshold, d_fac, lane->cublas, lane->stream, overlap_ctas)) return rc;
+  OAK_CUDA(cudaEventRecord(lane->join, lane->stream));
+  return sgpr_stats2_impl(spec, d_pointsZ, m, d_fac, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store,
+                          stream_, overlap_ctas, lane->join);
 }
 
 extern "C" size_t oak_sgpr_finish2_work_bytes(int64_t m) {

@@ -160,6 +160,7 @@ class SGPR(GPModel):
             raise ValueError("distributed=True needs an initialised torch.distributed process group (world size > 1)")
         self.whiten_stats = whiten_stats
         self.cond_threshold = float(cond_threshold)
+        self.overlap_ctas = -1      # CTAs lent to the overlapped factorisation (-1 automatic, 0 serial)
         self.last_route = None      # route / condition estimate of the last evaluation (diagnostics)
         self.last_cond_estimate = None
         self.last_timings = {}
@@ -188,8 +189,10 @@ class SGPR(GPModel):
             self.kernel._check_discrete(Zs, spec._keep)
             pz, px = _device.Points(spec, Zs), _device.Points(spec, Xs)
             # Kuu(iv, kernel) + jitter I, L = chol, L^-1, route flag -- before the statistics, all on the device
-            fac = _device.sgpr_factor(spec, pz, DEFAULT_JITTER, route=self._route(), cond_threshold=self.cond_threshold)
-            stats = _device.sgpr_stats2(spec, pz, px, Yd, fac, chunk=self.chunk)
+            # (one call: the factorisation is hidden behind the first chunk's Kuf tiles)
+            fac, stats = _device.sgpr_factor_stats(spec, pz, px, Yd, DEFAULT_JITTER, route=self._route(),
+                                                   cond_threshold=self.cond_threshold, chunk=self.chunk,
+                                                   overlap_ctas=self.overlap_ctas)
             n_total = int(Xs.shape[0])
             if self.distributed:
                 parallel.allreduce_sum_(stats)

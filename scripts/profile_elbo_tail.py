@@ -36,3 +36,9 @@ for route in (0, 1):
     f2 = _device.sgpr_factor(spec, pz, DEFAULT_JITTER, route=route)
     t_s, _ = T(lambda: _device.sgpr_stats2(spec, pz, px, Yd, f2, chunk=262144), reps=5)
     print(f"  stats phase, forced route {route}: {t_s:.3f} ms")
+# the fused call: factorisation on a side stream next to the first chunk's Kuf tiles
+for ov in [int(v) for v in os.environ.get("AB_OVERLAPS", "0,4,6,8,12,16").split(",")]:
+    t_fs, _ = T(lambda: _device.sgpr_factor_stats(spec, pz, px, Yd, DEFAULT_JITTER, chunk=262144, overlap_ctas=ov), reps=10)
+    model.overlap_ctas = ov
+    t_e, _ = T(model.elbo, reps=10)
+    print(f"  overlap_ctas {ov:3d}: factor + stats {t_fs:.3f} ms, whole ELBO evaluation {t_e:.3f} ms")

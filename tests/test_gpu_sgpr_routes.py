@@ -212,3 +212,35 @@ def test_failed_factorisation_is_reported_at_the_single_readback():
     cfg["Z"] = cfg["X"][: len(cfg["Z"])].copy()
     with pytest.raises(OakNativeError, match="Cholesky"):
         _sgpr(cfg).elbo()
+
+
+@pytest.mark.parametrize("route", [0, 1])
+@pytest.mark.parametrize("overlap", [-1, 4, 8])
+def test_overlapped_factorisation_is_bit_identical_to_the_two_serial_calls(route, overlap):
+    """``oak_sgpr_factor_stats_f64``: the factorisation on a side stream next to the first chunk's Kuf tiles
+    (fewer CTAs for both kernels) changes the schedule, not one bit of the factor, the statistics or the bound."""
+    import torch
+
+    from oak_b200 import _device
+    from oak_b200.workloads import build_kernel
+
+    cfg = mixed_config(n=2500, seed=11, depth=3)
+    Z = cfg["X"][:300].copy()
+    k = build_kernel(cfg)
+    spec = k._make_spec()
+    try:
+        pz = _device.Points(spec, _device.to_device(Z))
+        px = _device.Points(spec, _device.to_device(cfg["X"]))
+        y = _device.to_device(cfg["y"])
+        fac0 = _device.sgpr_factor(spec, pz, 1e-6, route=route)
+        st0 = _device.sgpr_stats2(spec, pz, px, y, fac0, chunk=1024)
+        out0 = _device.sgpr_finish2(fac0, st0, 2500, 0.05).host()
+        for _ in range(3):   # repeated: the side stream's events and buffers are reused
+            fac1, st1 = _device.sgpr_factor_stats(spec, pz, px, y, 1e-6, route=route, chunk=1024, overlap_ctas=overlap)
+            out1 = _device.sgpr_finish2(fac1, st1, 2500, 0.05).host()
+            assert torch.equal(fac0.buf[: fac0.ld * fac0.m], fac1.buf[: fac1.ld * fac1.m])
+            assert torch.equal(st0, st1)
+            assert np.array_equal(out0, out1)
+        assert out1[6] == route
+    finally:
+        spec.close()
