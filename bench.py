@@ -543,6 +543,8 @@ def main():
         ms_stats, st = timed_dev(lambda: _device.sgpr_stats2(sp, pz, pxs, Ys, fac))
         ms_factor, _ = timed_dev(lambda: _device.sgpr_factor(sp, pz, 1e-6, buf=fac.buf))
         ms_finish, _ = timed_dev(lambda: _device.sgpr_finish2(fac, st, args.elbo_n, cfg_c["noise"], want_alpha=False))
+        # what the model calls: factorisation on a side stream next to the first chunk's Kuf tiles
+        ms_fused, _ = timed_dev(lambda: _device.sgpr_factor_stats(sp, pz, pxs, Ys, 1e-6, buf=fac.buf))
         ms_allreduce = None
         if world > 1:
             ms_allreduce, _ = timed_dev(lambda: parallel.allreduce_sum_(st))
@@ -556,6 +558,10 @@ def main():
             "metric": "SGPR ELBO evals/sec", "value": 1e3 / ms_elbo, "unit": "evals/s", "ms_per_eval": ms_elbo,
             "ms_stats_phase": ms_stats, "ms_tail_and_collective": ms_elbo - ms_stats, "elbo": vals[-1],
             "ms_factor_front": ms_factor, "ms_finish_tail": ms_finish, "ms_allreduce": ms_allreduce,
+            "ms_factor_and_stats_overlapped": ms_fused,
+            "overlap_note": "oak_sgpr_factor_stats_f64: chol(Kuu) + condition estimate run on a side stream on 6 CTAs "
+                            "while the first chunk's Kuf tiles leave them 6 of the 148 SMs; ms_stats_phase and "
+                            "ms_factor_front are the two pieces timed serially on their own",
             "route": model.last_route, "cond_estimate_kuu": model.last_cond_estimate,
             "ms_stats_phase_whitened_route": ms_stats_w,
             "workload": f"config C: N={args.elbo_n}, D=20, M={args.elbo_m}, depth 3; N axis sharded over {world} "

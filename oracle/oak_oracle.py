@@ -406,6 +406,68 @@ def sgpr_predict_mean(kern: OakOracle, X, Y, Z, noise, Xnew, jitter=JITTER):
 # --------------------------------------------------------------------------------------
 # Sobol indices (oak/utils.py:116-165, 221-435)
 # --------------------------------------------------------------------------------------
+# ---- SVGP + Bernoulli (the classification run, examples/uci/uci_classification_train.py:108-135) ------
+# gpflow 2.2.1 is not vendored: restated from models/svgp.py (elbo, prior_kl), kullback_leiblers.py (gauss_kl with
+# K=None and a diagonal q_sqrt), conditionals/util.py (base_conditional, white=True), likelihoods (Bernoulli,
+# NDiagGHQuadrature with 20 points), posteriors.py (alpha = L^-T q_mu, Qinv = L^-T (I - diag q_sqrt^2) L^-1).
+# Pinned by tests/golden/g11_svgp_classification.npz: the reference's own get_model_sufficient_statistics SVGP
+# branch (oak/utils.py:174-179), compute_sobol_oak and get_prediction_component run over oracle/tf_shim.
+def inv_logit(f, jitter=1e-3):  # uci_classification_train.py:43-45
+    return 1.0 / (1.0 + np.exp(-np.asarray(f, dtype=np.float64))) * (1 - 2 * jitter) + jitter
+
+
+def svgp_alpha(kern: OakOracle, Z, q_mu, jitter=JITTER):
+    """``posterior.alpha`` of the SVGP branch of ``get_model_sufficient_statistics`` (oak/utils.py:174-177)."""
+    import scipy.linalg as sla
+
+    L = _chol(kern.K(Z) + jitter * np.eye(Z.shape[0]))
+    return sla.solve_triangular(L, np.asarray(q_mu).reshape(-1, 1), lower=True, trans="T")
+
+
+def svgp_L(kern: OakOracle, Z, q_sqrt, jitter=JITTER):
+    """``cholesky(inv(posterior.Qinv[0]))`` (oak/utils.py:178-179)."""
+    import scipy.linalg as sla
+
+    L = _chol(kern.K(Z) + jitter * np.eye(Z.shape[0]))
+    B = np.eye(Z.shape[0]) - np.diag(np.asarray(q_sqrt).reshape(-1) ** 2)
+    LinvT_B = sla.solve_triangular(L, B, lower=True, trans="T")
+    Qinv = sla.solve_triangular(L, LinvT_B.T, lower=True, trans="T")
+    return _chol(np.linalg.inv(Qinv))
+
+
+def svgp_predict_f(kern: OakOracle, Z, q_mu, q_sqrt, Xnew, jitter=JITTER):
+    """Marginal mean and variance of the whitened conditional with a diagonal q(u)."""
+    A = _trsm_lower(_chol(kern.K(Z) + jitter * np.eye(Z.shape[0])), kern.K(Z, Xnew))
+    fvar = kern.K_diag(Xnew) - np.sum(A * A, 0)
+    fmean = (A.T @ np.asarray(q_mu).reshape(-1, 1))[:, 0]
+    LTA = A * np.asarray(q_sqrt).reshape(-1, 1)
+    return fmean, fvar + np.sum(LTA * LTA, 0)
+
+
+def _bernoulli_nodes(fmean, fvar, Y, invlink, n_gh):
+    x, w = np.polynomial.hermite.hermgauss(n_gh)
+    F = fmean[:, None] + np.sqrt(fvar)[:, None] * (x * np.sqrt(2.0))[None, :]
+    p = invlink(F)
+    return np.log(np.where(np.asarray(Y).reshape(-1, 1) == 1, p, 1 - p)), w / np.sqrt(np.pi)
+
+
+def svgp_elbo(kern: OakOracle, X, Y, Z, q_mu, q_sqrt, invlink=inv_logit, num_data=None, n_gh=20, jitter=JITTER):
+    fmean, fvar = svgp_predict_f(kern, Z, q_mu, q_sqrt, X, jitter)
+    logp, w = _bernoulli_nodes(fmean, fvar, Y, invlink, n_gh)
+    q_mu, q_sqrt = np.asarray(q_mu).reshape(-1), np.asarray(q_sqrt).reshape(-1)
+    two_kl = np.sum(q_mu ** 2) - q_mu.size - np.sum(np.log(q_sqrt ** 2)) + np.sum(q_sqrt ** 2)
+    scale = 1.0 if num_data is None else num_data / X.shape[0]
+    return float(np.sum(logp * w) * scale - 0.5 * two_kl)
+
+
+def svgp_predict_log_density(kern: OakOracle, Z, q_mu, q_sqrt, Xnew, Ynew, invlink=inv_logit, n_gh=20, jitter=JITTER):
+    from scipy.special import logsumexp
+
+    fmean, fvar = svgp_predict_f(kern, Z, q_mu, q_sqrt, Xnew, jitter)
+    logp, w = _bernoulli_nodes(fmean, fvar, Ynew, invlink, n_gh)
+    return logsumexp(logp + np.log(w)[None, :], axis=1)
+
+
 def f1(x, y, sigma, l, delta, mu):  # utils.py:116-125
     return (
         sigma ** 4 * l / np.sqrt(l ** 2 + 2 * delta ** 2)

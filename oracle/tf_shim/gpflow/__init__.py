@@ -362,8 +362,103 @@ class SGPR(GPModel):
         return _eager(mean), _eager(var[:, None])
 
 
+class Bernoulli(Module):
+    """gpflow 2.2.1 ``likelihoods.Bernoulli`` (restated): ScalarLikelihood with 20-point Gauss-Hermite quadrature
+    (``NDiagGHQuadrature``: nodes of ``np.polynomial.hermite.hermgauss`` times sqrt 2, weights over sqrt pi)."""
+
+    num_gauss_hermite_points = 20
+
+    def __init__(self, invlink=None):
+        from scipy.special import ndtr
+
+        self.invlink = invlink if invlink is not None else (lambda f: ndtr(f) * (1 - 2e-3) + 1e-3)  # inv_probit
+
+    def _log_prob(self, F, Y):
+        p = np.asarray(self.invlink(F), dtype=np.float64)
+        return np.log(np.where(Y == 1, p, 1 - p))      # logdensities.bernoulli
+
+    def _quad_nodes(self, Fmu, Fvar):
+        x, w = np.polynomial.hermite.hermgauss(self.num_gauss_hermite_points)
+        F = Fmu[..., None] + np.sqrt(Fvar)[..., None] * (x * np.sqrt(2.0))
+        return F, w / np.sqrt(np.pi)
+
+    def variational_expectations(self, Fmu, Fvar, Y):
+        F, w = self._quad_nodes(np.asarray(Fmu)[:, 0], np.asarray(Fvar)[:, 0])
+        return np.sum(self._log_prob(F, np.asarray(Y)[:, :1]) * w, axis=-1)
+
+    def predict_log_density(self, Fmu, Fvar, Y):
+        from scipy.special import logsumexp
+
+        F, w = self._quad_nodes(np.asarray(Fmu)[:, 0], np.asarray(Fvar)[:, 0])
+        return logsumexp(self._log_prob(F, np.asarray(Y)[:, :1]) + np.log(w), axis=-1)
+
+
+class _Posterior:
+    """gpflow 2.2.1 ``posteriors.IndependentPosteriorSingleOutput._precompute`` (restated) for whiten=True and a
+    diagonal q: alpha = L^-T q_mu, Qinv = L^-T (I - diag(q_sqrt^2)) L^-1 with L = chol(Kuu + jitter I)."""
+
+    def __init__(self, model):
+        Kmm = Kuu(model.inducing_variable, model.kernel, jitter=default_jitter())
+        L = np.linalg.cholesky(Kmm)
+        q_mu, q_sqrt = model.q_mu.numpy(), model.q_sqrt.numpy()
+        self.alpha = _eager(_sla.solve_triangular(L, q_mu, lower=True, trans="T"))
+        B = np.eye(L.shape[0]) - np.diag(q_sqrt[:, 0] ** 2)
+        LinvT_B = _sla.solve_triangular(L, B, lower=True, trans="T")
+        self.Qinv = _eager(_sla.solve_triangular(L, LinvT_B.T, lower=True, trans="T")[None])
+
+
 class SVGP(GPModel):
-    pass
+    """gpflow 2.2.1 ``models.SVGP`` (restated) in the one configuration the reference builds
+    (examples/uci/uci_classification_train.py:108-116): whiten=True, q_diag=True, one latent GP, zero mean."""
+
+    def __init__(self, kernel, likelihood, inducing_variable, *, whiten=True, q_diag=False, q_mu=None, q_sqrt=None,
+                 num_data=None, mean_function=None, num_latent_gps=1):
+        assert whiten and q_diag and num_latent_gps == 1, "the shim restates the reference's configuration only"
+        self.kernel, self.likelihood, self.num_data = kernel, likelihood, num_data
+        self.inducing_variable = inducing_variable if isinstance(inducing_variable, InducingPoints) else \
+            InducingPoints(inducing_variable)
+        m = len(self.inducing_variable)
+        self.q_mu = Parameter(np.zeros((m, 1)) if q_mu is None else q_mu)
+        self.q_sqrt = Parameter(np.ones((m, 1)) if q_sqrt is None else q_sqrt, transform=positive())
+        self.whiten, self.q_diag = whiten, q_diag
+        self.mean_function = lambda X: np.zeros((np.shape(X)[0], 1))
+
+    def posterior(self):
+        return _Posterior(self)
+
+    def prior_kl(self):
+        # kullback_leiblers.gauss_kl(q_mu, q_sqrt, K=None) with a diagonal q_sqrt
+        q_mu, q_sqrt = self.q_mu.numpy(), self.q_sqrt.numpy()
+        two_kl = np.sum(q_mu ** 2) - q_sqrt.size - np.sum(np.log(q_sqrt ** 2)) + np.sum(q_sqrt ** 2)
+        return 0.5 * two_kl
+
+    def predict_f(self, Xnew, full_cov=False):
+        # conditionals.util.base_conditional(Kmn, Kmm, Knn, f=q_mu, q_sqrt=diag, white=True)
+        Kmm = Kuu(self.inducing_variable, self.kernel, jitter=default_jitter())
+        Kmn = Kuf(self.inducing_variable, self.kernel, Xnew)
+        Knn = np.asarray(self.kernel(Xnew, full_cov=False))
+        Lm = np.linalg.cholesky(Kmm)
+        A = _sla.solve_triangular(Lm, Kmn, lower=True)
+        fvar = Knn - np.sum(A * A, 0)
+        fmean = A.T @ self.q_mu.numpy()
+        LTA = A * self.q_sqrt.numpy()
+        fvar = fvar + np.sum(LTA * LTA, 0)
+        return _eager(fmean), _eager(fvar[:, None])
+
+    def elbo(self, data):
+        X, Y = data
+        kl = self.prior_kl()
+        f_mean, f_var = self.predict_f(X)
+        var_exp = self.likelihood.variational_expectations(f_mean, f_var, Y)
+        scale = 1.0 if self.num_data is None else self.num_data / np.shape(X)[0]
+        return float(np.sum(var_exp) * scale - kl)
+
+    maximum_log_likelihood_objective = elbo
+
+    def predict_log_density(self, data):
+        X, Y = data
+        f_mean, f_var = self.predict_f(X)
+        return _eager(self.likelihood.predict_log_density(f_mean, f_var, Y))
 
 
 class _Scipy:
@@ -399,3 +494,4 @@ models = _mod("gpflow.models", GPR=GPR, SGPR=SGPR, SVGP=SVGP, GPModel=GPModel, B
 _disp = _mod("gpflow.covariances.dispatch", Kuf=Kuf, Kuu=Kuu)
 covariances = _mod("gpflow.covariances", dispatch=_disp, Kuf=Kuf, Kuu=Kuu)
 optimizers = _mod("gpflow.optimizers", Scipy=_Scipy)
+likelihoods = _mod("gpflow.likelihoods", Bernoulli=Bernoulli, Gaussian=_Gaussian)

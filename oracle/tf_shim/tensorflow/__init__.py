@@ -144,6 +144,7 @@ def fill(dims, value):
 class math:  # noqa: N801
     erf = staticmethod(lambda x: _erf(_a(x)))
     log = staticmethod(lambda x: np.log(_a(x)))
+    sigmoid = staticmethod(lambda x: _w(1.0 / (1.0 + np.exp(-_a(x)))))
 
 
 class linalg:  # noqa: N801

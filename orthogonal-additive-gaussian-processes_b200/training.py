@@ -157,7 +157,7 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
     """(elbo, d/d lengthscales [num sub-kernels], d/d order variances [P+1], d/d noise)."""
     torch = _device._torch()
     Xd, Yd = model._device_data()
-    Xs = model._slice_for_kernel(Xd)
+    Xs = model._sliced_training_inputs(Xd)
     Zs = model._Z_device()
     noise = scalar_of(model.likelihood.variance)
     kern = model.kernel
@@ -295,7 +295,7 @@ def gpr_lml_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
     """(log marginal likelihood, d/d lengthscales, d/d order variances, d/d noise)."""
     torch = _device._torch()
     Xd, Yd = model._device_data()
-    Xs = model._slice_for_kernel(Xd)
+    Xs = model._sliced_training_inputs(Xd)
     noise = scalar_of(model.likelihood.variance)
     kern = model.kernel
     spec = kern._make_spec()

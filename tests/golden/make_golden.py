@@ -325,6 +325,50 @@ def main():
          sobol=np.asarray(sob), tuple_of_indices_json=np.array(json.dumps(jsonable(oak.tuple_of_indices))),
          restated_elbo=np.array(float(oak.m.elbo())))
 
+    # --- G11: the classification chain of examples/uci/uci_classification_train.py:108-160 -- the reference's own
+    # get_model_sufficient_statistics (SVGP branch, utils.py:174-179), compute_sobol_oak (:361) and
+    # get_prediction_component (:514) on a whitened, diagonal-q SVGP with the script's own inv_logit.  gpflow's
+    # SVGP / Bernoulli / posterior are the shim's restatement of gpflow 2.2.1 (flagged restated_*). -----------
+    import ast
+
+    script = open("/root/reference/examples/uci/uci_classification_train.py").read()
+    fn = next(n for n in ast.parse(script).body if isinstance(n, ast.FunctionDef) and n.name == "inv_logit")
+    import tensorflow as tf_shim  # noqa: E402  (the shim)
+
+    ns = {"tf": tf_shim}
+    exec(compile(ast.Module([fn], []), "uci_classification_train.py", "exec"), ns)   # the script's own definition
+    inv_logit = ns["inv_logit"]
+    n, m11 = 70, 16
+    Xc = np.column_stack([rng.standard_normal(n), rng.standard_normal(n) * 0.7 + 0.2, (rng.random(n) < 0.4).astype(float)])
+    Yc = (rng.random(n) < 1 / (1 + np.exp(-(1.5 * np.sin(Xc[:, 0]) + Xc[:, 1] * (Xc[:, 2] - 0.5))))).astype(float)[:, None]
+    k11 = OAKKernel([gpflow.kernels.RBF, gpflow.kernels.RBF, None], num_dims=3, max_interaction_depth=3,
+                    constrain_orthogonal=True, p0=[None, None, float(1 - Xc[:, 2].mean())], p=[None, None, None],
+                    lengthscale_bounds=[1e-3, 1e3])
+    k11.kernels[0].base_kernel.lengthscales.assign(0.9)
+    k11.kernels[1].base_kernel.lengthscales.assign(1.7)
+    for v, s_ in zip(k11.variances, [0.3, 1.2, 0.6, 0.2]):
+        v.assign(s_)
+    Z11 = Xc[rng.permutation(n)[:m11]].copy()
+    Z11[:, :2] += 0.05 * rng.standard_normal((m11, 2))
+    svgp = gpflow.models.SVGP(kernel=k11, likelihood=gpflow.likelihoods.Bernoulli(invlink=inv_logit),
+                              inducing_variable=Z11, whiten=True, q_diag=True)
+    svgp.q_mu.assign(0.8 * rng.standard_normal((m11, 1)))
+    svgp.q_sqrt.assign(rng.uniform(0.3, 0.9, (m11, 1)))
+    svgp.data = (Xc, Yc)                                  # as the script does before the Sobol step (:145)
+    Xt11 = Xc[:15] + np.array([0.2, -0.1, 0.0])
+    alpha11, L11 = ref_utils.get_model_sufficient_statistics(svgp, get_L=True)
+    idx11, sobol11 = ref_utils.compute_sobol_oak(svgp, 1.0, 0.0)
+    comps11 = ref_utils.get_prediction_component(svgp, np.asarray(alpha11), Xt11)
+    fm, fv = svgp.predict_f(Xt11)
+    save("g11_svgp_classification", cfg_from_kernel(k11), X=Xc, Y=Yc, Z=Z11, X_test=Xt11,
+         q_mu=svgp.q_mu.numpy(), q_sqrt=svgp.q_sqrt.numpy(), alpha=np.asarray(alpha11), L=np.asarray(L11),
+         sobol=np.asarray(sobol11, dtype=np.float64), sobol_index_json=np.array(json.dumps(jsonable(idx11))),
+         components=np.stack([np.asarray(c) for c in comps11]),
+         restated_elbo=np.array(svgp.elbo((Xc, Yc))), restated_predict_mean=np.asarray(fm),
+         restated_predict_var=np.asarray(fv),
+         restated_predict_log_density=np.asarray(svgp.predict_log_density((Xt11, Yc[:15]))),
+         inv_logit_of_grid=np.asarray(inv_logit(np.linspace(-6, 6, 25))))
+
 
 if __name__ == "__main__":
     main()

@@ -138,3 +138,41 @@ def test_oak_model_pipeline_matches_the_references_model_utils():
     for i in (2, 3):
         assert abs(float(k.kernels[i].base_kernel.lengthscales.numpy()) - cfg["dims"][i]["lengthscale"]) < 1e-14
         assert (k.kernels[i].measure.mu, k.kernels[i].measure.var) == (0.0, 1.0)
+
+
+def test_oracle_svgp_chain_matches_the_references_classification_path():
+    """g11: the reference's get_model_sufficient_statistics (SVGP branch), compute_sobol_oak and
+    get_prediction_component on a whitened diagonal-q SVGP; the torch oracle that checks the CUDA gradients is
+    held to the same vectors."""
+    import torch
+
+    from oracle import oak_grad_oracle as go
+
+    cfg, g = load_golden("g11_svgp_classification")
+    ref = build_oracle(cfg, expanded=True)
+    X, Y, Z, Xt, q_mu, q_sqrt = g["X"], g["Y"], g["Z"], g["X_test"], g["q_mu"], g["q_sqrt"]
+    assert max_rel_err(oo.inv_logit(np.linspace(-6, 6, 25)), g["inv_logit_of_grid"]) < TIGHT
+    assert max_rel_err(oo.svgp_alpha(ref, Z, q_mu), g["alpha"]) < 1e-10
+    assert max_rel_err(oo.svgp_L(ref, Z, q_sqrt), g["L"]) < 1e-8
+    idx, sob = oo.sobol_oak(ref, Z, g["alpha"])
+    assert idx == json.loads(str(g["sobol_index_json"]))
+    assert max_rel_err(sob, g["sobol"]) < 1e-10
+    assert max_rel_err(np.array(oo.predict_components(ref, Z, g["alpha"], Xt)), g["components"]) < 1e-10
+    fm, fv = oo.svgp_predict_f(ref, Z, q_mu, q_sqrt, Xt)
+    assert max_rel_err(fm, g["restated_predict_mean"][:, 0]) < 1e-10
+    assert max_rel_err(fv, g["restated_predict_var"][:, 0]) < 1e-10
+    assert abs(oo.svgp_elbo(ref, X, Y, Z, q_mu, q_sqrt) - float(g["restated_elbo"])) < 1e-10 * abs(float(g["restated_elbo"]))
+    assert max_rel_err(oo.svgp_predict_log_density(ref, Z, q_mu, q_sqrt, Xt, Y[:15]), g["restated_predict_log_density"]) < 1e-10
+    # constant term + components = latent mean (uci_classification_train.py:171-184)
+    const = g["alpha"].sum() * cfg["variances"][0]
+    assert max_rel_err(const + g["components"].sum(0), g["restated_predict_mean"][:, 0]) < 1e-9
+    # the torch oracle (continuous dims only) on the two continuous columns of the same case
+    cfg2 = dict(cfg)
+    cfg2["dims"] = cfg["dims"][:2]
+    ref2 = build_oracle(cfg2, expanded=False)
+    t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    ls = [d["lengthscale"] for d in cfg2["dims"]]
+    a_t = go.svgp_alpha(t(Z[:, :2]), t(ls), t(cfg["variances"]), t(q_mu)).numpy()
+    assert max_rel_err(a_t, oo.svgp_alpha(ref2, Z[:, :2], q_mu)) < 1e-9
+    e_t = float(go.svgp_elbo(t(X[:, :2]), t(Y), t(Z[:, :2]), t(ls), t(cfg["variances"]), t(q_mu)[:, 0], t(q_sqrt)[:, 0]))
+    assert abs(e_t - oo.svgp_elbo(ref2, X[:, :2], Y, Z[:, :2], q_mu, q_sqrt)) < 1e-9 * abs(e_t)

@@ -135,3 +135,34 @@ def test_cuda_oak_model_pipeline_matches_the_references_model_utils():
     sob = oak.get_sobol()
     assert json.loads(str(g["tuple_of_indices_json"])) == [[int(i) for i in t] for t in oak.tuple_of_indices]
     assert max_rel_err(sob, g["sobol"]) < 1e-7
+
+
+def test_cuda_svgp_classification_chain_matches_the_references_golden():
+    """g11: the SVGP model of examples/uci/uci_classification_train.py:108-160 -- the reference's own
+    get_model_sufficient_statistics (SVGP branch), compute_sobol_oak and get_prediction_component -- against
+    ``models.SVGP`` on the device."""
+    from oak_b200._gpflow_shim import Bernoulli, inv_logit
+    from oak_b200.models import SVGP
+    from oak_b200.utils import compute_sobol_oak, get_model_sufficient_statistics, get_prediction_component
+    from oak_b200.workloads import build_kernel
+
+    cfg, g = load_golden("g11_svgp_classification")
+    X, Y, Z, Xt = g["X"], g["Y"], g["Z"], g["X_test"]
+    assert max_rel_err(inv_logit(np.linspace(-6, 6, 25)), g["inv_logit_of_grid"]) < 1e-15
+    m = SVGP(kernel=build_kernel(cfg), likelihood=Bernoulli(invlink=inv_logit), inducing_variable=Z, whiten=True,
+             q_diag=True, q_mu=g["q_mu"], q_sqrt=g["q_sqrt"])
+    m.data = (X, Y)                          # as the script does before the Sobol step (:145)
+    alpha, L = get_model_sufficient_statistics(m, get_L=True)
+    assert max_rel_err(alpha, g["alpha"]) < RTOL
+    assert max_rel_err(L, g["L"]) < 1e-7    # chol(inv(Qinv)): two inversions on top of cond(Kuu)
+    idx, sob = compute_sobol_oak(m, 1.0, 0.0)
+    assert idx == json.loads(str(g["sobol_index_json"]))
+    assert max_rel_err(sob, g["sobol"]) < RTOL
+    comps = get_prediction_component(m, g["alpha"], Xt)
+    assert max_rel_err(np.array(comps), g["components"]) < RTOL
+    elbo = m.elbo((X, Y))
+    assert abs(elbo - float(g["restated_elbo"])) < RTOL * abs(float(g["restated_elbo"]))
+    mean, var = m.predict_f(Xt)
+    assert max_rel_err(mean, g["restated_predict_mean"]) < RTOL
+    assert max_rel_err(var, g["restated_predict_var"]) < RTOL
+    assert max_rel_err(m.predict_log_density((Xt, Y[:15])), g["restated_predict_log_density"]) < RTOL
