@@ -559,8 +559,8 @@ def main():
             "ms_stats_phase": ms_stats, "ms_tail_and_collective": ms_elbo - ms_stats, "elbo": vals[-1],
             "ms_factor_front": ms_factor, "ms_finish_tail": ms_finish, "ms_allreduce": ms_allreduce,
             "ms_factor_and_stats_overlapped": ms_fused,
-            "overlap_note": "oak_sgpr_factor_stats_f64: chol(Kuu) + condition estimate run on a side stream on 6 CTAs "
-                            "while the first chunk's Kuf tiles leave them 6 of the 148 SMs; ms_stats_phase and "
+            "overlap_note": "oak_sgpr_factor_stats_f64: chol(Kuu) + condition estimate run on a side stream on 4-8 CTAs "
+                            "while the first chunk's Kuf tiles leave them as many of the 148 SMs; ms_stats_phase and "
                             "ms_factor_front are the two pieces timed serially on their own",
             "route": model.last_route, "cond_estimate_kuu": model.last_cond_estimate,
             "ms_stats_phase_whitened_route": ms_stats_w,

@@ -263,7 +263,7 @@ int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, 
  * chunk's Kuf tiles (oak/utils.py:184 -- they need neither) keep the other SMs busy; `stream` joins the side
  * stream before the first kernel that reads the flag, so on return everything is ordered on `stream`.
  * overlap_ctas: 0 = serial (exactly the two calls above), > 0 = that many CTAs for the factorisation,
- * < 0 = automatic (6 when the first chunk is long enough to cover it, else serial; OAK_SGPR_OVERLAP overrides).
+ * < 0 = automatic (4 or 8 when the first chunk is long enough to cover it, else serial; OAK_SGPR_OVERLAP overrides).
  * Results are bit-identical for every value of overlap_ctas. */
 int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, int route,
                               double cond_threshold, double* d_fac, const void* d_pointsX, const double* d_y,

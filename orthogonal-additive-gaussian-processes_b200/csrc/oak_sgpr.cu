@@ -886,8 +886,8 @@ extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, 
 // (1024 dependent pivots: 0.57 ms on a whole GPU it cannot fill), the tiles are throughput bound, so lending the
 // factorisation 8 of 148 SMs costs the tiles 5 % of ONE chunk instead of 0.57 ms on the critical path of every
 // evaluation -- which is replicated on every rank (it is what held the 8-GPU ELBO below linear scaling).
-// overlap_ctas: 0 = serial (exactly the two calls), > 0 = that many CTAs, < 0 = automatic (6 when the first chunk
-// is long enough to cover the slower factorisation, else serial).  On return all work is ordered on `stream`.
+// overlap_ctas: 0 = serial (exactly the two calls), > 0 = that many CTAs, < 0 = automatic (4 or 8 when the first
+// chunk is long enough to cover the slower factorisation, else serial).  On return all work is ordered on `stream`.
 extern "C" int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter,
                                          int route, double cond_threshold, double* d_fac, const void* d_pointsX,
                                          const double* d_y, int64_t n_local, int64_t chunk, double* d_stats,
@@ -901,7 +901,9 @@ extern "C" int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_poi
     // the factorisation on 8 CTAs takes ~3x its whole-GPU time; the tiles of the first chunk must outlast it:
     // m * nc Gram entries at ~5e10 entries/s against ~1.6 us * m (1.6 ms at M = 1024)
     const int64_t nc = n_local < chunk ? n_local : chunk;
-    overlap_ctas = env_overlap >= 0 ? env_overlap : (nc >= 100000 && m >= 256 ? 6 : 0);
+    // measured at M = 1024 (profiles/r02r_*): the factorisation takes ~2.0 / 2.7 / 3.9 ms on 8 / 6 / 4 CTAs, the first
+    // chunk's tiles 2.5 ms per 125 000 points -- 8 CTAs leave a margin on short chunks, 4 are enough on long ones
+    overlap_ctas = env_overlap >= 0 ? env_overlap : (m < 256 || nc < 100000 ? 0 : (nc >= 250000 ? 4 : 8));
   }
   if (overlap_ctas == 0 || n_local <= 0) {
     if (int rc = oak_sgpr_factor_f64(spec, d_pointsZ, m, jitter, route, cond_threshold, d_fac, stream_)) return rc;

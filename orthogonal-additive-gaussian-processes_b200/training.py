@@ -182,7 +182,7 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         n_total = n_local
         if model.distributed:
             parallel.allreduce_sum_(stats)
-            n_total = parallel.allreduce_int(n_total)
+            n_total = parallel.global_count(n_total, id(model))
         Kuu = _device.gram(spec, pz)
         # statistics: Phi arrives as column-major lower == upper triangle of the row-major view
         U = torch.triu(stats[: m * m].view(m, m))
@@ -354,7 +354,8 @@ def svgp_elbo_and_grad(model, data, want_grad: bool = True):
             raise ValueError("one label per input row")
         # N axis sharded over ranks (like the SGPR statistics): the minibatch scale refers to the global batch
         sharded = bool(getattr(model, "distributed", False))
-        n_global = parallel.allreduce_int(n) if sharded else n
+        # (exchanged only when the minibatch scale needs it: the batch is an argument here, not model state)
+        n_global = parallel.allreduce_int(n) if (sharded and model.num_data is not None) else n
         scale = 1.0 if model.num_data is None else float(model.num_data) / n_global
         dev = Xs.device
         q_mu = _device.to_device(model.q_mu.numpy(), ndim=1).reshape(-1)
