@@ -258,10 +258,11 @@ int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, int64_t m, 
                         const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
                         double* d_stats, void* d_work, double* d_kuf_store, void* stream);
 /* oak_sgpr_factor_f64 followed by oak_sgpr_stats2_f64 as one call that takes the factorisation off the
- * critical path (it is replicated on every rank): the Kuu tiles run on `stream`, then [L ; L^-T], the
- * condition estimate and the route flag run on an internal side stream on `overlap_ctas` CTAs while the first
- * chunk's Kuf tiles (oak/utils.py:184 -- they need neither) keep the other SMs busy; `stream` joins the side
- * stream before the first kernel that reads the flag, so on return everything is ordered on `stream`.
+ * critical path (it is replicated on every rank): the first chunk's Kuf tiles (oak/utils.py:184 -- they need
+ * neither L nor the route) are launched first on `stream` and leave `overlap_ctas` SMs free; the Kuu tiles,
+ * [L ; L^-T], the condition estimate and the route flag run on an internal side stream capped at that many
+ * CTAs; `stream` joins the side stream before the first kernel that reads the flag, so on return everything
+ * is ordered on `stream`.
  * overlap_ctas: 0 = serial (exactly the two calls above), > 0 = that many CTAs for the factorisation,
  * < 0 = automatic (4 or 8 when the first chunk is long enough to cover it, else serial; OAK_SGPR_OVERLAP overrides).
  * Results are bit-identical for every value of overlap_ctas. */

@@ -116,7 +116,8 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
                 int64_t row_end, const double2* pcol, int64_t n_col_pad, int64_t col_begin,
                 int64_t col_end, int mode, double* K, int64_t ldk, cudaStream_t stream, double* Kt = nullptr,
                 int64_t ldkt = 0, const double* ydot_y = nullptr, double* ydot_part = nullptr, int sm_reserve = 0);
-// sm_reserve: the persistent grid leaves that many SMs free (for a small kernel running next to the tiles)
+// sm_reserve > 0: the persistent grid leaves that many SMs free (for a small kernel running next to the tiles);
+// sm_reserve < 0: the grid is capped at -sm_reserve CTAs (this launch IS the small kernel)
 // the folded K y of the general-mode tiles (depth <= 4): ydot_part holds ceil(cols / 64) x rows partial sums
 inline bool gram_can_fold_ky(const oak_spec* spec) { return spec->depth <= 4; }
 // per-dimension min / max keys of the prepared coordinate: [D] min keys then [D] max keys

@@ -826,6 +826,7 @@ int gram_launch(const oak_spec* spec, const double2* prow, int64_t n_row_pad, in
   prm.num_tiles = 0;
   int sms = sm_count(spec->device);
   if (sm_reserve > 0) sms = sms - sm_reserve > 1 ? sms - sm_reserve : 1;
+  if (sm_reserve < 0 && -sm_reserve < sms) sms = -sm_reserve;  // cap: the kernel itself is the small one
   const int algo = spec->algo;
   switch (depth) {
     case 0:

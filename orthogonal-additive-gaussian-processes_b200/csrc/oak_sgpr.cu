@@ -13,6 +13,7 @@
 #include <cusolverDn.h>
 
 #include <cmath>
+#include <functional>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -689,13 +690,15 @@ extern "C" int64_t oak_sgpr_lb_ld(int64_t m) { return m < 1 ? 0 : lb_ld(m); }
 
 // Kuu(iv, kernel) (oak/utils.py:185) + jitter I with the identity border, column 1-norms, start vector
 static int factor_pre(const oak_spec* spec, const void* d_pointsZ, int64_t m, double jitter, double* d_fac,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, int max_ctas = 0) {
   const int64_t mp = fac_mp(m), ld = fac_ld(m);
   double* hdr = d_fac + ld * m;
   double* scratch = hdr + kHdrDoubles;  // colsum | wa | wb | wc
   const double2* pz = (const double2*)d_pointsZ;
   // row-major with pitch LD == column-major (symmetric)
-  if (int rc = gram_launch(spec, pz, padded(m), 0, m, pz, padded(m), 0, m, 1, d_fac, ld, stream)) return rc;
+  if (int rc = gram_launch(spec, pz, padded(m), 0, m, pz, padded(m), 0, m, 1, d_fac, ld, stream, nullptr, 0, nullptr,
+                           nullptr, max_ctas > 0 ? -max_ctas : 0))
+    return rc;
   fac_init_kernel<<<(unsigned)m, 256, 0, stream>>>(d_fac, (int)m, (int)mp, ld, jitter, scratch, scratch + mp);
   OAK_LAUNCHED();
   return 0;
@@ -786,7 +789,7 @@ extern "C" size_t oak_sgpr_stats2_work_bytes(int64_t m, int64_t chunk) {
 static int sgpr_stats2_impl(const oak_spec* spec, const void* d_pointsZ, int64_t m, double* d_fac,
                             const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
                             double* d_stats, void* d_work, double* d_kuf_store, void* stream_, int sm_reserve,
-                            cudaEvent_t route_ready) {
+                            cudaEvent_t route_ready, const std::function<int()>& after_first_tiles) {
   OAK_REQUIRE(spec && d_pointsZ && d_fac && d_stats && d_work, "oak_sgpr_stats2_f64: null argument");
   OAK_REQUIRE(m >= 1, "oak_sgpr_stats2_f64: need at least one inducing point");
   OAK_REQUIRE(n_local >= 0, "oak_sgpr_stats2_f64: negative n");
@@ -826,6 +829,11 @@ static int sgpr_stats2_impl(const oak_spec* spec, const void* d_pointsZ, int64_t
     if (int rc = gram_launch(spec, pz, m_pad, 0, m, px, n_pad, c0, c0 + nc, 0, kuf, chunk, stream, nullptr, 0,
                              fold ? d_y + c0 : nullptr, fold ? ypart : nullptr, c0 == 0 ? sm_reserve : 0))
       return rc;
+    if (c0 == 0 && after_first_tiles) {
+      // the heavy kernel is in flight: now enqueue the side stream's work (which records route_ready) ...
+      if (int rc = after_first_tiles()) return rc;
+    }
+    // ... and wait for it before the first kernel that reads the route flag
     if (c0 == 0 && route_ready) OAK_CUDA(cudaStreamWaitEvent(stream, route_ready, 0));
     // route 1: A_r = L^-1 Kuf_r (utils.py:189), a no-op launch otherwise
     if (int rc = panel_gemm_dmma(d_fac + mp, ld, kuf, chunk, abuf, chunk, (int)m, (int)m, nc, 1, nullptr, nullptr,
@@ -876,15 +884,15 @@ extern "C" int oak_sgpr_stats2_f64(const oak_spec* spec, const void* d_pointsZ, 
                                    const void* d_pointsX, const double* d_y, int64_t n_local, int64_t chunk,
                                    double* d_stats, void* d_work, double* d_kuf_store, void* stream_) {
   return sgpr_stats2_impl(spec, d_pointsZ, m, d_fac, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store,
-                          stream_, 0, nullptr);
+                          stream_, 0, nullptr, nullptr);
 }
 
-// oak_sgpr_factor_f64 + oak_sgpr_stats2_f64 as ONE call that hides the factorisation: the Kuu tiles run first on
-// `stream`; [L ; L^-T], the condition estimate and the route flag then run on an internal side stream on
-// `overlap_ctas` CTAs while the first chunk's Kuf tiles -- which need neither -- occupy the other SMs, and `stream`
-// joins the side stream before the first kernel that reads the flag.  The bordered Cholesky is latency bound
-// (1024 dependent pivots: 0.57 ms on a whole GPU it cannot fill), the tiles are throughput bound, so lending the
-// factorisation 8 of 148 SMs costs the tiles 5 % of ONE chunk instead of 0.57 ms on the critical path of every
+// oak_sgpr_factor_f64 + oak_sgpr_stats2_f64 as ONE call that hides the factorisation: the first chunk's Kuf tiles --
+// which need neither L nor the route flag -- are launched first and leave `overlap_ctas` SMs free; the Kuu tiles,
+// [L ; L^-T], the condition estimate and the route flag run on an internal side stream capped at that many CTAs, and
+// `stream` joins the side stream before the first kernel that reads the flag.  The bordered Cholesky is latency bound
+// (1024 dependent pivots: 0.4 ms on a whole GPU it cannot fill), the tiles are throughput bound, so lending the
+// factorisation 8 of 148 SMs costs the tiles 5 % of ONE chunk instead of 0.5 ms on the critical path of every
 // evaluation -- which is replicated on every rank (it is what held the 8-GPU ELBO below linear scaling).
 // overlap_ctas: 0 = serial (exactly the two calls), > 0 = that many CTAs, < 0 = automatic (4 or 8 when the first
 // chunk is long enough to cover the slower factorisation, else serial).  On return all work is ordered on `stream`.
@@ -908,17 +916,23 @@ extern "C" int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_poi
   if (overlap_ctas == 0 || n_local <= 0) {
     if (int rc = oak_sgpr_factor_f64(spec, d_pointsZ, m, jitter, route, cond_threshold, d_fac, stream_)) return rc;
     return sgpr_stats2_impl(spec, d_pointsZ, m, d_fac, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store,
-                            stream_, 0, nullptr);
+                            stream_, 0, nullptr, nullptr);
   }
   SideLane* lane = nullptr;
   if (int rc = side_lane(&lane)) return rc;
-  if (int rc = factor_pre(spec, d_pointsZ, m, jitter, d_fac, stream)) return rc;
+  // the side stream starts from the prepared points (everything enqueued on `stream` so far) ...
   OAK_CUDA(cudaEventRecord(lane->fork, stream));
   OAK_CUDA(cudaStreamWaitEvent(lane->stream, lane->fork, 0));
-  if (int rc = factor_chol(spec, m, route, cond_threshold, d_fac, lane->cublas, lane->stream, overlap_ctas)) return rc;
-  OAK_CUDA(cudaEventRecord(lane->join, lane->stream));
+  // ... but its kernels are enqueued AFTER the first chunk's tiles, so that the GPU starts on the heavy kernel at once
+  // and the Kuu tiles, the factorisation and the estimate (all capped at overlap_ctas CTAs) fill the SMs it leaves
+  auto side_work = [&]() -> int {
+    if (int rc = factor_pre(spec, d_pointsZ, m, jitter, d_fac, lane->stream, overlap_ctas)) return rc;
+    if (int rc = factor_chol(spec, m, route, cond_threshold, d_fac, lane->cublas, lane->stream, overlap_ctas)) return rc;
+    OAK_CUDA(cudaEventRecord(lane->join, lane->stream));
+    return 0;
+  };
   return sgpr_stats2_impl(spec, d_pointsZ, m, d_fac, d_pointsX, d_y, n_local, chunk, d_stats, d_work, d_kuf_store,
-                          stream_, overlap_ctas, lane->join);
+                          stream_, overlap_ctas, lane->join, side_work);
 }
 
 extern "C" size_t oak_sgpr_finish2_work_bytes(int64_t m) {
