@@ -141,6 +141,15 @@ def fill(dims, value):
     return np.full(dims, value)
 
 
+def custom_gradient(f):
+    """Forward value only (no autodiff in the shim)."""
+    return lambda *a, **k: f(*a, **k)[0]
+
+
+def numpy_function(func, inp, Tout, name=None):
+    return func(*[np.asarray(i) for i in inp])
+
+
 class math:  # noqa: N801
     erf = staticmethod(lambda x: _erf(_a(x)))
     log = staticmethod(lambda x: np.log(_a(x)))

@@ -82,3 +82,44 @@ def test_header_is_plain_c():
     assert out.returncode == 0, out.stderr
     text = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "oak_b200.h")).read(), flags=re.S)
     assert "torch" not in text and "cudaStream_t" not in text and "at::" not in text  # outside the comments
+
+
+def _build_c_program(tmpdir):
+    """gcc -std=c99 tests/c/abi_link.c against include/oak_b200.h and the in-tree liboak_b200.so."""
+    import os
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if gcc is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "orthogonal-additive-gaussian-processes_b200")
+    exe = os.path.join(str(tmpdir), "abi_link")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(root, "include"),
+           "-I", os.path.join(cuda, "include"), os.path.join(root, "tests", "c", "abi_link.c"), "-o", exe,
+           "-L", pkg, "-loak_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + pkg, "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_c_program_links_the_abi(tmp_path):
+    """A C99 translation unit compiles against the header, links the shared library and runs its housekeeping entry
+    points (no device needed)."""
+    import subprocess
+
+    out = subprocess.run([_build_c_program(tmp_path), "--no-gpu"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "oak_version" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_computes_a_gram_through_the_abi(tmp_path):
+    """The same program end to end on the device: spec, prologue, Gram and K_diag against closed forms in C."""
+    import subprocess
+
+    out = subprocess.run([_build_c_program(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
