@@ -12,6 +12,60 @@ namespace oak {
 
 constexpr int kSmallEmpirical = 64;
 
+// One (point, sub-kernel) pair: the prepared coordinate / correction (RBF) or the table offsets (discrete).
+// lo / hi receive the prepared coordinate of an RBF dim (min / max keys), +-inf otherwise.
+__device__ __forceinline__ double2 prepare_one(const DimDev& d, double x, double inv_sqrt_v_k,
+                                               const double* __restrict__ tables, double& lo, double& hi) {
+  double2 out;
+  if (d.type == OAK_DIM_RBF) {
+    out.x = x * d.xscale;
+    lo = hi = out.x;
+    double c = 0.0;
+    switch (d.measure) {
+      case OAK_MEASURE_GAUSSIAN: {  // ortho_rbf_kernel.py:82-92
+        const double t = x - d.c1;
+        c = d.c0 * exp(-(t * t) * d.c2);
+        break;
+      }
+      case OAK_MEASURE_UNIFORM:  // ortho_rbf_kernel.py:49-63
+        c = d.c0 * (erf((d.c2 - x) * d.inv_sqrt2_l) - erf((d.c1 - x) * d.inv_sqrt2_l));
+        break;
+      case OAK_MEASURE_MOG: {  // ortho_rbf_kernel.py:124-136
+        const double l2 = d.lengthscale * d.lengthscale;
+        double acc = 0.0;
+        for (int q = 0; q < d.count; ++q) {
+          const double sc = l2 + d.v1[q];
+          const double t = x - d.v0[q];
+          acc += exp(-0.5 * (t * t) / sc) / sqrt(sc) * d.v2[q];
+        }
+        c = d.c0 * acc;
+        break;
+      }
+      case OAK_MEASURE_EMPIRICAL: {  // ortho_rbf_kernel.py:101-107
+        double acc = 0.0;
+        const int cnt = d.count <= kSmallEmpirical ? d.count : 0;  // large: tiled kernel below
+        for (int q = 0; q < cnt; ++q) {
+          const double t = (x - d.v0[q]) * d.inv_sqrt2_l;
+          acc = fma(d.v1[q], exp(-t * t), acc);
+        }
+        c = d.c0 * acc;
+        break;
+      }
+      default:
+        break;
+    }
+    out.y = c * inv_sqrt_v_k;
+  } else {
+    // tf.cast(x, int32): truncation toward zero (ortho_binary_kernel.py:47-51); clamped
+    // into the table (the host wrapper validates the range and raises).
+    int idx = (int)x;
+    idx = max(0, min(idx, d.count - 1));
+    out.x = __hiloint2double(idx * d.count, idx);
+    out.y = tables[d.table_off + d.count * d.count + idx];
+  }
+  return out;
+}
+
 __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
                                       const double* __restrict__ inv_sqrt_v,
                                       const double* __restrict__ tables,
@@ -24,53 +78,7 @@ __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
   double lo = INFINITY, hi = -INFINITY;
   if (i < n) {
     const DimDev d = dims[k];
-    const double x = X[i * ldx + d.column];
-    if (d.type == OAK_DIM_RBF) {
-      out.x = x * d.xscale;
-      lo = hi = out.x;
-      double c = 0.0;
-      switch (d.measure) {
-        case OAK_MEASURE_GAUSSIAN: {  // ortho_rbf_kernel.py:82-92
-          const double t = x - d.c1;
-          c = d.c0 * exp(-(t * t) * d.c2);
-          break;
-        }
-        case OAK_MEASURE_UNIFORM:  // ortho_rbf_kernel.py:49-63
-          c = d.c0 * (erf((d.c2 - x) * d.inv_sqrt2_l) - erf((d.c1 - x) * d.inv_sqrt2_l));
-          break;
-        case OAK_MEASURE_MOG: {  // ortho_rbf_kernel.py:124-136
-          const double l2 = d.lengthscale * d.lengthscale;
-          double acc = 0.0;
-          for (int q = 0; q < d.count; ++q) {
-            const double sc = l2 + d.v1[q];
-            const double t = x - d.v0[q];
-            acc += exp(-0.5 * (t * t) / sc) / sqrt(sc) * d.v2[q];
-          }
-          c = d.c0 * acc;
-          break;
-        }
-        case OAK_MEASURE_EMPIRICAL: {  // ortho_rbf_kernel.py:101-107
-          double acc = 0.0;
-          const int cnt = d.count <= kSmallEmpirical ? d.count : 0;  // large: tiled kernel below
-          for (int q = 0; q < cnt; ++q) {
-            const double t = (x - d.v0[q]) * d.inv_sqrt2_l;
-            acc = fma(d.v1[q], exp(-t * t), acc);
-          }
-          c = d.c0 * acc;
-          break;
-        }
-        default:
-          break;
-      }
-      out.y = c * inv_sqrt_v[k];
-    } else {
-      // tf.cast(x, int32): truncation toward zero (ortho_binary_kernel.py:47-51); clamped
-      // into the table (the host wrapper validates the range and raises).
-      int idx = (int)x;
-      idx = max(0, min(idx, d.count - 1));
-      out.x = __hiloint2double(idx * d.count, idx);
-      out.y = tables[d.table_off + d.count * d.count + idx];
-    }
+    out = prepare_one(d, X[i * ldx + d.column], inv_sqrt_v[k], tables, lo, hi);
   }
   if (i < n_pad) pts[(int64_t)k * n_pad + i] = out;
   // block-wide min / max of the prepared coordinate -> one atomic pair per block
@@ -89,6 +97,58 @@ __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
       lo = fmin(lo, s_lo[w]);
       hi = fmax(hi, s_hi[w]);
+    }
+    if (lo <= hi) {
+      atomicMin(minmax + k, order_key(lo));
+      atomicMax(minmax + D + k, order_key(hi));
+    }
+  }
+}
+
+// The same prologue for narrow inputs (ldx <= kRowTileMaxLd): one block takes kRowTile ROWS of X -- a contiguous
+// range of the row-major matrix, read once with coalesced loads into shared memory -- and walks all D sub-kernels.
+// The column-per-block kernel above reads a column with a stride of ldx doubles: 8 x the sectors, D times over
+// (0.41 ms for 10^6 x 20 inputs, against 0.48 GB of useful traffic).
+constexpr int kRowTile = 128;
+constexpr int kRowTileMaxLd = 40;  // 128 x 40 doubles = 40 KB of dynamic shared memory (+ 4 KB static: under the 48 KB default)
+constexpr int kRowTileMaxD = 64;
+
+__global__ void __launch_bounds__(kRowTile) prepare_points_rows_kernel(
+    const DimDev* __restrict__ dims, const double* __restrict__ inv_sqrt_v, const double* __restrict__ tables,
+    const double* __restrict__ X, int64_t n, int64_t n_pad, int ldx, double2* __restrict__ pts,
+    unsigned long long* __restrict__ minmax, int D) {
+  extern __shared__ double sx[];  // [kRowTile][ldx]
+  __shared__ double s_lo[kRowTile / 32][kRowTileMaxD], s_hi[kRowTile / 32][kRowTileMaxD];
+  const int64_t i0 = (int64_t)blockIdx.x * kRowTile;
+  const int rows = (int)min((int64_t)kRowTile, n - i0);  // may be <= 0 for pure padding blocks
+  const int64_t base = i0 * ldx;
+  for (int e = threadIdx.x; e < rows * ldx; e += kRowTile) sx[e] = X[base + e];
+  __syncthreads();
+  const int t = threadIdx.x;
+  const int64_t i = i0 + t;
+  for (int k = 0; k < D; ++k) {
+    double2 out = make_double2(0.0, 0.0);
+    double lo = INFINITY, hi = -INFINITY;
+    if (t < rows) {
+      const DimDev d = dims[k];
+      out = prepare_one(d, sx[t * ldx + d.column], inv_sqrt_v[k], tables, lo, hi);
+    }
+    if (i < n_pad) pts[(int64_t)k * n_pad + i] = out;
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((t & 31) == 0) {
+      s_lo[t >> 5][k] = lo;
+      s_hi[t >> 5][k] = hi;
+    }
+  }
+  __syncthreads();
+  for (int k = t; k < D; k += kRowTile) {
+    double lo = s_lo[0][k], hi = s_hi[0][k];
+    for (int w = 1; w < kRowTile / 32; ++w) {
+      lo = fmin(lo, s_lo[w][k]);
+      hi = fmax(hi, s_hi[w][k]);
     }
     if (lo <= hi) {
       atomicMin(minmax + k, order_key(lo));
@@ -221,10 +281,14 @@ extern "C" int oak_prepare_points_f64(const oak_spec* spec, const double* d_X, i
   if (n == 0) return 0;
   OAK_REQUIRE(d_X, "oak_prepare_points_f64: null X");
   const int threads = 256;
-  dim3 grid((unsigned)((n_pad + threads - 1) / threads), (unsigned)D);
-  prepare_points_kernel<<<grid, threads, 0, stream>>>(spec->d_dims, spec->d_inv_sqrt_v,
-                                                      spec->d_tables, d_X, n, n_pad, ldx,
-                                                      (double2*)d_points, minmax, D);
+  if (ldx <= kRowTileMaxLd && D <= kRowTileMaxD) {
+    prepare_points_rows_kernel<<<(unsigned)(n_pad / kRowTile), kRowTile, (size_t)kRowTile * ldx * sizeof(double), stream>>>(
+        spec->d_dims, spec->d_inv_sqrt_v, spec->d_tables, d_X, n, n_pad, (int)ldx, (double2*)d_points, minmax, D);
+  } else {
+    dim3 grid((unsigned)((n_pad + threads - 1) / threads), (unsigned)D);
+    prepare_points_kernel<<<grid, threads, 0, stream>>>(spec->d_dims, spec->d_inv_sqrt_v, spec->d_tables, d_X, n, n_pad,
+                                                        ldx, (double2*)d_points, minmax, D);
+  }
   OAK_LAUNCHED();
   // large empirical measures: overwrite with the tiled kernel
   for (int k = 0; k < spec->Dc; ++k) {
