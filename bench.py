@@ -336,6 +336,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def by_rank(v):
+        """The per-rank values of a timing (diagnostic: which rank is the straggler of a max-over-ranks number)."""
+        if world == 1:
+            return [v]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = v
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [round(float(x), 4) for x in t.tolist()]
+
     # ---- measured FP64 peak (roofline denominator) -------------------------------------------
     peak_slots = _device.measure_fp64_peak(1.0)
     peak_tflops = 2 * peak_slots / 1e12
@@ -522,7 +531,8 @@ def main():
         vals = [model.elbo() for _ in range(k_e)]
         b2.record()
         torch.cuda.synchronize()
-        ms_elbo = max_over_ranks(a.elapsed_time(b2) / k_e)
+        ms_elbo_rank = by_rank(a.elapsed_time(b2) / k_e)
+        ms_elbo = max(ms_elbo_rank)
         # phases on their own: statistics (tiles + DMMA contraction), the factor-first front, the tail
         sp = kc._make_spec()
         Xs, Ys = model._device_data()
@@ -558,7 +568,7 @@ def main():
             "metric": "SGPR ELBO evals/sec", "value": 1e3 / ms_elbo, "unit": "evals/s", "ms_per_eval": ms_elbo,
             "ms_stats_phase": ms_stats, "ms_tail_and_collective": ms_elbo - ms_stats, "elbo": vals[-1],
             "ms_factor_front": ms_factor, "ms_finish_tail": ms_finish, "ms_allreduce": ms_allreduce,
-            "ms_factor_and_stats_overlapped": ms_fused,
+            "ms_factor_and_stats_overlapped": ms_fused, "ms_per_eval_by_rank": ms_elbo_rank,
             "overlap_note": "oak_sgpr_factor_stats_f64: chol(Kuu) + condition estimate run on a side stream on 4-8 CTAs "
                             "while the first chunk's Kuf tiles leave them as many of the 148 SMs; ms_stats_phase and "
                             "ms_factor_front are the two pieces timed serially on their own",
