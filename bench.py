@@ -704,6 +704,21 @@ def main():
             ms, _ = timed(lambda: _device.flow_objective(xcol, 0.5, True, [0.1, -0.5, 0.05, 0.0]), reps=5)
             widening["flow_objective_pass_n4000000"] = {"ms": ms, "points_per_s": 4e6 / (ms * 1e-3)}
             del xcol, dataw
+            # k-means inducing points at config C's scale: scikit-learn's algorithm on the device (kmeans.KMeans)
+            from oak_b200.kmeans import KMeans
+
+            Xk = _device.to_device(rng_w.standard_normal((1_000_000, 20)) + 2.0 * rng_w.standard_normal((64, 20))[
+                rng_w.integers(0, 64, 1_000_000)])
+            tk = {}
+            for iters in (1, 11):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                KMeans(n_clusters=1024, random_state=0, max_iter=iters).fit(Xk)
+                torch.cuda.synchronize()
+                tk[iters] = time.perf_counter() - t0
+            widening["kmeans_n1000000_d20_k1024"] = {"kmeanspp_seeding_plus_one_iteration_s": tk[1],
+                                                     "ms_per_lloyd_iteration": (tk[11] - tk[1]) * 100.0}
+            del Xk
         except Exception as exc:
             widening = {"error": repr(exc)}
 

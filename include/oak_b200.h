@@ -281,6 +281,32 @@ size_t oak_sgpr_finish2_work_bytes(int64_t m);
 int oak_sgpr_finish2_f64(double* d_fac, double* d_stats, int64_t m, int64_t n_total, double noise,
                          double* d_out, double* d_alpha, double* d_LB, void* d_work, void* stream);
 
+/* ---- k-means for the inducing-point initialisation (csrc/oak_kmeans.cu) -----------------------
+ * Replaces the scikit-learn KMeans(n_clusters, random_state=0).fit(X).cluster_centers_ calls of
+ * oak/model_utils.py:31-41, 376-383 and oak/utils.py:549-552, 570-573 on the continuous columns: the same
+ * algorithm (centring, k-means++ with 2 + log k local trials, Lloyd with first-index ties, centres = sums / counts,
+ * strict / tolerance stopping rule); the random numbers are drawn on the host from numpy's RandomState exactly as
+ * scikit-learn draws them, everything O(N) runs here.  All reductions have a fixed order (deterministic). */
+size_t oak_kmeans_work_bytes(int64_t n, int64_t d, int64_t k, int64_t trials);
+/* d_Xc (n x d, contiguous) = X - column means; d_stats[0..d) = the means, d_stats[d] = mean of the column variances
+ * (sklearn's tolerance scale, _kmeans.py:_tolerance). */
+int oak_kmeans_center_f64(const double* d_X, int64_t n, int64_t d, int64_t ldx, double* d_Xc, double* d_stats,
+                          void* d_work, void* stream);
+/* One k-means++ round (_kmeans.py:_kmeans_plusplus): candidates d_cand[t] = searchsorted(cumsum(d_closest),
+ * d_thresholds[t]) clipped to n - 1 (d_thresholds == NULL: d_cand is given), d_dist[t*n + i] = min(d_closest[i],
+ * |x_i - x_cand[t]|^2) (d_closest == NULL: no min), d_pots[t] = sum_i d_dist[t*n + i].  d_cum: n doubles. */
+int oak_kmeanspp_round_f64(const double* d_Xc, int64_t n, int64_t d, const double* d_closest,
+                           const double* d_thresholds, int64_t trials, int64_t* d_cand, double* d_cum, double* d_dist,
+                           double* d_pots, void* d_work, void* stream);
+/* One Lloyd iteration (_k_means_lloyd.pyx lloyd_iter_chunked_dense, _k_means_common.pyx _average_centers /
+ * _center_shift).  d_labels (int32): previous labels in, new labels out.  d_out: 4 x 8 bytes: [0] double, sum of the
+ * squared centre shifts; [2] uint64, number of empty clusters (their rows of d_centers_new keep the old centre);
+ * [3] uint64, number of labels that changed.  update_centers == 0: labels only.  d <= 64 runs the register-tiled
+ * assignment, wider inputs a plain one. */
+int oak_kmeans_lloyd_f64(const double* d_Xc, int64_t n, int64_t d, const double* d_centers, int64_t k,
+                         int32_t* d_labels, double* d_centers_new, double* d_sums, double* d_counts, double* d_out,
+                         int update_centers, void* d_work, void* stream);
+
 /* ---- dense building blocks of the tails (csrc/oak_chol.cu, csrc/oak_pgemm.cu) ---------------- */
 /* Cholesky factorisation with border rows in one cooperative launch, replacing the tf.linalg.cholesky +
  * tf.linalg.triangular_solve pairs of oak/utils.py:188-195.  d_A: column-major, leading dimension ld

@@ -375,12 +375,16 @@ def flow_objective(x, offset: float, use_log: bool, theta, work=None):
 
 
 def cuda_available() -> bool:
+    """True on a machine with a CUDA device.  On such a machine a missing or broken ``liboak_b200.so`` is an ERROR
+    (``_cabi.load`` raises): the host-side preprocessing must never drift onto a CPU path on a GPU box."""
     try:
         import torch
 
-        return torch.cuda.is_available() and _cabi.load().oak_device_count() > 0
-    except Exception:
+        if not torch.cuda.is_available():
+            return False
+    except ImportError:
         return False
+    return _cabi.load().oak_device_count() > 0
 
 
 def column_unique(Xd, col: int):

@@ -24,11 +24,12 @@ from .utils import compute_sobol_oak
 
 
 def get_kmeans_centers(X: np.ndarray, K: int = 500) -> np.ndarray:
-    """K-means centres used as inducing points (model_utils.py:31-41); host preprocessing (sklearn)."""
-    from sklearn.cluster import KMeans
+    """K-means centres used as inducing points (model_utils.py:31-41): scikit-learn's algorithm on the device
+    (``kmeans.KMeans``)."""
+    from .kmeans import kmeans_class
 
     np.random.seed(44)
-    return KMeans(n_clusters=K, random_state=0).fit(X).cluster_centers_
+    return kmeans_class()(n_clusters=K, random_state=0).fit(X).cluster_centers_
 
 
 def save_model(model, filename) -> None:
@@ -354,12 +355,11 @@ class oak_model:
         )
 
     def _kmeans_inducing(self, Xs, p0, p):
-        """k-means inducing points (:377-391, utils.py:555-574): one-off host preprocessing."""
-        try:
-            from sklearn.cluster import KMeans
-        except Exception as exc:  # pragma: no cover
-            raise NotImplementedError("k-means initialisation needs scikit-learn; pass "
-                                      "initialise_inducing_points=False") from exc
+        """k-means inducing points (:377-391, utils.py:555-574): the continuous block on the device
+        (``kmeans.KMeans``: scikit-learn's algorithm and random stream), discrete columns as the reference."""
+        from .kmeans import kmeans_class
+
+        KMeans = kmeans_class()
         if (p0 is None) and (p is None):
             return KMeans(n_clusters=self.num_inducing, random_state=0).fit(Xs).cluster_centers_
         from .utils import initialize_kmeans_with_categorical

@@ -98,16 +98,24 @@ def f4(x, y, sigma, lengthscales, delta, mu):
     return _sobol_term(3, x, y, sigma, lengthscales, delta, mu)
 
 
-# ---- k-means inducing points with discrete columns (utils.py:533-574): sklearn on the host, as the reference ----
+# ---- k-means inducing points with discrete columns (utils.py:533-574) ---------------------------------------------
 def initialize_kmeans_with_binary(X, binary_index: list, continuous_index: Optional[list] = None,
                                   n_clusters: Optional[int] = 200) -> np.ndarray:
-    """One k-means per binary column (centres truncated to integers) and one over the continuous block."""
-    from sklearn.cluster import KMeans
+    """One k-means per binary column (centres truncated to integers) and one over the continuous block.
 
+    The continuous block -- the O(N k d) part -- runs on the device (``kmeans.KMeans``: scikit-learn's algorithm and
+    random stream).  The one-column k-means of a DISCRETE feature asks for more clusters than the column has distinct
+    values; what comes out of scikit-learn there is decided by its handling of duplicate points and empty clusters on
+    rounding-level distances, so that call stays the library's (N x 1, negligible)."""
+    from sklearn.cluster import KMeans as SklearnKMeans
+
+    from .kmeans import kmeans_class
+
+    KMeans = kmeans_class()
     X = np.asarray(X, dtype=np.float64)
     Z = np.zeros([n_clusters, X.shape[1]])
     for index in binary_index:
-        km = KMeans(n_clusters=n_clusters, random_state=0).fit(X[:, index][:, None])
+        km = SklearnKMeans(n_clusters=n_clusters, random_state=0).fit(X[:, index][:, None])
         Z[:, index] = km.cluster_centers_.astype(int)[:, 0]
     if continuous_index is not None:
         km = KMeans(n_clusters=n_clusters, random_state=0).fit(X[:, continuous_index])
