@@ -17,9 +17,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "== ncu dram bytes at the bench size (one pass)"
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__inst_executed_pipe_fp64.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg \
     --clock-control none -k regex:gram_kernel -s 2 -c 1 --csv --log-file $OUT/gram_dram_n65536.csv \
-    python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-elbo > /dev/null 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-elbo --no-sweep > /dev/null 2>&1
 echo "== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_kernel -s 2 -c 1 -o $OUT/gram_full_n32768 -f \
-    python bench.py --n 32768 --steps 1 --warmup 1 --no-cpu --no-e2e --no-elbo > $OUT/ncu_full.log 2>&1
+    python bench.py --n 32768 --steps 1 --warmup 1 --no-cpu --no-e2e --no-elbo --no-sweep > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
 ls -la $OUT
