@@ -1,14 +1,20 @@
 // SGPR statistics and the dense M^3 / N^3 tails.
 //
-// oak_sgpr_stats_f64 replaces the Kuf build and the A A^T / A err contractions of gpflow's
-// SGPR.elbo as re-derived in oak/utils.py:180-191.  The local N points are streamed in chunks: the
-// fused Gram tile kernel writes an M x chunk block of Kuf (sized to stay L2 resident), cuBLAS
-// DSYRK folds it into Phi = Kuf Kuf^T and DGEMV into Kuf y; K_diag and y^T y are reduced by
-// deterministic single-block kernels.  Phi | Kuf y | sum K_diag | y^T y is one contiguous vector:
-// the only thing that has to be all-reduced across ranks.
-//
-// oak_sgpr_finish_f64 / oak_gpr_finish_f64 are the dense tails (cuSOLVER potrf, cuBLAS
-// trsm/trsv), timed separately from the tile kernels.
+// Two generations of entry points live here.
+//   * oak_sgpr_factor_f64 / oak_sgpr_stats2_f64 / oak_sgpr_factor_stats_f64 / oak_sgpr_finish2_f64 (round 2, what
+//     models.SGPR calls): L = chol(Kuu) FIRST by the one-launch bordered Cholesky (oak_chol.cu), a condition estimate
+//     and a device-side route flag; the local N points are streamed in chunks -- fused Gram tiles write an M x chunk
+//     block of Kuf (with Kuf y folded into the tile epilogue), the hand-written stream-K DMMA kernel of oak_syrk.cu
+//     contracts it into Phi = Kuf Kuf^T (route 0) or, after the DMMA whitening product of oak_pgemm.cu, into
+//     Psi = sum (L^-1 Kuf)(L^-1 Kuf)^T (route 1: gpflow's operation order, oak/utils.py:186-190); K_diag and y^T y are
+//     reduced by deterministic fixed-order kernels.  Phi | Kuf y | sum K_diag | y^T y is one contiguous vector: the
+//     only thing that is all-reduced across ranks.  The tail is one more bordered Cholesky with (L^-1 Kuf y) / noise as
+//     its border row.  The fused call hides the factorisation behind the first chunk's tiles (side stream).
+//   * oak_sgpr_stats_f64 / oak_sgpr_stats_keep_f64 / oak_sgpr_finish_f64 (round 1, kept for the training path, which
+//     needs the un-whitened Kuf blocks): the same chunk loop with the contraction selectable by OAK_SYRK_MODE
+//     (30 = the DMMA kernel, default; 0 / 1 / 9 / 20 = cuBLAS DSYRK / recursive DGEMM / DGEMM / batched DGEMM, the
+//     alternatives measured in profiles/r01_ab_sgpr_contraction.txt) and a cuSOLVER potrf + cuBLAS trsm / trsv tail.
+// oak_gpr_finish_f64 is the GPR tail (cuSOLVER potrf / potrs), timed separately from the tile kernels.
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
