@@ -734,7 +734,29 @@ def main():
         ms_ = SGPR((cfg_s["X"], cfg_s["y"]), kernel=build_kernel(cfg_s), inducing_variable=cfg_s["Z"])
         ms_.likelihood.variance.assign(cfg_s["noise"])
         elbo_gpu = ms_.elbo()
+        # per-configuration parity on samples of the named shapes (element-wise for Gram entries)
+        per_cfg = {}
+        try:
+            from oak_b200.workloads import config_A, config_D, config_E
+            from oracle import cpu_baseline as cb
+
+            rng_p = np.random.default_rng(123)
+            for name, cfg_x in (("A", config_A()), ("D", config_D()), ("E", config_E())):
+                rows = rng_p.choice(cfg_x["X"].shape[0], 384, replace=False)
+                cols = rng_p.choice(cfg_x["X"].shape[0], 320, replace=False)
+                Xa, Xb = cfg_x["X"][rows], cfg_x["X"][cols]
+                Kg = np.asarray(build_kernel(cfg_x).K(Xa, Xb))
+                Kr = cb.gram(cfg_x, torch.as_tensor(Xa), torch.as_tensor(Xb)).numpy()
+                dg = np.asarray(build_kernel(cfg_x).K_diag(Xa))
+                dr = cb.gram_diag(cfg_x, torch.as_tensor(Xa)).numpy().reshape(-1)
+                per_cfg[name] = {"gram_max_elementwise_rel_err": float(np.max(np.abs(Kg - Kr) / np.maximum(np.abs(Kr), 1e-12))),
+                                 "gram_max_err_over_max": float(np.max(np.abs(Kg - Kr)) / np.max(np.abs(Kr))),
+                                 "k_diag_max_rel_err": float(np.max(np.abs(dg.reshape(-1) - dr) / np.abs(dr))),
+                                 "sample": "384 x 320 random rows / columns of the configuration's inputs"}
+        except Exception as exc:
+            per_cfg = {"error": repr(exc)}
         cpu = {"value": v, "unit": "unique entries/s", "cores": threads, "kind": "port",
+               "parity_other_configs": per_cfg,
                "sample": f"K(X,X) N={args.n_cpu}, D=16, depth=4 (reference op sequence, oracle/cpu_baseline.py, "
                          f"torch-CPU FP64), median of 3: {t_eval:.2f} s per evaluation",
                "parity_max_elementwise_rel_err_gram": gram_err,
