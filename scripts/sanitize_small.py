@@ -53,6 +53,25 @@ if "backward" in which:
     W = torch.randn(130, 700, dtype=torch.float64, device="cuda")
     g = _device.gram_backward(spec, pz, W, px2=px)
     print("backward", float(g[0]))
+if "overlap" in which:
+    # the fused factor + statistics call with the factorisation on the side stream (forced: the sizes are tiny)
+    for whiten in (False, True):
+        m = SGPR((cfg["X"], cfg["y"]), kernel=k, inducing_variable=cfg["Z"], chunk=256, whiten_stats=whiten)
+        m.likelihood.variance.assign(cfg["noise"])
+        m.overlap_ctas = 4
+        print("sgpr overlapped", whiten, m.elbo(), m.elbo())
+if "kmeans" in which:
+    from oak_b200.kmeans import KMeans
+    rng = np.random.default_rng(1)
+    for n_, d_, k_ in ((900, 5, 12), (5000, 20, 70), (600, 70, 7)):
+        Xk = rng.standard_normal((n_, d_)) + 3.0 * rng.standard_normal((8, d_))[rng.integers(0, 8, n_)]
+        km = KMeans(n_clusters=k_, random_state=0).fit(Xk)
+        print("kmeans", n_, d_, k_, km.n_iter_, float(km.cluster_centers_[0, 0]))
+if "unique" in which:
+    col = np.round(np.random.default_rng(2).standard_normal(5000) * 4) / 4
+    Xu = _device.to_device(np.column_stack([col, col[::-1]]))
+    v, c = _device.column_unique(Xu, 0)
+    print("unique", len(v), int(c.sum()), _device.column_mean(Xu, 1))
 spec.close()
 torch.cuda.synchronize()
 print("sanitize_small done")
