@@ -917,7 +917,10 @@ extern "C" int oak_sgpr_factor_stats_f64(const oak_spec* spec, const void* d_poi
     const int64_t nc = n_local < chunk ? n_local : chunk;
     // measured at M = 1024 (profiles/r02r_*): the factorisation takes ~2.0 / 2.7 / 3.9 ms on 8 / 6 / 4 CTAs, the first
     // chunk's tiles 2.5 ms per 125 000 points -- 8 CTAs leave a margin on short chunks, 4 are enough on long ones
-    overlap_ctas = env_overlap >= 0 ? env_overlap : (m < 256 || nc < 100000 ? 0 : (nc >= 250000 ? 4 : 8));
+    // (depth <= 4: the one-CTA-per-SM tile kernel, which leaves whole SMs free when its grid is capped; the deeper
+    // geometries are not measured and stay serial)
+    overlap_ctas = env_overlap >= 0 ? env_overlap
+                                    : (m < 256 || nc < 100000 || spec->depth > 4 ? 0 : (nc >= 250000 ? 4 : 8));
   }
   if (overlap_ctas == 0 || n_local <= 0) {
     if (int rc = oak_sgpr_factor_f64(spec, d_pointsZ, m, jitter, route, cond_threshold, d_fac, stream_)) return rc;
