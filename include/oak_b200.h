@@ -347,11 +347,13 @@ size_t oak_sobol_L_work_bytes(const oak_spec* spec, int32_t dim, int64_t m);
 int oak_sobol_gaussian_terms_f64(const double* d_x, const double* d_y, int64_t n, double sigma,
                                  double lengthscale, double delta, double mu, double* d_out, void* stream);
 /* Replaces the component loop of compute_sobol_oak (oak/utils.py:369-432):
- * out[c] = scale[c] * alpha^T (prod_{d in S_c} L_d) alpha.  d_Lstack: (num_dims x m x m). */
+ * out[c] = scale[c] * alpha^T (prod_{d in S_c} L_d) alpha.  d_Lstack: (num_dims x m x m); d_work:
+ * oak_sobol_quadforms_work_bytes bytes (row-split partial sums, folded in a fixed order). */
+size_t oak_sobol_quadforms_work_bytes(int32_t num_components, int64_t m);
 int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
                             const int32_t* d_subsets, const double* d_scale,
                             int32_t num_components, int32_t max_order, const double* d_alpha,
-                            double* d_out, void* stream);
+                            double* d_out, void* d_work, void* stream);
 
 /* ---- backward tiles (training) ------------------------------------------------------ */
 /* Replaces TensorFlow's autodiff through OAKKernel.K / K_diag inside the gpflow objectives

@@ -136,7 +136,8 @@ SIGNATURES = {
     "oak_gpr_finish_f64": (C.c_int, [_dp, _dp, _i64, C.c_double, _dp, _dp, _vp, _vp]),
     "oak_sobol_L_f64": (C.c_int, [_vp, _i32, _dp, _i64, _i64, C.c_double, C.c_double, _dp, _i64, _vp, _vp]),
     "oak_sobol_L_work_bytes": (_sz, [_vp, _i32, _i64]),
-    "oak_sobol_quadforms_f64": (C.c_int, [_dp, _i32, _i64, _vp, _dp, _i32, _i32, _dp, _dp, _vp]),
+    "oak_sobol_quadforms_work_bytes": (_sz, [_i32, _i64]),
+    "oak_sobol_quadforms_f64": (C.c_int, [_dp, _i32, _i64, _vp, _dp, _i32, _i32, _dp, _dp, _vp, _vp]),
     "oak_measure_fp64_peak": (C.c_int, [C.c_double, C.POINTER(C.c_double), _vp]),
     "oak_launch_count": (_i64, []),
 }

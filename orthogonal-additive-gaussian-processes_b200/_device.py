@@ -746,10 +746,12 @@ def sobol_quadforms(Lstack, subsets: Sequence[Sequence[int]], scale: Sequence[fl
     d_scale = torch.as_tensor(np.asarray(scale, dtype=np.float64)).to(dev)
     out = torch.empty(nc, dtype=torch.float64, device=dev)
     a = alpha.reshape(-1).contiguous()
+    lib = _cabi.load()
+    work = torch.empty(max(int(lib.oak_sobol_quadforms_work_bytes(nc, int(Lstack.shape[1]))) // 8, 1),
+                       dtype=torch.float64, device=dev)
     check(
-        _cabi.load().oak_sobol_quadforms_f64(_p(Lstack), int(Lstack.shape[0]), int(Lstack.shape[1]), _p(d_tab),
-                                             _p(d_scale), nc, max_order, _p(a), _p(out),
-                                             C.c_void_p(stream_ptr())),
+        lib.oak_sobol_quadforms_f64(_p(Lstack), int(Lstack.shape[0]), int(Lstack.shape[1]), _p(d_tab), _p(d_scale), nc,
+                                    max_order, _p(a), _p(out), _p(work), C.c_void_p(stream_ptr())),
         "oak_sobol_quadforms_f64",
     )
     return out

@@ -119,13 +119,13 @@ __global__ void empirical_kxu_kernel(const double* __restrict__ az, const double
   Kw[l * m + i] = w[l] * k;
 }
 
-// out[c] = scale[c] * sum_ij alpha_i alpha_j prod_{d in S_c} L_d[i,j]; one block per component
+// part[c][s] = sum over the rows of split s of alpha_i alpha_j prod_{d in S_c} L_d[i,j]: block (component c, row
+// split s); rows outermost, columns strided over the threads (no index division), fixed-order block reduction
 __global__ void __launch_bounds__(512) sobol_quadforms_kernel(
-    const double* __restrict__ Lstack, int64_t m, const int32_t* __restrict__ subsets,
-    const double* __restrict__ scale, int max_order, const double* __restrict__ alpha,
-    double* __restrict__ out) {
+    const double* __restrict__ Lstack, int64_t m, const int32_t* __restrict__ subsets, int max_order,
+    const double* __restrict__ alpha, int splits, double* __restrict__ part) {
   __shared__ double sh[512];
-  const int c = blockIdx.x;
+  const int c = blockIdx.x, sp = blockIdx.y;
   const double* Ls[OAK_MAX_DEPTH];
   int order = 0;
   for (int q = 0; q < max_order; ++q) {
@@ -133,13 +133,17 @@ __global__ void __launch_bounds__(512) sobol_quadforms_kernel(
     if (d < 0) break;
     Ls[order++] = Lstack + (int64_t)d * m * m;
   }
+  const int64_t rows_per = (m + splits - 1) / splits;
+  const int64_t i0 = sp * rows_per, i1 = i0 + rows_per < m ? i0 + rows_per : m;
   double acc = 0.0;
-  const int64_t total = m * m;
-  for (int64_t idx = threadIdx.x; idx < total; idx += 512) {
-    const int64_t i = idx / m, j = idx - i * m;
-    double v = alpha[i] * alpha[j];
-    for (int q = 0; q < order; ++q) v *= Ls[q][idx];
-    acc += v;
+  for (int64_t i = i0; i < i1; ++i) {
+    const double ai = alpha[i];
+    const int64_t base = i * m;
+    for (int64_t j = threadIdx.x; j < m; j += 512) {
+      double v = ai * alpha[j];
+      for (int q = 0; q < order; ++q) v *= Ls[q][base + j];
+      acc += v;
+    }
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -147,7 +151,16 @@ __global__ void __launch_bounds__(512) sobol_quadforms_kernel(
     if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[c] = scale[c] * sh[0];
+  if (threadIdx.x == 0) part[(int64_t)c * splits + sp] = sh[0];
+}
+// out[c] = scale[c] * sum_s part[c][s] (fixed order)
+__global__ void sobol_quadforms_fold_kernel(const double* __restrict__ part, int splits, const double* __restrict__ scale,
+                                            int n, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double acc = 0.0;
+  for (int s = 0; s < splits; ++s) acc += part[(int64_t)c * splits + s];
+  out[c] = scale[c] * acc;
 }
 
 static cublasHandle_t g_sobol_cublas[64] = {nullptr};
@@ -250,17 +263,38 @@ extern "C" int oak_sobol_L_f64(const oak_spec* spec, int32_t dim, const double* 
   return 0;
 }
 
+static int quadform_splits(int32_t num_components, int64_t m) {
+  // few components (config A: 255): split the rows of every component over several blocks so that the 592 block
+  // slots of the device are filled
+  constexpr int kSlots = 592, kMaxSplits = 16;
+  int splits = num_components < kSlots ? (kSlots + num_components - 1) / num_components : 1;
+  if (splits > kMaxSplits) splits = kMaxSplits;
+  if ((int64_t)splits * 8 > m) splits = (int)((m + 7) / 8);
+  return splits < 1 ? 1 : splits;
+}
+
+extern "C" size_t oak_sobol_quadforms_work_bytes(int32_t num_components, int64_t m) {
+  if (num_components <= 0 || m <= 0) return 0;
+  return (size_t)num_components * quadform_splits(num_components, m) * sizeof(double);
+}
+
 extern "C" int oak_sobol_quadforms_f64(const double* d_Lstack, int32_t num_dims, int64_t m,
                                        const int32_t* d_subsets, const double* d_scale,
                                        int32_t num_components, int32_t max_order,
-                                       const double* d_alpha, double* d_out, void* stream_) {
-  OAK_REQUIRE(d_Lstack && d_subsets && d_scale && d_alpha && d_out,
+                                       const double* d_alpha, double* d_out, void* d_work, void* stream_) {
+  OAK_REQUIRE(d_Lstack && d_subsets && d_scale && d_alpha && d_out && d_work,
               "oak_sobol_quadforms_f64: null argument");
   OAK_REQUIRE(max_order >= 1 && max_order <= OAK_MAX_DEPTH, "oak_sobol_quadforms_f64: bad max_order");
   (void)num_dims;
   if (num_components <= 0) return 0;
-  sobol_quadforms_kernel<<<(unsigned)num_components, 512, 0, (cudaStream_t)stream_>>>(
-      d_Lstack, m, d_subsets, d_scale, max_order, d_alpha, d_out);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int splits = quadform_splits(num_components, m);
+  double* part = (double*)d_work;  // [num_components][splits]
+  sobol_quadforms_kernel<<<dim3((unsigned)num_components, (unsigned)splits), 512, 0, stream>>>(
+      d_Lstack, m, d_subsets, max_order, d_alpha, splits, part);
+  OAK_LAUNCHED();
+  sobol_quadforms_fold_kernel<<<(unsigned)((num_components + 255) / 256), 256, 0, stream>>>(part, splits, d_scale,
+                                                                                           num_components, d_out);
   OAK_LAUNCHED();
   return 0;
 }
