@@ -110,7 +110,7 @@ __global__ void prepare_points_kernel(const DimDev* __restrict__ dims,
 // The column-per-block kernel above reads a column with a stride of ldx doubles: 8 x the sectors, D times over
 // (0.41 ms for 10^6 x 20 inputs, against 0.48 GB of useful traffic).
 constexpr int kRowTile = 128;
-constexpr int kRowTileMaxLd = 40;  // 128 x 40 doubles = 40 KB of dynamic shared memory (+ 4 KB static: under the 48 KB default)
+constexpr int kRowTileMaxLd = 96;  // 128 x 96 doubles = 96 KB of dynamic shared memory (opt-in above 48 KB; + 4 KB static)
 constexpr int kRowTileMaxD = 64;
 
 __global__ void __launch_bounds__(kRowTile) prepare_points_rows_kernel(
@@ -282,6 +282,10 @@ extern "C" int oak_prepare_points_f64(const oak_spec* spec, const double* d_X, i
   OAK_REQUIRE(d_X, "oak_prepare_points_f64: null X");
   const int threads = 256;
   if (ldx <= kRowTileMaxLd && D <= kRowTileMaxD) {
+    const size_t tile_bytes = (size_t)kRowTile * ldx * sizeof(double);
+    if (tile_bytes > 40 * 1024)
+      OAK_CUDA(cudaFuncSetAttribute(prepare_points_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kRowTile * kRowTileMaxLd * (int)sizeof(double)));
     prepare_points_rows_kernel<<<(unsigned)(n_pad / kRowTile), kRowTile, (size_t)kRowTile * ldx * sizeof(double), stream>>>(
         spec->d_dims, spec->d_inv_sqrt_v, spec->d_tables, d_X, n, n_pad, (int)ldx, (double2*)d_points, minmax, D);
   } else {
