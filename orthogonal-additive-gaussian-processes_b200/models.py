@@ -208,7 +208,7 @@ class SGPR(GPModel):
             n_total = int(Xs.shape[0])
             if self.distributed:
                 parallel.allreduce_sum_(stats)
-                n_total = parallel.global_count(n_total, id(self))
+                n_total = parallel.global_count(self, n_total)
         finally:
             spec.close()
         tail = _device.sgpr_finish2(fac, stats, n_total, scalar_of(self.likelihood.variance), want_alpha=want_alpha)

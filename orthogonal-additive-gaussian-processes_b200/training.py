@@ -182,7 +182,7 @@ def sgpr_elbo_and_grad(model) -> Tuple[float, np.ndarray, np.ndarray, float]:
         n_total = n_local
         if model.distributed:
             parallel.allreduce_sum_(stats)
-            n_total = parallel.global_count(n_total, id(model))
+            n_total = parallel.global_count(model, n_total)
         Kuu = _device.gram(spec, pz)
         # statistics: Phi arrives as column-major lower == upper triangle of the row-major view
         U = torch.triu(stats[: m * m].view(m, m))
