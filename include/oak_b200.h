@@ -307,6 +307,16 @@ int oak_kmeans_lloyd_f64(const double* d_Xc, int64_t n, int64_t d, const double*
                          int32_t* d_labels, double* d_centers_new, double* d_sums, double* d_counts, double* d_out,
                          int update_centers, void* d_work, void* stream);
 
+/* E step + M-step sums of a one-dimensional spherical Gaussian mixture: the MOG input measure fitted by
+ * GaussianMixture(n_components=K, random_state=0, covariance_type="spherical") in oak/model_utils.py:753-770
+ * (sklearn/mixture/_gaussian_mixture.py: _estimate_log_gaussian_prob, _estimate_gaussian_parameters).
+ * d_par: 4 x K doubles = means | precisions | log precisions_cholesky | log weights; d_labels (int32, nullable): hard
+ * responsibilities of the k-means initialisation instead of the E step.  d_out[3K + 1] = sum_i resp_ik |
+ * sum_i resp_ik x_i | sum_i resp_ik x_i^2 | sum_i log p(x_i).  K <= 16. */
+size_t oak_gmm1d_work_bytes(int64_t n, int64_t K);
+int oak_gmm1d_estep_f64(const double* d_x, int64_t n, int64_t K, const double* d_par, const int32_t* d_labels,
+                        double* d_out, void* d_work, void* stream);
+
 /* ---- dense building blocks of the tails (csrc/oak_chol.cu, csrc/oak_pgemm.cu) ---------------- */
 /* Cholesky factorisation with border rows in one cooperative launch, replacing the tf.linalg.cholesky +
  * tf.linalg.triangular_solve pairs of oak/utils.py:188-195.  d_A: column-major, leading dimension ld

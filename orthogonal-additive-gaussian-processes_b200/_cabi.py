@@ -127,6 +127,8 @@ SIGNATURES = {
     "oak_kmeans_center_f64": (C.c_int, [_dp, _i64, _i64, _i64, _dp, _dp, _vp, _vp]),
     "oak_kmeanspp_round_f64": (C.c_int, [_dp, _i64, _i64, _dp, _dp, _i64, _vp, _dp, _dp, _dp, _vp, _vp]),
     "oak_kmeans_lloyd_f64": (C.c_int, [_dp, _i64, _i64, _dp, _i64, _vp, _dp, _dp, _dp, _dp, C.c_int, _vp, _vp]),
+    "oak_gmm1d_work_bytes": (_sz, [_i64, _i64]),
+    "oak_gmm1d_estep_f64": (C.c_int, [_dp, _i64, _i64, _dp, _vp, _dp, _vp, _vp]),
     "oak_sgpr_finish2_work_bytes": (_sz, [_i64]),
     "oak_sgpr_finish2_f64": (C.c_int, [_dp, _dp, _i64, _i64, C.c_double, _dp, _dp, _dp, _vp, _vp]),
     "oak_chol_f64": (C.c_int, [_dp, _i64, _i64, _i64, _i64, C.c_int, _vp, _dp, _vp]),

@@ -485,3 +485,100 @@ extern "C" int oak_kmeans_lloyd_f64(const double* d_Xc, int64_t n, int64_t d, co
   OAK_LAUNCHED();
   return 0;
 }
+
+// ---- one-dimensional spherical Gaussian mixture (the MOG input measure) -----------------------------------------------
+// oak/model_utils.py:753-770 fits sklearn's GaussianMixture(n_components=K, random_state=0,
+// covariance_type="spherical") to one input column.  The E step and the sufficient statistics of the M step -- the O(N K)
+// part of every EM iteration -- run here; the K-element M step and the stopping rule stay on the host (gmm.py).
+// part[v][block], v = k (sum resp_k), K + k (sum resp_k x), 2K + k (sum resp_k x^2), 3K (sum log p(x)).
+// labels != NULL: hard responsibilities from the k-means initialisation (mixture/_base.py:119-128).
+namespace oak {
+constexpr int kGmmMaxK = 16;
+
+__global__ void __launch_bounds__(km::kThreads) gmm1d_estep_kernel(const double* __restrict__ x, int64_t n, int K,
+                                                                   const double* __restrict__ par,  // [4][K]
+                                                                   const int32_t* __restrict__ labels,
+                                                                   double* __restrict__ part) {
+  __shared__ double sh[8];
+  __shared__ double sp[4 * kGmmMaxK];
+  if (threadIdx.x < 4 * K) sp[threadIdx.x] = par[threadIdx.x];
+  __syncthreads();
+  const double* means = sp;               // mu_k
+  const double* prec = sp + K;            // precisions_k = precisions_cholesky_k^2
+  const double* logdet = sp + 2 * K;      // log precisions_cholesky_k
+  const double* logw = sp + 3 * K;        // log weights_k
+  double s0[kGmmMaxK], s1[kGmmMaxK], s2[kGmmMaxK], ll = 0.0;
+#pragma unroll
+  for (int k = 0; k < kGmmMaxK; ++k) s0[k] = s1[k] = s2[k] = 0.0;
+  const int64_t lo = (int64_t)blockIdx.x * km::kSeg;
+  const int64_t hi = lo + km::kSeg < n ? lo + km::kSeg : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += km::kThreads) {
+    const double xi = x[i], x2 = xi * xi;
+    double r[kGmmMaxK];
+    if (labels) {
+#pragma unroll
+      for (int k = 0; k < kGmmMaxK; ++k) r[k] = (k < K && labels[i] == k) ? 1.0 : 0.0;
+    } else {
+      // _estimate_log_gaussian_prob (spherical) + log weights, then scipy's logsumexp
+      double lp[kGmmMaxK], mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < kGmmMaxK; ++k) {
+        if (k < K) {
+          const double q = means[k] * means[k] * prec[k] - 2.0 * (xi * (means[k] * prec[k])) + x2 * prec[k];
+          lp[k] = -0.5 * (1.8378770664093453 + q) + logdet[k] + logw[k];
+          mx = fmax(mx, lp[k]);
+        }
+      }
+      double se = 0.0;
+#pragma unroll
+      for (int k = 0; k < kGmmMaxK; ++k)
+        if (k < K) se += exp(lp[k] - mx);
+      const double lse = log(se) + mx;
+      ll += lse;
+#pragma unroll
+      for (int k = 0; k < kGmmMaxK; ++k) r[k] = (k < K) ? exp(lp[k] - lse) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kGmmMaxK; ++k) {
+      s0[k] += r[k];
+      s1[k] = fma(r[k], xi, s1[k]);
+      s2[k] = fma(r[k], x2, s2[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kGmmMaxK; ++k) {
+    if (k < K) {
+      double v = km::block_sum(s0[k], sh);
+      if (threadIdx.x == 0) part[(int64_t)k * gridDim.x + blockIdx.x] = v;
+      v = km::block_sum(s1[k], sh);
+      if (threadIdx.x == 0) part[(int64_t)(K + k) * gridDim.x + blockIdx.x] = v;
+      v = km::block_sum(s2[k], sh);
+      if (threadIdx.x == 0) part[(int64_t)(2 * K + k) * gridDim.x + blockIdx.x] = v;
+    }
+  }
+  const double v = km::block_sum(ll, sh);
+  if (threadIdx.x == 0) part[(int64_t)(3 * K) * gridDim.x + blockIdx.x] = v;
+}
+}  // namespace oak
+
+extern "C" size_t oak_gmm1d_work_bytes(int64_t n, int64_t K) {
+  if (n < 0 || K < 1) return 0;
+  return (size_t)(3 * K + 1) * (size_t)((n + km::kSeg - 1) / km::kSeg + 1) * sizeof(double);
+}
+
+// d_par: [4][K] = means | precisions | log precisions_cholesky | log weights (ignored with d_labels);
+// d_out[3K + 1] = sum resp_k | sum resp_k x | sum resp_k x^2 | sum_i log p(x_i)
+extern "C" int oak_gmm1d_estep_f64(const double* d_x, int64_t n, int64_t K, const double* d_par,
+                                   const int32_t* d_labels, double* d_out, void* d_work, void* stream_) {
+  OAK_REQUIRE(d_x && d_par && d_out && d_work, "oak_gmm1d_estep_f64: null argument");
+  OAK_REQUIRE(n >= 1 && K >= 1 && K <= kGmmMaxK, "oak_gmm1d_estep_f64: bad shape (at most 16 components)");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int blocks = (int)((n + km::kSeg - 1) / km::kSeg);
+  gmm1d_estep_kernel<<<blocks, km::kThreads, 0, stream>>>(d_x, n, (int)K, d_par, d_labels, (double*)d_work);
+  OAK_LAUNCHED();
+  const int nv = (int)(3 * K + 1);
+  kmeans_fold_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, stream>>>((const double*)d_work, blocks, nv, 1.0, d_out,
+                                                                      nullptr);
+  OAK_LAUNCHED();
+  return 0;
+}

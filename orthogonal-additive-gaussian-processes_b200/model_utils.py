@@ -142,14 +142,20 @@ def apply_normalise_flow(X, input_flows):
 
 
 def estimate_one_dim_gmm(K: int, X: np.ndarray) -> MOGMeasure:
-    """Spherical Gaussian mixture fitted to one input column (model_utils.py:753-770); host preprocessing."""
-    from sklearn.mixture import GaussianMixture
+    """Spherical Gaussian mixture fitted to one input column (model_utils.py:753-770): scikit-learn's EM on the device
+    (``gmm.GaussianMixture1D``); the library's own class only on a machine without a CUDA device."""
+    from .gmm import GaussianMixture1D, on_device
 
     X = np.asarray(X, dtype=np.float64)
     if X.ndim != 1:
         raise ValueError(f"expected a 1-D array, got shape {X.shape}")
     assert K > 0
-    gm = GaussianMixture(n_components=int(K), random_state=0, covariance_type="spherical").fit(X.reshape(-1, 1))
+    if on_device():
+        gm = GaussianMixture1D(n_components=int(K), random_state=0).fit(X)
+    else:
+        from sklearn.mixture import GaussianMixture
+
+        gm = GaussianMixture(n_components=int(K), random_state=0, covariance_type="spherical").fit(X.reshape(-1, 1))
     assert np.allclose(gm.weights_.sum(), 1.0)
     return MOGMeasure(weights=gm.weights_, means=gm.means_.reshape(-1), variances=gm.covariances_)
 

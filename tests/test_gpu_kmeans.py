@@ -79,3 +79,26 @@ def test_too_few_samples_raise_like_scikit_learn():
 
     with pytest.raises(ValueError, match="should be >= n_clusters"):
         KMeans(n_clusters=10, random_state=0).fit(np.zeros((4, 2)))
+
+
+@pytest.mark.parametrize("n,K,seed", [(400, 2, 0), (3000, 3, 1), (20000, 5, 2), (1500, 1, 3)])
+def test_one_dimensional_gaussian_mixture_matches_scikit_learn(n, K, seed):
+    """The MOG input measure (oak/model_utils.py:753-770): GaussianMixture(K, random_state=0, spherical) on one column."""
+    from sklearn.mixture import GaussianMixture
+
+    from oak_b200.gmm import GaussianMixture1D
+    from oak_b200.model_utils import estimate_one_dim_gmm
+
+    rng = np.random.default_rng(seed)
+    comp = rng.integers(0, max(K, 2), n)
+    x = rng.standard_normal(n) * (0.4 + 0.3 * comp) + 2.5 * comp
+    ref = GaussianMixture(n_components=K, random_state=0, covariance_type="spherical").fit(x.reshape(-1, 1))
+    got = GaussianMixture1D(n_components=K, random_state=0).fit(x)
+    assert got.n_iter_ == ref.n_iter_ and got.converged_ == ref.converged_
+    assert max_rel_err(got.weights_, ref.weights_) < 1e-9
+    assert max_rel_err(got.means_, ref.means_) < 1e-9
+    assert max_rel_err(got.covariances_, ref.covariances_) < 1e-9
+    mog = estimate_one_dim_gmm(K, x)
+    assert max_rel_err(mog.means, ref.means_.reshape(-1)) < 1e-9
+    assert max_rel_err(mog.variances, ref.covariances_) < 1e-9
+    assert max_rel_err(mog.weights, ref.weights_) < 1e-9
