@@ -669,7 +669,7 @@ def main():
             sd.close()
             del outd
             ce = config_E()
-            me = SGPR((ce["X"], ce["y"]), kernel=build_kernel(ce), inducing_variable=ce["Z"], chunk=65536)
+            me = SGPR((ce["X"], ce["y"]), kernel=build_kernel(ce), inducing_variable=ce["Z"])
             me.likelihood.variance.assign(ce["noise"])
             ms, _ = timed(lambda: compute_sobol_oak(me, 1.0, 0.0), reps=1)
             others["E_sobol_d50_n200000_m512_1275_components"] = {"ms": ms}
