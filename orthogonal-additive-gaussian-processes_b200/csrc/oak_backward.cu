@@ -29,7 +29,10 @@
 namespace oak {
 
 namespace bw {
-constexpr int kDimChunk = 16;
+#ifndef OAK_BW_DIMCHUNK
+#define OAK_BW_DIMCHUNK 16  // dims per pipeline stage (A/B aid: 8 halves the staging buffers for two CTAs per SM)
+#endif
+constexpr int kDimChunk = OAK_BW_DIMCHUNK;
 constexpr int kThreads = 256;
 constexpr int kTXD = 16, kTYD = 16;
 constexpr int kMaxDims = 512;  // per-warp shared slots for the lengthscale partials
@@ -81,8 +84,17 @@ __device__ __forceinline__ double entry_exp(double d, double ax, const unsigned 
   return exp_neg_scaled(fma(d, d, ax), tab_bytes, lane_bits);
 }
 
+#ifndef OAK_BW_MINB
+#define OAK_BW_MINB 1  // A/B aid: 2 = two CTAs per SM (needs the 2 x 4 micro-tile to stay within 128 registers)
+#endif
+#ifndef OAK_BW_RM3
+#define OAK_BW_RM3 4   // rows of the micro-tile at depth <= 3
+#endif
+#ifndef OAK_BW_RN3
+#define OAK_BW_RN3 4
+#endif
 template <int P, int RM, int RN, bool ZG>
-__global__ void __launch_bounds__(bw::kThreads, 1) gram_backward_kernel(const BwParams prm) {
+__global__ void __launch_bounds__(bw::kThreads, OAK_BW_MINB) gram_backward_kernel(const BwParams prm) {
   using namespace bw;
   constexpr int TM = kTYD * RM, TN = kTXD * RN;
   constexpr int kTabDoubles = kExpTab * kExpRepl;
@@ -942,9 +954,9 @@ static int gram_backward_impl(const oak_spec* spec, const void* d_points, const 
   }
   int grid = 0, rc = 0;
   switch (depth) {
-    case 1: rc = launch_backward<1, 4, 4>(prm, sms, stream, &grid); break;
-    case 2: rc = launch_backward<2, 4, 4>(prm, sms, stream, &grid); break;
-    case 3: rc = launch_backward<3, 4, 4>(prm, sms, stream, &grid); break;
+    case 1: rc = launch_backward<1, OAK_BW_RM3, OAK_BW_RN3>(prm, sms * OAK_BW_MINB, stream, &grid); break;
+    case 2: rc = launch_backward<2, OAK_BW_RM3, OAK_BW_RN3>(prm, sms * OAK_BW_MINB, stream, &grid); break;
+    case 3: rc = launch_backward<3, OAK_BW_RM3, OAK_BW_RN3>(prm, sms * OAK_BW_MINB, stream, &grid); break;
     case 4: rc = launch_backward<4, 2, 4>(prm, sms, stream, &grid); break;
     case 5: rc = launch_backward<5, 2, 2>(prm, sms, stream, &grid); break;
     case 6: rc = launch_backward<6, 2, 2>(prm, sms, stream, &grid); break;
