@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-elbo", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--algo", type=int, default=0, help="0 Newton-Girard (reference), 1 direct recurrence")
+    ap.add_argument("--algo", type=int, default=1, help="0 Newton-Girard (the reference's scheme), 1 direct recurrence (package default)")
     return ap.parse_args()
 
 
@@ -434,15 +434,18 @@ def main():
     roofline = {
         "bound": "fp64",
         "bound_note": "FP64 (DFMA) pipe: neither of the template's roofs binds -- 8 B of HBM traffic per entry "
-                      "against >= 242 FP64 instructions, no tensor-core work in this kernel; the hbm sub-object "
+                      "against >= 213 FP64 instructions, no tensor-core work in this kernel; the hbm sub-object "
                       "carries the HBM line",
         "achieved": head["achieved_tflops"], "peak": peak_tflops, "unit": "TFLOP/s",
         "frac": head["roofline_frac"], "traffic": ncu_file.get("gram_kernel_dram_bytes_per_launch"),
-        "kernel": "oak::gram_kernel<4,4,4,NG>", "kernel_ms": kern_ms,
-        "fp64_pipe_active_pct_ncu": ncu_file.get("gram_kernel_fp64_pipe_active_pct"),
-        "fp64_pipe_note": "frac is the ALGORITHMIC roofline (work model 306 slots per entry; the kernel issues ~242 FP64 "
-                          "instructions per entry); the pipe utilisation behind it is ncu's "
-                          "sm__pipe_fp64_cycles_active of the committed capture (profiles/)",
+        "kernel": "oak::gram_kernel<4,4,4,%s>" % ("NG" if args.algo == 0 else "direct"), "kernel_ms": kern_ms,
+        "fp64_pipe_active_pct_ncu": ncu_file.get("gram_kernel_fp64_pipe_active_pct" if args.algo == 1
+                                                 else "gram_kernel_fp64_pipe_active_pct_newton_girard"),
+        "fp64_pipe_note": "frac is the ALGORITHMIC roofline: the work model charges 306 slots per entry (the reference's "
+                          "power sums + Newton-Girard); the kernel issues ~%d FP64 instructions per entry (%s), so frac "
+                          "can pass 1.0; the pipe utilisation behind it is ncu's sm__pipe_fp64_cycles_active of the "
+                          "committed capture (profiles/)" % ((242, "Newton-Girard tiles") if args.algo == 0
+                                                              else (213, "direct-recurrence tiles, the package default")),
         "peak_source": "measured in this run: oak_measure_fp64_peak (register-resident DFMA chains, burst); "
                        "MEASURED_PEAKS.json has no FP64 entry",
         "work_model": f"{SLOTS_B:.0f} FP64 issue slots (x2 flop) per unique entry (BASELINE.md section 3)",

@@ -46,8 +46,9 @@ enum {
 
 /* how e_n is formed from the per-dimension kernels */
 enum {
-  OAK_ESP_NEWTON_GIRARD = 0, /* power sums + Newton-Girard, oak/oak_kernel.py:236-249 (default) */
-  OAK_ESP_DIRECT = 1         /* e_n += k_d * e_{n-1}; same polynomial, better conditioned       */
+  OAK_ESP_NEWTON_GIRARD = 0, /* power sums + Newton-Girard, oak/oak_kernel.py:236-249 (the reference) */
+  OAK_ESP_DIRECT = 1         /* e_n += k_d * e_{n-1}; same polynomial, better conditioned, fewer
+                                FP64 instructions: what the Python host layer passes by default */
 };
 
 /* One input dimension.  All pointers are HOST pointers, read during oak_spec_create(). */

@@ -9,8 +9,12 @@ from . import _cabi, _device
 from ._cabi import DimSpec
 from ._gpflow_shim import Kernel
 
-# process-wide default for how e_n is formed (the reference uses Newton-Girard)
-_DEFAULT_ALGORITHM = _cabi.ESP_NEWTON_GIRARD
+# Process-wide default for how e_n is formed.  The reference accumulates power sums and applies Newton-Girard
+# (oak_kernel.py:236-249, kept as ESP_NEWTON_GIRARD and exercised by the same parity tests); the direct recurrence
+# e_n += k_d e_{n-1} evaluates the same polynomial with P instead of S_pow(P) FP64 instructions per entry and
+# dimension and without the cancellation of the Newton-Girard identities.  Measured on B200
+# (profiles/r02au_ab_gram_esp_default.txt): depth 4 (config B) +3 %, depth 8 (config A's shape) +22 %, depth 2 equal.
+_DEFAULT_ALGORITHM = _cabi.ESP_DIRECT
 
 
 class NativeKernel(Kernel):

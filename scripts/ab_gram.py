@@ -60,21 +60,22 @@ out = torch.empty((1024, 131072), dtype=torch.float64, device="cuda")
 t = timeit(lambda: _device.gram(spec, pz, px, out=out))
 out_line.append(f"C Kuf 1024x131072: {t:.3f} ms frac(352) {1024*131072*352/(t*1e-3)/peak:.3f}")
 from oak_b200.workloads import config_D, config_A
-cfg = config_D(32768)
-k = build_kernel(cfg); spec = k._make_spec()
-Xd = _device.to_device(cfg["X"])
-px = _device.Points(spec, Xd)
-out = torch.empty((32768, 32768), dtype=torch.float64, device="cuda")
-t = timeit(lambda: _device.gram(spec, px, out=out))
-out_line.append(f"D sym n=32768 (8 cont + 4 discrete, P=2): {t:.3f} ms frac(135) {32768*32769/2*135/(t*1e-3)/peak:.3f}")
-spec.close()
-cfg = config_A(8192)
-k = build_kernel(cfg); spec = k._make_spec()
-Xd = _device.to_device(cfg["X"])
-px = _device.Points(spec, Xd)
-out = torch.empty((8192, 8192), dtype=torch.float64, device="cuda")
-t = timeit(lambda: _device.gram(spec, px, out=out))
-out_line.append(f"A-shaped sym n=8192 (D=8, P=8): {t:.3f} ms frac(244) {8192*8193/2*244/(t*1e-3)/peak:.3f}")
-spec.close()
+for algo in (0, 1):
+    cfg = config_D(32768)
+    k = build_kernel(cfg); k.esp_algorithm = algo; spec = k._make_spec()
+    Xd = _device.to_device(cfg["X"])
+    px = _device.Points(spec, Xd)
+    out = torch.empty((32768, 32768), dtype=torch.float64, device="cuda")
+    t = timeit(lambda: _device.gram(spec, px, out=out))
+    out_line.append(f"D sym algo{algo} n=32768 (8 cont + 4 discrete, P=2): {t:.3f} ms frac(135) {32768*32769/2*135/(t*1e-3)/peak:.3f}")
+    spec.close()
+    cfg = config_A(8192)
+    k = build_kernel(cfg); k.esp_algorithm = algo; spec = k._make_spec()
+    Xd = _device.to_device(cfg["X"])
+    px = _device.Points(spec, Xd)
+    out = torch.empty((8192, 8192), dtype=torch.float64, device="cuda")
+    t = timeit(lambda: _device.gram(spec, px, out=out))
+    out_line.append(f"A-shaped sym algo{algo} n=8192 (D=8, P=8): {t:.3f} ms frac(244) {8192*8193/2*244/(t*1e-3)/peak:.3f}")
+    spec.close()
 out_line.append(clk.stop())
 print(" | ".join(out_line), flush=True)
