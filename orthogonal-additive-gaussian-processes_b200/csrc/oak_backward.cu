@@ -256,6 +256,26 @@ __global__ void __launch_bounds__(bw::kThreads, OAK_BW_MINB) gram_backward_kerne
       __syncthreads();  // everybody has left sweep 1's last buffer before it is overwritten
       buf = 0;
       issue_stage(row0, col0, 0, 0);
+      // The warp sums of a dimension's two partials (d/dl, d/ds^2) are folded one butterfly round per micro-tile row
+      // of the NEXT dimension: five dependent shuffle + add rounds per dimension would otherwise sit between two
+      // dimension bodies with nothing to cover them but the scheduler's second warp, which is in step.  Same
+      // rounds, same order: the sums are bit-identical to the immediate reduction.  (Measured: -2.5 % on the plain
+      // tiles; the row-gradient variant, at 255 registers with its own half-warp sums, loses 2 % and keeps the
+      // immediate reduction: profiles/r02bd_ab_backward_deferred_butterfly.txt.)
+      constexpr bool kDefer = !ZG;
+      double pend_a = 0.0, pend_v = 0.0, pend_inv_s2 = 0.0;
+      int pend_slot = -1;      // dimension whose partials are in flight
+      bool pend_ls = false;    // ... and whether it has a lengthscale gradient
+      auto pend_round = [&](int o) {
+        pend_a += __shfl_xor_sync(0xffffffffu, pend_a, o);
+        pend_v += __shfl_xor_sync(0xffffffffu, pend_v, o);
+      };
+      auto pend_commit = [&]() {  // after the last round
+        if (lane == 0 && pend_slot >= 0) {
+          if (pend_ls) myG[pend_slot] += pend_a;
+          myG[vbase + pend_slot] += pend_v * pend_inv_s2;
+        }
+      };
       for (int ch = 0; ch < num_chunks; ++ch) {
         cp_async_wait_all();
         __syncthreads();
@@ -324,31 +344,51 @@ __global__ void __launch_bounds__(bw::kThreads, OAK_BW_MINB) gram_backward_kerne
               zb[r] = fma(wk, cv[c].y, zb[r]);
             }
           };
+          // rounds 16, 8, 4, 2 of the PREVIOUS dimension's butterfly after the rows of this one (RM = 4: one each,
+          // RM = 2: two each), round 1 and the commit behind the last row
+          constexpr int kRoundsPerRow = 4 / RM;
+          static_assert(RM == 2 || RM == 4, "the deferred butterfly deals four rounds over the micro-tile rows");
           if (fast) {
 #pragma unroll
-            for (int r = 0; r < RM; ++r)
+            for (int r = 0; r < RM; ++r) {
 #pragma unroll
               for (int c = 0; c < RN; ++c) {
                 const double d = rv[r].x - cv[c].x;
                 entry(r, c, d, entry_exp<true>(d, ax, tab_bytes, lane_bits));
               }
+              if constexpr (kDefer) {
+#pragma unroll
+                for (int q = 0; q < kRoundsPerRow; ++q) pend_round(16 >> (r * kRoundsPerRow + q));
+              }
+            }
           } else {
 #pragma unroll
-            for (int r = 0; r < RM; ++r)
+            for (int r = 0; r < RM; ++r) {
 #pragma unroll
               for (int c = 0; c < RN; ++c) {
                 const double d = rv[r].x - cv[c].x;
                 entry(r, c, d, entry_exp<false>(d, ax, tab_bytes, lane_bits));
               }
-          }
+              if constexpr (kDefer) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            accv += __shfl_xor_sync(0xffffffffu, accv, o);
+                for (int q = 0; q < kRoundsPerRow; ++q) pend_round(16 >> (r * kRoundsPerRow + q));
+              }
+            }
           }
-          if (lane == 0) {
-            if (bd.kind != 0.0) myG[d0 + dl] += acc;
-            myG[vbase + d0 + dl] += accv * bd.inv_s2;
+          if constexpr (kDefer) {
+            pend_round(1);
+            pend_commit();
+          }
+          pend_a = acc;
+          pend_v = accv;
+          pend_inv_s2 = bd.inv_s2;
+          pend_slot = d0 + dl;
+          pend_ls = bd.kind != 0.0;
+          if constexpr (!kDefer) {  // immediate reduction
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pend_round(o);
+            pend_commit();
+            pend_slot = -1;
           }
           if constexpr (ZG) {  // the 16 threads of a half warp share their rows
 #pragma unroll
@@ -398,6 +438,12 @@ __global__ void __launch_bounds__(bw::kThreads, OAK_BW_MINB) gram_backward_kerne
             }
         }
         buf ^= 1;
+      }
+      // the last continuous dimension's partials
+      if constexpr (kDefer) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pend_round(o);
+        pend_commit();
       }
       __syncthreads();  // stage buffers are re-issued by the next tile
     }
