@@ -1,5 +1,6 @@
-"""A/B of the 64 x 128 tile geometry of depth <= 2 (OAK_GRAM_WIDE=0/1; development aid, not the bench):
-config D Gram (symmetric, mixed inputs), its cross-covariance, config E's Kuf tiles and a depth-2 ELBO."""
+"""Timing of the depth-2 shapes (development aid, not the bench): config D Gram (symmetric, mixed inputs), its
+cross-covariance, config E's Kuf tiles and a depth-2 ELBO.  Written for the A/B of the 64 x 128 tile geometry
+(profiles/r02bb_ab_gram_wide_tile_negative.txt; that build read OAK_GRAM_WIDE, the shipped one ignores it)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

@@ -198,6 +198,25 @@ def test_normalising_flow_oracle_gradient_log_det_and_host_inverse():
         np.testing.assert_allclose(n.bijector.forward_log_det_jacobian(x[:50]), num, rtol=1e-6, atol=1e-7)
 
 
+def test_default_symmetric_polynomial_scheme_is_the_direct_recurrence_everywhere():
+    """The package default, the bench default and the header's enum agree: kernels pass OAK_ESP_DIRECT unless a
+    kernel instance asks for the reference's power sums + Newton-Girard (`esp_algorithm = 0`)."""
+    import os
+    import re
+
+    from oak_b200 import _native_kernel
+
+    assert (_cabi.ESP_NEWTON_GIRARD, _cabi.ESP_DIRECT) == (0, 1)
+    assert _native_kernel._DEFAULT_ALGORITHM == _cabi.ESP_DIRECT
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "oak_b200.h")).read()
+    assert re.search(r"OAK_ESP_NEWTON_GIRARD\s*=\s*0", header) and re.search(r"OAK_ESP_DIRECT\s*=\s*1", header)
+    bench = open(os.path.join(root, "bench.py")).read()
+    assert re.search(r'"--algo", type=int, default=1', bench)
+    k = OAKKernel([RBF] * 3, num_dims=3, max_interaction_depth=2, active_dims=[[0], [1], [2]])
+    assert k.esp_algorithm is None  # instances follow the process-wide default until told otherwise
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver times beside ours): one JSON line with the
     contract's keys, runnable without a GPU."""
