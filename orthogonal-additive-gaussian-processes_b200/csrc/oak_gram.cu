@@ -164,7 +164,9 @@ __device__ __forceinline__ double finish(const double (&a)[P], const double* __r
   return r;
 }
 
-template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT = false>
+// DISC: the spec has discrete dimensions (table gathers).  Continuous-only specs run an instantiation without that
+// code: the depth-4 tile's schedule (and 2 % of its time) turned out to depend on what else the function contains.
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT = false, bool DISC = true>
 __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_constant__ GramParams prm) {
   using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int TM = L::TM, TN = L::TN;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
   const unsigned lane_bits = (unsigned)(tx & (kExpRepl - 1)) * 8u;
   // discrete B tables: a few dozen doubles gathered 16 times per thread, dimension and tile -- from shared memory
   // when the blob fits (global / L1 gathers held the mixed-input configuration at 0.76 of its roofline)
-  const bool tables_in_smem = prm.tables_len > 0 && prm.tables_len <= kTableStage;
+  const bool tables_in_smem = DISC && prm.tables_len > 0 && prm.tables_len <= kTableStage;
   if (tables_in_smem)
     for (int i = tid; i < prm.tables_len; i += kThreads) sTables[i] = prm.tables[i];
 
@@ -396,6 +398,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
             }
         }
       }
+      if constexpr (DISC) {
       if (tables_in_smem) {
         // discrete dims, tables staged in shared memory: 32-bit shared-window byte offsets (row part and column part
         // + table base formed once per dimension), one IADD + one LDS.64 per entry.  The generic-pointer form below
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(TXD * TYD, MINB) gram_kernel(const __grid_cons
             for (int c = 0; c < RN; ++c) accumulate<P, ALGO>(acc[r][c], __ldg(tbl + ro[r] + co[c]));
         }
       }
+      }  // DISC
       buf ^= 1;
     }
 
@@ -578,8 +582,8 @@ static int encode_output_map(CUtensorMap* tm, double* K, int64_t cols, int64_t r
   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
-template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT = false>
-static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream) {
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT, bool DISC>
+static int launch_gram_impl(GramParams prm, int sms, int device, cudaStream_t stream) {
   using L = SmemLayout<TXD, TYD, RM, RN>;
   constexpr int kThreads = TXD * TYD;
   constexpr int TM = L::TM, TN = L::TN;
@@ -607,7 +611,7 @@ static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream)
       prm.use_tma = 1;
   }
   const size_t smem = L::bytes(prm.use_tma != 0);
-  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO, MINB, YDOT>;
+  auto kern = gram_kernel<P, TXD, TYD, RM, RN, ALGO, MINB, YDOT, DISC>;
   static int cached_per_sm[64][2] = {{0}};  // per instantiation, device and shared-memory footprint
   const int fp = prm.use_tma ? 1 : 0;
   int per_sm = (device >= 0 && device < 64) ? cached_per_sm[device][fp] : 0;
@@ -622,6 +626,12 @@ static int launch_gram(GramParams prm, int sms, int device, cudaStream_t stream)
   kern<<<(unsigned)grid, kThreads, smem, stream>>>(prm);
   OAK_LAUNCHED();
   return 0;
+}
+
+template <int P, int TXD, int TYD, int RM, int RN, int ALGO, int MINB, bool YDOT = false>
+static int launch_gram(const GramParams& prm, int sms, int device, cudaStream_t stream) {
+  if (prm.D > prm.Dc) return launch_gram_impl<P, TXD, TYD, RM, RN, ALGO, MINB, YDOT, true>(prm, sms, device, stream);
+  return launch_gram_impl<P, TXD, TYD, RM, RN, ALGO, MINB, YDOT, false>(prm, sms, device, stream);
 }
 
 template <int P, int TXD, int TYD, int RM, int RN, int MINB>
